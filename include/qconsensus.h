@@ -1,0 +1,189 @@
+/*
+ * qconsensus.h -- C ABI of the B200-native consensus hot path (libqconsensus.so).
+ *
+ * This is the drop-in boundary for the one compute path of shelvick/quoracle that
+ * this repository accelerates: embed the N candidate values of one action
+ * parameter, cosine-compare them, and emit the verdict.  The reference has no FFI
+ * on this path (it is pure Elixir); the seams an Erlang NIF built on this header
+ * plugs into are function-valued options.  Each entry point cites the reference
+ * interface it stands behind (paths relative to the reference checkout):
+ *
+ *   qc_embed_batch        <- `:embedding_fn` 2-arity closure,
+ *                            lib/quoracle/actions/consensus_rules.ex:302-327, and
+ *                            Quoracle.Models.Embeddings.get_embedding/2,
+ *                            lib/quoracle/models/embeddings.ex:41-63 (the provider
+ *                            HTTP call at :277-298 is what the local encoder replaces)
+ *   qc_similarity_batch   <- ConsensusRules.cosine_similarity/2 + the
+ *                            `all i>=1: cos(e_0,e_i) >= threshold` rule,
+ *                            lib/quoracle/actions/consensus_rules.ex:189-210,277-286;
+ *                            Aggregator.cosine_similarity/2,
+ *                            lib/quoracle/consensus/aggregator.ex:335-350
+ *   qc_decide_batch       <- use_embeddings_similarity/5 for every pending decision
+ *                            of the agent tree at once,
+ *                            lib/quoracle/actions/consensus_rules.ex:249-299
+ *                            (per-agent caller: lib/quoracle/agent/consensus_handler.ex:64)
+ *   qc_first_match_batch  <- LessonManager.find_similar_lesson/5,
+ *                            lib/quoracle/agent/lesson_manager.ex:150-173
+ *   qc_chunk_mean         <- Embeddings.average_embeddings/1,
+ *                            lib/quoracle/models/embeddings.ex:371-383
+ *
+ * Conventions
+ *   - Plain C: pointers + sizes, no C++/torch types.  Host entry points take HOST
+ *     memory owned by the caller; `_dev` entry points take DEVICE memory on the
+ *     context's device and a cudaStream_t passed as void* (NULL = context stream).
+ *   - Return value: QC_OK (0) or a negative qc_status.  Nothing is thrown.  Each
+ *     status maps 1:1 to the Elixir error atom the reference uses on this path
+ *     (lib/quoracle/models/embeddings.ex:49-50,184,228-229,300-331,344).
+ *   - A context is bound to ONE device (one process per GPU); calls on one context
+ *     are serialised by the caller.  No globals, no CPU fallback: every entry point
+ *     fails with QC_ERR_NO_DEVICE when no sm_100 device is usable.
+ *   - Zero-norm vectors give cosine 0.0 (never NaN), as both reference cosines do
+ *     (consensus_rules.ex:205-209, aggregator.ex:343-347).
+ */
+#ifndef QCONSENSUS_H
+#define QCONSENSUS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QC_ABI_VERSION 1
+
+typedef enum qc_status {
+  QC_OK = 0,
+  QC_ERR_INVALID_INPUT = -1,      /* :invalid_input          */
+  QC_ERR_NOT_CONFIGURED = -2,     /* :not_configured         (no encoder weights loaded) */
+  QC_ERR_NO_DEVICE = -3,          /* :service_unavailable    (no usable sm_100 GPU)      */
+  QC_ERR_CUDA = -4,               /* :service_unavailable    (CUDA runtime error)        */
+  QC_ERR_OUT_OF_MEMORY = -5,      /* :service_unavailable                                 */
+  QC_ERR_CONTEXT_LENGTH = -6,     /* :context_length_exceeded (T > encoder max_tokens)    */
+  QC_ERR_UNSUPPORTED = -7,        /* :bad_request            (shape outside the ABI)      */
+  QC_ERR_TOKEN_RANGE = -8,        /* :invalid_input          (token id >= vocab)          */
+  QC_ERR_KERNEL_TIMEOUT = -9      /* :service_unavailable    (device barrier watchdog)    */
+} qc_status;
+
+/* Limits of this ABI version. */
+#define QC_MAX_POOL 64            /* N: candidates per decision (BASELINE sweep: 2..64)   */
+#define QC_PAD_TOKEN (-1)         /* padding marker in token_ids                          */
+#define QC_MAX_TOKENS 8192        /* T: token slots per candidate; the reference chunks above
+                                     floor(0.9*8191) tokens, lib/quoracle/models/embeddings/token_chunker.ex:13-15,48-53 */
+
+/*
+ * The local encoder (the reference fixes none -- SURVEY.md section 8(d)):
+ *   h = L2normalise( mean_{t < len} GELU_tanh( E[tok_t] . W ) )
+ * E: bf16 [vocab x dim] row-major, W: bf16 [dim x dim] row-major (in x out),
+ * fp32 accumulation.  dim must be one of 384 / 768 / 1536.
+ * Both arrays are HOST pointers to raw bf16 bit patterns; copied at create time.
+ */
+typedef struct qc_encoder_cfg {
+  int32_t vocab;
+  int32_t dim;
+  const uint16_t* table_bf16; /* [vocab * dim] */
+  const uint16_t* w_bf16;     /* [dim * dim]   */
+} qc_encoder_cfg;
+
+typedef struct qc_ctx qc_ctx;
+
+/* Context --------------------------------------------------------------------------- */
+
+/* enc may be NULL: similarity-only context (embed/decide then return QC_ERR_NOT_CONFIGURED). */
+int qc_ctx_create(qc_ctx** out, int device_id, const qc_encoder_cfg* enc);
+void qc_ctx_destroy(qc_ctx* ctx);
+int qc_ctx_device(const qc_ctx* ctx);
+int qc_ctx_dim(const qc_ctx* ctx);
+/* Blocks until all work queued on the context stream has finished. */
+int qc_ctx_synchronize(qc_ctx* ctx);
+
+/* Pinned host memory (so a NIF can stage binaries without an extra copy). */
+void* qc_host_alloc(size_t bytes);
+void qc_host_free(void* p);
+
+/* Host entry points ----------------------------------------------------------------- */
+
+/*
+ * Full path for B decisions of N candidates each, T token slots per candidate.
+ *   token_ids [B*N*T] int32, QC_PAD_TOKEN beyond lens; lens [B*N] int32 in [0,T];
+ *   thr [B] f32 (the schema threshold of the parameter being merged).
+ * Outputs (each may be NULL):
+ *   out_ref_ok [B]  1 iff for all i>=1: cos(e_0,e_i) >= thr  (reference rule: value_0 wins)
+ *   out_medoid [B]  argmax_i mean_j cos(e_i,e_j), lowest index on ties (north-star vote)
+ *   out_cos    [B*N*N] f32 cosine matrix,  out_emb [B*N*dim] f32 normalised embeddings.
+ */
+int qc_decide_batch(qc_ctx* ctx, const int32_t* token_ids, const int32_t* lens, int B, int N, int T,
+                    const float* thr, int32_t* out_ref_ok, int32_t* out_medoid, float* out_cos,
+                    float* out_emb);
+
+/* Embedding only: R candidate rows -> out_emb [R*dim] f32 (what an `:embedding_fn` returns). */
+int qc_embed_batch(qc_ctx* ctx, const int32_t* token_ids, const int32_t* lens, int R, int T,
+                   float* out_emb);
+
+/* Similarity only, for callers that already hold embeddings: emb [B*N*D] f32 (any D >= 1). */
+int qc_similarity_batch(qc_ctx* ctx, const float* emb, int B, int N, int D, const float* thr,
+                        int32_t* out_ref_ok, int32_t* out_medoid, float* out_cos);
+
+/*
+ * Lesson dedup: for each of Q queries, the FIRST row m of its M candidates with
+ * cos(query, row_m) >= thr[q], else -1.  query [Q*D], rows [Q*M*D] f32.
+ * out_cos (optional) [Q*M].
+ */
+int qc_first_match_batch(qc_ctx* ctx, const float* query, const float* rows, int Q, int M, int D,
+                         const float* thr, int32_t* out_index, float* out_cos);
+
+/* Unweighted, un-normalised element-wise mean of C chunk vectors per group: in [G*C*D] -> out [G*D]. */
+int qc_chunk_mean(qc_ctx* ctx, const float* chunks, int G, int C, int D, float* out_mean);
+
+/* Device entry points (inputs/outputs already resident in HBM) ------------------------ */
+
+int qc_decide_batch_dev(qc_ctx* ctx, const int32_t* d_token_ids, const int32_t* d_lens, int B, int N,
+                        int T, const float* d_thr, int32_t* d_ref_ok, int32_t* d_medoid,
+                        float* d_cos, float* d_emb, void* stream);
+int qc_embed_batch_dev(qc_ctx* ctx, const int32_t* d_token_ids, const int32_t* d_lens, int R, int T,
+                       float* d_emb, void* stream);
+int qc_similarity_batch_dev(qc_ctx* ctx, const float* d_emb, int B, int N, int D, const float* d_thr,
+                            int32_t* d_ref_ok, int32_t* d_medoid, float* d_cos, void* stream);
+
+/* Introspection ---------------------------------------------------------------------- */
+
+const char* qc_strerror(int status);
+/* Elixir atom name the status maps to (without the leading colon). */
+const char* qc_status_atom(int status);
+int qc_abi_version(void);
+
+/* Kernel ids for the counters below. */
+#define QC_K_ENCODE 0     /* K1: token gather + tcgen05 GEMM + GELU + token-sum          */
+#define QC_K_FINALIZE 1   /* K2: block-sum -> mean -> L2 normalise                        */
+#define QC_K_SIMILARITY 2 /* K3: N x N cosine + reference verdict + medoid vote           */
+#define QC_K_FIRST_MATCH 3
+#define QC_K_CHUNK_MEAN 4
+#define QC_K_COUNT 5
+
+/*
+ * Synchronises the context and reports device-side status raised by earlier (asynchronous)
+ * `_dev` calls: QC_ERR_TOKEN_RANGE, QC_ERR_KERNEL_TIMEOUT or QC_OK.  Host entry points call it
+ * themselves.  qc_last_hang returns {flag, barrier tag, block, thread} of the last watchdog hit.
+ */
+int qc_check_status(qc_ctx* ctx);
+int qc_last_hang(const qc_ctx* ctx, int32_t info[4]);
+
+/* Number of kernels of this library launched on the context since the last reset. */
+uint64_t qc_launch_count(const qc_ctx* ctx);
+/*
+ * Per-kernel device timing with CUDA events on the launching stream.  When enabled,
+ * every launch is bracketed by events; qc_kernel_stats synchronises the context and
+ * returns accumulated milliseconds and launch counts per kernel id since the reset.
+ */
+int qc_profile_enable(qc_ctx* ctx, int on);
+int qc_profile_reset(qc_ctx* ctx);
+int qc_kernel_stats(qc_ctx* ctx, double ms[QC_K_COUNT], uint64_t launches[QC_K_COUNT]);
+/* Encoder tiling in use: cta_group (1|2), token block, W stages. Returns QC_OK / NOT_CONFIGURED. */
+int qc_encoder_info(const qc_ctx* ctx, int32_t* cta_group, int32_t* token_block, int32_t* w_stages);
+/* Test hook: force the encoder variant (cta_group 1 or 2) for subsequent launches. */
+int qc_encoder_set_cta_group(qc_ctx* ctx, int cta_group);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCONSENSUS_H */

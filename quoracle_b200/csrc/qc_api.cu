@@ -1,0 +1,701 @@
+// qc_api.cu -- the C ABI declared in include/qconsensus.h: context, workspaces, host<->device
+// staging, kernel sequencing (K1 encode -> K2 finalise -> K3 similarity) and event timing.
+// No CPU compute path exists in this library: without a usable sm_100 device every entry
+// point returns QC_ERR_NO_DEVICE.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/qconsensus.h"
+#include "qc_common.cuh"
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      want = bytes;
+      e = cudaMalloc(&p, want);
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct HostBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost(&p, bytes + bytes / 4);
+    if (e == cudaSuccess) cap = bytes + bytes / 4;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct ProfRec {
+  int kernel;
+  cudaEvent_t start, stop;
+};
+
+}  // namespace
+
+struct qc_ctx {
+  int device = -1;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  // encoder
+  bool has_encoder = false;
+  int dim = 0, vocab = 0, cta_group = 1;
+  uint16_t* d_table = nullptr;
+  uint16_t* d_wt = nullptr;  // W^T [dim(out) x dim(in)] bf16
+  CUtensorMap w_tmap;
+  int32_t* d_err = nullptr;   // int32[8] device status words
+  int32_t hang[4] = {};
+  // workspaces
+  DevBuf part, emb, tok, lens, thr, cosm, refok, medoid, q, rows, idx;
+  HostBuf h_in, h_out;
+  // counters / profiling
+  uint64_t launches = 0;
+  bool profiling = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  double ms[QC_K_COUNT] = {};
+  uint64_t nl[QC_K_COUNT] = {};
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int cuda_status(cudaError_t e) {
+  if (e == cudaSuccess) return QC_OK;
+  if (e == cudaErrorMemoryAllocation) return QC_ERR_OUT_OF_MEMORY;
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) return QC_ERR_NO_DEVICE;
+  return QC_ERR_CUDA;
+}
+
+#define QC_CUDA(expr)                                  \
+  do {                                                 \
+    cudaError_t _e = (expr);                           \
+    if (_e != cudaSuccess) {                           \
+      cudaGetLastError();                              \
+      return cuda_status(_e);                          \
+    }                                                  \
+  } while (0)
+
+cudaEvent_t get_event(qc_ctx* c) {
+  if (!c->pool.empty()) {
+    cudaEvent_t e = c->pool.back();
+    c->pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct KernelScope {
+  qc_ctx* c;
+  int k;
+  cudaStream_t s;
+  ProfRec r{};
+  KernelScope(qc_ctx* c_, int k_, cudaStream_t s_) : c(c_), k(k_), s(s_) {
+    c->launches++;
+    if (c->profiling) {
+      r.kernel = k;
+      r.start = get_event(c);
+      r.stop = get_event(c);
+      cudaEventRecord(r.start, s);
+    }
+  }
+  ~KernelScope() {
+    if (c->profiling) {
+      cudaEventRecord(r.stop, s);
+      c->recs.push_back(r);
+    }
+  }
+};
+
+void drain_profile(qc_ctx* c) {
+  for (ProfRec& r : c->recs) {
+    cudaEventSynchronize(r.stop);
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.start, r.stop) == cudaSuccess) {
+      c->ms[r.kernel] += t;
+      c->nl[r.kernel] += 1;
+    }
+    c->pool.push_back(r.start);
+    c->pool.push_back(r.stop);
+  }
+  c->recs.clear();
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_w_tmap(qc_ctx* c) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) return QC_ERR_CUDA;
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(c->dim), static_cast<cuuint64_t>(c->dim)};  // {k, feature}
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(c->dim) * 2};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&c->w_tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->d_wt, gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? QC_OK : QC_ERR_CUDA;
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Stage `bytes` of caller host memory to device: direct when the caller's buffer is pinned,
+// through the context's pinned staging area otherwise.  `stage_off` advances through h_in.
+int h2d(qc_ctx* c, void* dst, const void* src, size_t bytes, size_t* stage_off) {
+  if (bytes == 0) return QC_OK;
+  if (is_pinned(src)) {
+    QC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return QC_OK;
+  }
+  char* st = static_cast<char*>(c->h_in.p) + *stage_off;
+  memcpy(st, src, bytes);
+  *stage_off += (bytes + 255) & ~size_t(255);
+  QC_CUDA(cudaMemcpyAsync(dst, st, bytes, cudaMemcpyHostToDevice, c->stream));
+  return QC_OK;
+}
+
+struct PendingOut {
+  void* user;
+  const void* staged;
+  size_t bytes;
+};
+
+int d2h(qc_ctx* c, void* user, const void* dsrc, size_t bytes, size_t* stage_off, std::vector<PendingOut>* pend) {
+  if (bytes == 0 || user == nullptr) return QC_OK;
+  if (is_pinned(user)) {
+    QC_CUDA(cudaMemcpyAsync(user, dsrc, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return QC_OK;
+  }
+  char* st = static_cast<char*>(c->h_out.p) + *stage_off;
+  *stage_off += (bytes + 255) & ~size_t(255);
+  QC_CUDA(cudaMemcpyAsync(st, dsrc, bytes, cudaMemcpyDeviceToHost, c->stream));
+  pend->push_back({user, st, bytes});
+  return QC_OK;
+}
+
+size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
+
+int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, int T, float* d_emb, cudaStream_t s) {
+  const int TB = qc::encoder_token_block(c->dim);
+  const int bpc = (T + TB - 1) / TB;
+  QC_CUDA(c->part.ensure(static_cast<size_t>(R) * bpc * c->dim * sizeof(float)));
+  {
+    KernelScope ks(c, QC_K_ENCODE, s);
+    qc::EncoderLaunch a;
+    a.w_tmap = &c->w_tmap;
+    a.table = c->d_table;
+    a.token_ids = d_tok;
+    a.lens = d_lens;
+    a.part = static_cast<float*>(c->part.p);
+    a.err_flag = c->d_err;
+    a.R = R;
+    a.T = T;
+    a.dim = c->dim;
+    a.vocab = c->vocab;
+    a.cta_group = c->cta_group;
+    a.num_sms = c->num_sms;
+    a.stream = s;
+    QC_CUDA(qc::launch_encode(a));
+  }
+  {
+    KernelScope ks(c, QC_K_FINALIZE, s);
+    QC_CUDA(qc::launch_finalize(static_cast<const float*>(c->part.p), d_lens, d_emb, R, bpc, TB, c->dim, s));
+  }
+  return QC_OK;
+}
+
+// Synchronises the context stream and reads the device status words written by K1:
+// [0..3] barrier watchdog record (a protocol bug ended the kernel early), [4] token id out of range.
+int check_token_flag(qc_ctx* c) {
+  int32_t flags[8] = {};
+  QC_CUDA(cudaMemcpyAsync(flags, c->d_err, sizeof(flags), cudaMemcpyDeviceToHost, c->stream));
+  QC_CUDA(cudaStreamSynchronize(c->stream));
+  if (flags[0] != 0 || flags[4] != 0) {
+    QC_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(flags), c->stream));
+    QC_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  if (flags[0] != 0) {
+    for (int i = 0; i < 4; ++i) c->hang[i] = flags[i];
+    return QC_ERR_KERNEL_TIMEOUT;
+  }
+  if (flags[4] != 0) return QC_ERR_TOKEN_RANGE;
+  return QC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qc_abi_version(void) { return QC_ABI_VERSION; }
+
+const char* qc_strerror(int status) {
+  switch (status) {
+    case QC_OK: return "ok";
+    case QC_ERR_INVALID_INPUT: return "invalid input";
+    case QC_ERR_NOT_CONFIGURED: return "encoder not configured";
+    case QC_ERR_NO_DEVICE: return "no usable sm_100 CUDA device";
+    case QC_ERR_CUDA: return "CUDA runtime error";
+    case QC_ERR_OUT_OF_MEMORY: return "out of device or pinned memory";
+    case QC_ERR_CONTEXT_LENGTH: return "candidate longer than QC_MAX_TOKENS";
+    case QC_ERR_UNSUPPORTED: return "shape not supported by this ABI version";
+    case QC_ERR_TOKEN_RANGE: return "token id outside the encoder vocabulary";
+    case QC_ERR_KERNEL_TIMEOUT: return "device barrier watchdog fired (see qc_last_hang)";
+    default: return "unknown status";
+  }
+}
+
+const char* qc_status_atom(int status) {
+  switch (status) {
+    case QC_OK: return "ok";
+    case QC_ERR_INVALID_INPUT: return "invalid_input";
+    case QC_ERR_NOT_CONFIGURED: return "not_configured";
+    case QC_ERR_NO_DEVICE: return "service_unavailable";
+    case QC_ERR_CUDA: return "service_unavailable";
+    case QC_ERR_OUT_OF_MEMORY: return "service_unavailable";
+    case QC_ERR_CONTEXT_LENGTH: return "context_length_exceeded";
+    case QC_ERR_UNSUPPORTED: return "bad_request";
+    case QC_ERR_TOKEN_RANGE: return "invalid_input";
+    case QC_ERR_KERNEL_TIMEOUT: return "service_unavailable";
+    default: return "invalid_response";
+  }
+}
+
+void* qc_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void qc_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int qc_ctx_create(qc_ctx** out, int device_id, const qc_encoder_cfg* enc) {
+  if (out == nullptr) return QC_ERR_INVALID_INPUT;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return QC_ERR_NO_DEVICE;
+  }
+  if (device_id < 0 || device_id >= ndev) return QC_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  QC_CUDA(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major != 10) return QC_ERR_NO_DEVICE;  // kernels are sm_100a only
+  if (enc != nullptr) {
+    if (enc->table_bf16 == nullptr || enc->w_bf16 == nullptr || enc->vocab <= 0) return QC_ERR_INVALID_INPUT;
+    if (!qc::encoder_supports(enc->dim, 1)) return QC_ERR_UNSUPPORTED;
+  }
+  qc_ctx* c = new (std::nothrow) qc_ctx();
+  if (c == nullptr) return QC_ERR_OUT_OF_MEMORY;
+  c->device = device_id;
+  c->num_sms = prop.multiProcessorCount;
+  DeviceGuard g(device_id);
+  int st = QC_OK;
+  do {
+    if ((st = cuda_status(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking))) != QC_OK) break;
+    if ((st = cuda_status(cudaMalloc(&c->d_err, 8 * sizeof(int32_t)))) != QC_OK) break;
+    if ((st = cuda_status(cudaMemset(c->d_err, 0, 8 * sizeof(int32_t)))) != QC_OK) break;
+    if (enc != nullptr) {
+      c->dim = enc->dim;
+      c->vocab = enc->vocab;
+      const size_t tb = static_cast<size_t>(enc->vocab) * enc->dim * 2;
+      const size_t wb = static_cast<size_t>(enc->dim) * enc->dim * 2;
+      if ((st = cuda_status(cudaMalloc(&c->d_table, tb))) != QC_OK) break;
+      if ((st = cuda_status(cudaMalloc(&c->d_wt, wb))) != QC_OK) break;
+      if ((st = cuda_status(cudaMemcpy(c->d_table, enc->table_bf16, tb, cudaMemcpyHostToDevice))) != QC_OK) break;
+      std::vector<uint16_t> wt(static_cast<size_t>(enc->dim) * enc->dim);
+      for (int k = 0; k < enc->dim; ++k)
+        for (int d = 0; d < enc->dim; ++d) wt[static_cast<size_t>(d) * enc->dim + k] = enc->w_bf16[static_cast<size_t>(k) * enc->dim + d];
+      if ((st = cuda_status(cudaMemcpy(c->d_wt, wt.data(), wb, cudaMemcpyHostToDevice))) != QC_OK) break;
+      if ((st = make_w_tmap(c)) != QC_OK) break;
+      c->has_encoder = true;
+      c->cta_group = 1;
+      const char* cg = getenv("QC_CTA_GROUP");
+      if (cg != nullptr && cg[0] == '2' && qc::encoder_supports(c->dim, 2)) c->cta_group = 2;
+    }
+  } while (false);
+  if (st != QC_OK) {
+    qc_ctx_destroy(c);
+    return st;
+  }
+  *out = c;
+  return QC_OK;
+}
+
+void qc_ctx_destroy(qc_ctx* c) {
+  if (c == nullptr) return;
+  DeviceGuard g(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  drain_profile(c);
+  for (cudaEvent_t e : c->pool) cudaEventDestroy(e);
+  c->part.release();
+  c->emb.release();
+  c->tok.release();
+  c->lens.release();
+  c->thr.release();
+  c->cosm.release();
+  c->refok.release();
+  c->medoid.release();
+  c->q.release();
+  c->rows.release();
+  c->idx.release();
+  c->h_in.release();
+  c->h_out.release();
+  if (c->d_table) cudaFree(c->d_table);
+  if (c->d_wt) cudaFree(c->d_wt);
+  if (c->d_err) cudaFree(c->d_err);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int qc_ctx_device(const qc_ctx* c) { return c ? c->device : -1; }
+int qc_ctx_dim(const qc_ctx* c) { return (c && c->has_encoder) ? c->dim : 0; }
+
+int qc_ctx_synchronize(qc_ctx* c) {
+  if (c == nullptr) return QC_ERR_INVALID_INPUT;
+  DeviceGuard g(c->device);
+  QC_CUDA(cudaStreamSynchronize(c->stream));
+  return QC_OK;
+}
+
+uint64_t qc_launch_count(const qc_ctx* c) { return c ? c->launches : 0; }
+
+int qc_check_status(qc_ctx* c) {
+  if (c == nullptr) return QC_ERR_INVALID_INPUT;
+  DeviceGuard g(c->device);
+  return check_token_flag(c);
+}
+
+int qc_last_hang(const qc_ctx* c, int32_t info[4]) {
+  if (c == nullptr || info == nullptr) return QC_ERR_INVALID_INPUT;
+  for (int i = 0; i < 4; ++i) info[i] = c->hang[i];
+  return QC_OK;
+}
+
+int qc_profile_enable(qc_ctx* c, int on) {
+  if (c == nullptr) return QC_ERR_INVALID_INPUT;
+  DeviceGuard g(c->device);
+  if (!on) drain_profile(c);
+  c->profiling = on != 0;
+  return QC_OK;
+}
+
+int qc_profile_reset(qc_ctx* c) {
+  if (c == nullptr) return QC_ERR_INVALID_INPUT;
+  DeviceGuard g(c->device);
+  drain_profile(c);
+  for (int k = 0; k < QC_K_COUNT; ++k) {
+    c->ms[k] = 0.0;
+    c->nl[k] = 0;
+  }
+  c->launches = 0;
+  return QC_OK;
+}
+
+int qc_kernel_stats(qc_ctx* c, double ms[QC_K_COUNT], uint64_t launches[QC_K_COUNT]) {
+  if (c == nullptr) return QC_ERR_INVALID_INPUT;
+  DeviceGuard g(c->device);
+  drain_profile(c);
+  for (int k = 0; k < QC_K_COUNT; ++k) {
+    if (ms) ms[k] = c->ms[k];
+    if (launches) launches[k] = c->nl[k];
+  }
+  return QC_OK;
+}
+
+int qc_encoder_info(const qc_ctx* c, int32_t* cta_group, int32_t* token_block, int32_t* w_stages) {
+  if (c == nullptr) return QC_ERR_INVALID_INPUT;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  if (cta_group) *cta_group = c->cta_group;
+  if (token_block) *token_block = qc::encoder_token_block(c->dim);
+  if (w_stages) *w_stages = qc::encoder_w_stages(c->dim, c->cta_group);
+  return QC_OK;
+}
+
+int qc_encoder_set_cta_group(qc_ctx* c, int cta_group) {
+  if (c == nullptr) return QC_ERR_INVALID_INPUT;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  if (!qc::encoder_supports(c->dim, cta_group)) return QC_ERR_UNSUPPORTED;
+  c->cta_group = cta_group;
+  return QC_OK;
+}
+
+// ---- device entry points ---------------------------------------------------------------
+
+int qc_embed_batch_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, int T, float* d_emb,
+                       void* stream) {
+  if (c == nullptr || d_tok == nullptr || d_lens == nullptr || d_emb == nullptr || R < 0 || T < 1)
+    return QC_ERR_INVALID_INPUT;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  if (T > QC_MAX_TOKENS) return QC_ERR_CONTEXT_LENGTH;
+  if (R == 0) return QC_OK;
+  DeviceGuard g(c->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  return encode_dev(c, d_tok, d_lens, R, T, d_emb, s);
+}
+
+int qc_similarity_batch_dev(qc_ctx* c, const float* d_emb, int B, int N, int D, const float* d_thr,
+                            int32_t* d_ref_ok, int32_t* d_medoid, float* d_cos, void* stream) {
+  if (c == nullptr || d_emb == nullptr || d_thr == nullptr || B < 0 || D < 1) return QC_ERR_INVALID_INPUT;
+  if (N < 1 || N > QC_MAX_POOL) return QC_ERR_UNSUPPORTED;
+  if (B == 0) return QC_OK;
+  DeviceGuard g(c->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  KernelScope ks(c, QC_K_SIMILARITY, s);
+  QC_CUDA(qc::launch_similarity(d_emb, B, N, D, d_thr, d_ref_ok, d_medoid, d_cos, c->num_sms, s));
+  return QC_OK;
+}
+
+int qc_decide_batch_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int B, int N, int T,
+                        const float* d_thr, int32_t* d_ref_ok, int32_t* d_medoid, float* d_cos, float* d_emb,
+                        void* stream) {
+  if (c == nullptr || d_tok == nullptr || d_lens == nullptr || d_thr == nullptr || B < 0 || T < 1)
+    return QC_ERR_INVALID_INPUT;
+  if (N < 1 || N > QC_MAX_POOL) return QC_ERR_UNSUPPORTED;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  if (T > QC_MAX_TOKENS) return QC_ERR_CONTEXT_LENGTH;
+  if (B == 0) return QC_OK;
+  DeviceGuard g(c->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  const int R = B * N;
+  float* emb = d_emb;
+  if (emb == nullptr) {
+    QC_CUDA(c->emb.ensure(static_cast<size_t>(R) * c->dim * sizeof(float)));
+    emb = static_cast<float*>(c->emb.p);
+  }
+  int st = encode_dev(c, d_tok, d_lens, R, T, emb, s);
+  if (st != QC_OK) return st;
+  return qc_similarity_batch_dev(c, emb, B, N, c->dim, d_thr, d_ref_ok, d_medoid, d_cos, s);
+}
+
+// ---- host entry points -------------------------------------------------------------------
+
+int qc_embed_batch(qc_ctx* c, const int32_t* token_ids, const int32_t* lens, int R, int T, float* out_emb) {
+  if (c == nullptr || token_ids == nullptr || lens == nullptr || out_emb == nullptr || R < 0 || T < 1)
+    return QC_ERR_INVALID_INPUT;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  if (T > QC_MAX_TOKENS) return QC_ERR_CONTEXT_LENGTH;
+  if (R == 0) return QC_OK;
+  for (int r = 0; r < R; ++r)
+    if (lens[r] < 0 || lens[r] > T) return QC_ERR_INVALID_INPUT;
+  DeviceGuard g(c->device);
+  const size_t tokb = static_cast<size_t>(R) * T * 4, lenb = static_cast<size_t>(R) * 4;
+  const size_t embb = static_cast<size_t>(R) * c->dim * 4;
+  QC_CUDA(c->tok.ensure(tokb));
+  QC_CUDA(c->lens.ensure(lenb));
+  QC_CUDA(c->emb.ensure(embb));
+  QC_CUDA(c->h_in.ensure(pad256(tokb) + pad256(lenb)));
+  QC_CUDA(c->h_out.ensure(pad256(embb)));
+  size_t off = 0;
+  int st;
+  if ((st = h2d(c, c->tok.p, token_ids, tokb, &off)) != QC_OK) return st;
+  if ((st = h2d(c, c->lens.p, lens, lenb, &off)) != QC_OK) return st;
+  st = encode_dev(c, static_cast<int32_t*>(c->tok.p), static_cast<int32_t*>(c->lens.p), R, T,
+                  static_cast<float*>(c->emb.p), c->stream);
+  if (st != QC_OK) return st;
+  std::vector<PendingOut> pend;
+  size_t ooff = 0;
+  if ((st = d2h(c, out_emb, c->emb.p, embb, &ooff, &pend)) != QC_OK) return st;
+  if ((st = check_token_flag(c)) != QC_OK) return st;
+  for (const PendingOut& p : pend) memcpy(p.user, p.staged, p.bytes);
+  return QC_OK;
+}
+
+int qc_similarity_batch(qc_ctx* c, const float* emb, int B, int N, int D, const float* thr, int32_t* out_ref_ok,
+                        int32_t* out_medoid, float* out_cos) {
+  if (c == nullptr || emb == nullptr || thr == nullptr || B < 0 || D < 1) return QC_ERR_INVALID_INPUT;
+  if (N < 1 || N > QC_MAX_POOL) return QC_ERR_UNSUPPORTED;
+  if (B == 0) return QC_OK;
+  DeviceGuard g(c->device);
+  const size_t embb = static_cast<size_t>(B) * N * D * 4, thrb = static_cast<size_t>(B) * 4;
+  const size_t cosb = static_cast<size_t>(B) * N * N * 4, ib = static_cast<size_t>(B) * 4;
+  QC_CUDA(c->emb.ensure(embb));
+  QC_CUDA(c->thr.ensure(thrb));
+  QC_CUDA(c->refok.ensure(ib));
+  QC_CUDA(c->medoid.ensure(ib));
+  if (out_cos) QC_CUDA(c->cosm.ensure(cosb));
+  QC_CUDA(c->h_in.ensure(pad256(embb) + pad256(thrb)));
+  QC_CUDA(c->h_out.ensure(pad256(cosb) + 2 * pad256(ib)));
+  size_t off = 0;
+  int st;
+  if ((st = h2d(c, c->emb.p, emb, embb, &off)) != QC_OK) return st;
+  if ((st = h2d(c, c->thr.p, thr, thrb, &off)) != QC_OK) return st;
+  st = qc_similarity_batch_dev(c, static_cast<float*>(c->emb.p), B, N, D, static_cast<float*>(c->thr.p),
+                               static_cast<int32_t*>(c->refok.p), static_cast<int32_t*>(c->medoid.p),
+                               out_cos ? static_cast<float*>(c->cosm.p) : nullptr, c->stream);
+  if (st != QC_OK) return st;
+  std::vector<PendingOut> pend;
+  size_t ooff = 0;
+  if ((st = d2h(c, out_ref_ok, c->refok.p, ib, &ooff, &pend)) != QC_OK) return st;
+  if ((st = d2h(c, out_medoid, c->medoid.p, ib, &ooff, &pend)) != QC_OK) return st;
+  if ((st = d2h(c, out_cos, c->cosm.p, cosb, &ooff, &pend)) != QC_OK) return st;
+  QC_CUDA(cudaStreamSynchronize(c->stream));
+  for (const PendingOut& p : pend) memcpy(p.user, p.staged, p.bytes);
+  return QC_OK;
+}
+
+int qc_decide_batch(qc_ctx* c, const int32_t* token_ids, const int32_t* lens, int B, int N, int T, const float* thr,
+                    int32_t* out_ref_ok, int32_t* out_medoid, float* out_cos, float* out_emb) {
+  if (c == nullptr || token_ids == nullptr || lens == nullptr || thr == nullptr || B < 0 || T < 1)
+    return QC_ERR_INVALID_INPUT;
+  if (N < 1 || N > QC_MAX_POOL) return QC_ERR_UNSUPPORTED;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  if (T > QC_MAX_TOKENS) return QC_ERR_CONTEXT_LENGTH;
+  if (B == 0) return QC_OK;
+  const int R = B * N;
+  for (int r = 0; r < R; ++r)
+    if (lens[r] < 0 || lens[r] > T) return QC_ERR_INVALID_INPUT;
+  DeviceGuard g(c->device);
+  const size_t tokb = static_cast<size_t>(R) * T * 4, lenb = static_cast<size_t>(R) * 4;
+  const size_t thrb = static_cast<size_t>(B) * 4, ib = static_cast<size_t>(B) * 4;
+  const size_t embb = static_cast<size_t>(R) * c->dim * 4, cosb = static_cast<size_t>(B) * N * N * 4;
+  QC_CUDA(c->tok.ensure(tokb));
+  QC_CUDA(c->lens.ensure(lenb));
+  QC_CUDA(c->thr.ensure(thrb));
+  QC_CUDA(c->emb.ensure(embb));
+  QC_CUDA(c->refok.ensure(ib));
+  QC_CUDA(c->medoid.ensure(ib));
+  if (out_cos) QC_CUDA(c->cosm.ensure(cosb));
+  QC_CUDA(c->h_in.ensure(pad256(tokb) + pad256(lenb) + pad256(thrb)));
+  QC_CUDA(c->h_out.ensure(2 * pad256(ib) + pad256(cosb) + pad256(embb)));
+  size_t off = 0;
+  int st;
+  if ((st = h2d(c, c->tok.p, token_ids, tokb, &off)) != QC_OK) return st;
+  if ((st = h2d(c, c->lens.p, lens, lenb, &off)) != QC_OK) return st;
+  if ((st = h2d(c, c->thr.p, thr, thrb, &off)) != QC_OK) return st;
+  st = qc_decide_batch_dev(c, static_cast<int32_t*>(c->tok.p), static_cast<int32_t*>(c->lens.p), B, N, T,
+                           static_cast<float*>(c->thr.p), static_cast<int32_t*>(c->refok.p),
+                           static_cast<int32_t*>(c->medoid.p), out_cos ? static_cast<float*>(c->cosm.p) : nullptr,
+                           static_cast<float*>(c->emb.p), c->stream);
+  if (st != QC_OK) return st;
+  std::vector<PendingOut> pend;
+  size_t ooff = 0;
+  if ((st = d2h(c, out_ref_ok, c->refok.p, ib, &ooff, &pend)) != QC_OK) return st;
+  if ((st = d2h(c, out_medoid, c->medoid.p, ib, &ooff, &pend)) != QC_OK) return st;
+  if ((st = d2h(c, out_cos, c->cosm.p, cosb, &ooff, &pend)) != QC_OK) return st;
+  if ((st = d2h(c, out_emb, c->emb.p, embb, &ooff, &pend)) != QC_OK) return st;
+  if ((st = check_token_flag(c)) != QC_OK) return st;
+  for (const PendingOut& p : pend) memcpy(p.user, p.staged, p.bytes);
+  return QC_OK;
+}
+
+int qc_first_match_batch(qc_ctx* c, const float* query, const float* rows, int Q, int M, int D, const float* thr,
+                         int32_t* out_index, float* out_cos) {
+  if (c == nullptr || query == nullptr || thr == nullptr || out_index == nullptr || Q < 0 || M < 0 || D < 1)
+    return QC_ERR_INVALID_INPUT;
+  if (M > 0 && rows == nullptr) return QC_ERR_INVALID_INPUT;
+  if (Q == 0) return QC_OK;
+  DeviceGuard g(c->device);
+  const size_t qb = static_cast<size_t>(Q) * D * 4, rb = static_cast<size_t>(Q) * M * D * 4;
+  const size_t tb = static_cast<size_t>(Q) * 4, cb = static_cast<size_t>(Q) * M * 4;
+  QC_CUDA(c->q.ensure(qb));
+  QC_CUDA(c->rows.ensure(rb ? rb : 4));
+  QC_CUDA(c->thr.ensure(tb));
+  QC_CUDA(c->idx.ensure(tb));
+  if (out_cos) QC_CUDA(c->cosm.ensure(cb ? cb : 4));
+  QC_CUDA(c->h_in.ensure(pad256(qb) + pad256(rb) + pad256(tb)));
+  QC_CUDA(c->h_out.ensure(pad256(tb) + pad256(cb)));
+  size_t off = 0;
+  int st;
+  if ((st = h2d(c, c->q.p, query, qb, &off)) != QC_OK) return st;
+  if ((st = h2d(c, c->rows.p, rows, rb, &off)) != QC_OK) return st;
+  if ((st = h2d(c, c->thr.p, thr, tb, &off)) != QC_OK) return st;
+  {
+    KernelScope ks(c, QC_K_FIRST_MATCH, c->stream);
+    QC_CUDA(qc::launch_first_match(static_cast<float*>(c->q.p), static_cast<float*>(c->rows.p), Q, M, D,
+                                   static_cast<float*>(c->thr.p), static_cast<int32_t*>(c->idx.p),
+                                   out_cos ? static_cast<float*>(c->cosm.p) : nullptr, c->stream));
+  }
+  std::vector<PendingOut> pend;
+  size_t ooff = 0;
+  if ((st = d2h(c, out_index, c->idx.p, tb, &ooff, &pend)) != QC_OK) return st;
+  if ((st = d2h(c, out_cos, c->cosm.p, cb, &ooff, &pend)) != QC_OK) return st;
+  QC_CUDA(cudaStreamSynchronize(c->stream));
+  for (const PendingOut& p : pend) memcpy(p.user, p.staged, p.bytes);
+  return QC_OK;
+}
+
+int qc_chunk_mean(qc_ctx* c, const float* chunks, int G, int C, int D, float* out_mean) {
+  if (c == nullptr || chunks == nullptr || out_mean == nullptr || G < 0 || C < 1 || D < 1) return QC_ERR_INVALID_INPUT;
+  if (G == 0) return QC_OK;
+  DeviceGuard g(c->device);
+  const size_t ib = static_cast<size_t>(G) * C * D * 4, ob = static_cast<size_t>(G) * D * 4;
+  QC_CUDA(c->rows.ensure(ib));
+  QC_CUDA(c->q.ensure(ob));
+  QC_CUDA(c->h_in.ensure(pad256(ib)));
+  QC_CUDA(c->h_out.ensure(pad256(ob)));
+  size_t off = 0;
+  int st;
+  if ((st = h2d(c, c->rows.p, chunks, ib, &off)) != QC_OK) return st;
+  {
+    KernelScope ks(c, QC_K_CHUNK_MEAN, c->stream);
+    QC_CUDA(qc::launch_chunk_mean(static_cast<float*>(c->rows.p), G, C, D, static_cast<float*>(c->q.p), c->stream));
+  }
+  std::vector<PendingOut> pend;
+  size_t ooff = 0;
+  if ((st = d2h(c, out_mean, c->q.p, ob, &ooff, &pend)) != QC_OK) return st;
+  QC_CUDA(cudaStreamSynchronize(c->stream));
+  for (const PendingOut& p : pend) memcpy(p.user, p.staged, p.bytes);
+  return QC_OK;
+}
+
+}  // extern "C"

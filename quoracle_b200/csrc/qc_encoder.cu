@@ -1,0 +1,391 @@
+// qc_encoder.cu -- K1: token gather + tcgen05 GEMM + GELU + per-block token sum  (sm_100a)
+//
+// Computes, for every candidate row r and every block j of TB consecutive token slots,
+//   part[r, j, d] = sum_{t in block j, t < len[r]} GELU_tanh( sum_k E[tok[r,t], k] * W[k, d] )
+// K2 (qc_finalize.cu) adds the blocks in a fixed order, divides by len and L2-normalises.
+// This is the local stand-in for the provider call behind Embeddings.get_embedding/2
+// (reference lib/quoracle/models/embeddings.ex:277-298); the encoder definition is this
+// build's, the reference fixes none.
+//
+// Tiling (DESIGN.md "K1"): the GEMM is issued TRANSPOSED -- M = output features (TMEM lanes),
+// N = tokens (TMEM columns) -- so that the token mean is a per-thread sum over the columns a
+// thread reads back from TMEM, with no cross-lane reduction.  Per CTA:
+//   * the TB x D bf16 token rows of one block are gathered from the embedding table with
+//     cp.async (16 B chunks, written in the 128-byte-swizzled K-major layout tcgen05 expects)
+//     and stay RESIDENT in shared memory: KB = D/64 k-blocks of TB x 128 B;
+//   * W^T tiles (128 features x 64 k, 16 KB) stream through a W_STAGES-deep TMA ring;
+//   * D/128 (or D/256 for a CTA pair) feature tiles reuse the resident tokens; the k-block
+//     buffers are released one by one during the last feature tile so the next block's gather
+//     overlaps the tail of this one;
+//   * accumulators live in TMEM (2 stages), read back by 4 epilogue warps with tcgen05.ld.
+// CG == 2 runs a CTA pair (cta_group::2): M = 256 features split across the pair, N = 2*TB
+// tokens (each CTA's resident block is half of the B operand), one MMA issuer in the leader.
+//
+// Warp roles (320 threads): 0-3 epilogue (TMEM lane quadrant = warp id), 4-7 gather,
+// 8 W-tile TMA producer, 9 MMA issuer + TMEM allocator.
+#include "qc_common.cuh"
+#include "ptx.cuh"
+
+namespace qc {
+
+using namespace ptx;
+
+template <int D_, int TB_, int CG_>
+struct EncTraits {
+  static constexpr int D = D_;
+  static constexpr int TB = TB_;
+  static constexpr int CG = CG_;
+  static constexpr int BK = 64;                   // bf16 elements per 128-byte swizzle row
+  static constexpr int KB = D / BK;               // resident k-blocks
+  static constexpr int MT = 128 * CG;             // features per MMA tile over the CTA group
+  static constexpr int NFT = D / MT;              // feature tiles
+  static constexpr int UMMA_N = TB * CG;          // tokens per MMA tile
+  static constexpr int TOK_KB_BYTES = TB * 128;
+  static constexpr int TOK_BYTES = KB * TOK_KB_BYTES;
+  static constexpr int W_STAGE_BYTES = 128 * 128;
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int SMEM_MAX = 232448;         // 227 KB opt-in limit
+  static constexpr int W_STAGES_FIT = (SMEM_MAX - 1024 - BAR_BYTES - TOK_BYTES) / W_STAGE_BYTES;
+  static constexpr int W_STAGES = W_STAGES_FIT > 8 ? 8 : W_STAGES_FIT;
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS = ACC_STAGES * UMMA_N;  // 128 / 256 / 512: powers of two >= 32
+  static constexpr int SMEM_BYTES = 1024 + TOK_BYTES + W_STAGES * W_STAGE_BYTES + BAR_BYTES;
+  static constexpr int GATHER_LAG = 4;            // cp.async groups in flight per gather thread
+  static_assert(D % MT == 0, "feature tiles must cover D");
+  static_assert(D % BK == 0, "k-blocks must cover D");
+  static_assert(TB % 32 == 0 && UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid UMMA N");
+  static_assert(W_STAGES >= 2, "need at least two W stages");
+  static_assert(KB > GATHER_LAG, "gather lag must be below the k-block count");
+  static_assert((2 * W_STAGES + 2 * KB + 2 * ACC_STAGES) * 8 + 8 <= BAR_BYTES, "barrier region too small");
+};
+
+constexpr int kEncThreads = 320;
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+  // 0.5 x (1 + tanh( sqrt(2/pi) (x + 0.044715 x^3) ))
+  const float x2 = x * x;
+  const float inner = x * fmaf(0.0356774081f, x2, 0.7978845608f);
+  const float t = tanh_approx(inner);
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+
+__device__ __forceinline__ int block_valid(const int32_t* __restrict__ lens, int blk, int nblocks, int bpc, int TB) {
+  if (blk >= nblocks) return 0;
+  const int cand = blk / bpc;
+  const int j = blk - cand * bpc;
+  int v = lens[cand] - j * TB;
+  v = v < 0 ? 0 : v;
+  return v > TB ? TB : v;
+}
+
+template <class Tr>
+__global__ void __launch_bounds__(kEncThreads, 1)
+qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D x D] bf16, box 64 x 128, SW128
+                 const uint16_t* __restrict__ table,                   // E [vocab x D] bf16
+                 const int32_t* __restrict__ token_ids,                // [R x T]
+                 const int32_t* __restrict__ lens,                     // [R]
+                 float* __restrict__ part,                             // [R x bpc x D]
+                 int32_t* __restrict__ dbg,                            // [0..3] watchdog, [4] token-range flag
+                 int R, int T, int bpc, int vocab) {
+  constexpr int D = Tr::D, TB = Tr::TB, CG = Tr::CG, KB = Tr::KB, NFT = Tr::NFT;
+  constexpr int UMMA_N = Tr::UMMA_N, WS = Tr::W_STAGES, LAG = Tr::GATHER_LAG;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tok_smem = smem;                                  // KB x (TB x 128 B), 1024-aligned each
+  uint8_t* w_smem = smem + Tr::TOK_BYTES;                    // WS x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + WS * Tr::W_STAGE_BYTES);
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = w_full + WS;
+  uint64_t* tok_full = w_empty + WS;
+  uint64_t* tok_empty = tok_full + KB;
+  uint64_t* acc_full = tok_empty + KB;
+  uint64_t* acc_empty = acc_full + Tr::ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + Tr::ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;   // position in the CTA pair
+  const bool leader = (rank == 0);
+  const int group = blockIdx.x / CG;                           // CTA (pair) index
+  const int ngroups = gridDim.x / CG;
+  const int nblocks = R * bpc;
+  const int nitems = (nblocks + CG - 1) / CG;                  // work items: CG blocks each
+
+  // ---- one-time setup -----------------------------------------------------------------
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&w_tmap);
+    for (int s = 0; s < WS; ++s) {
+      mbar_init(&w_full[s], 1);   // leader's producer arrive.expect_tx (TMA bytes of the whole group)
+      mbar_init(&w_empty[s], 1);  // tcgen05.commit
+    }
+    for (int k = 0; k < KB; ++k) {
+      mbar_init(&tok_full[k], 4 * CG);  // one arrival per gather warp of each CTA in the group
+      mbar_init(&tok_empty[k], 1);      // tcgen05.commit
+    }
+    for (int a = 0; a < Tr::ACC_STAGES; ++a) {
+      mbar_init(&acc_full[a], 1);        // tcgen05.commit
+      mbar_init(&acc_empty[a], 4 * CG);  // one arrival per epilogue warp of each CTA in the group
+    }
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 9) {
+    tmem_alloc<CG>(tmem_slot, Tr::TMEM_COLS);
+  }
+  tcgen05_fence_before();
+  if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== epilogue: TMEM -> GELU -> token sum -> part ======================
+    const int row = warp * 32 + lane;                         // feature row inside this CTA's tile half
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    uint32_t acc_iter = 0;
+    for (int item = group; item < nitems; item += ngroups) {
+      int valid[CG];
+      bool any = false;
+#pragma unroll
+      for (int s = 0; s < CG; ++s) {
+        valid[s] = block_valid(lens, item * CG + s, nblocks, bpc, TB);
+        any |= valid[s] > 0;
+      }
+      if (!any) continue;
+      for (int ft = 0; ft < NFT; ++ft, ++acc_iter) {
+        const uint32_t as = acc_iter & 1u;
+        mbar_wait(&acc_full[as], (acc_iter >> 1) & 1u, dbg, 100 + ft);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int s = 0; s < CG; ++s) {
+          float sum = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < TB; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + as * UMMA_N + s * TB + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum += gelu_tanh(__uint_as_float(v[i]));
+          }
+          if (valid[s] > 0) {
+            const size_t blk = static_cast<size_t>(item) * CG + s;
+            part[blk * D + ft * Tr::MT + rank * 128 + row] = sum;
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(&acc_empty[as], 0); else mbar_arrive(&acc_empty[as]);
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== gather: table rows -> swizzled resident token tiles ==============
+    const int p = threadIdx.x - 128;           // 0..127
+    const int r16 = p >> 3;                    // row within a 16-row slab
+    const int c = p & 7;                       // 16-byte chunk within the 128-byte row
+    const uint32_t tok_base = smem_u32(tok_smem);
+    // swizzle: chunk index XOR (row mod 8); rows of one thread are congruent mod 16 so it is constant
+    const uint32_t dst_off0 = static_cast<uint32_t>(r16 * 128 + ((c ^ (r16 & 7)) << 4));
+    uint32_t it = 0;
+    for (int item = group; item < nitems; item += ngroups) {
+      bool any = false;
+#pragma unroll
+      for (int s = 0; s < CG; ++s) any |= block_valid(lens, item * CG + s, nblocks, bpc, TB) > 0;
+      if (!any) continue;
+      const int blk = item * CG + static_cast<int>(rank);
+      const int valid = block_valid(lens, blk, nblocks, bpc, TB);
+      const int cand = blk < nblocks ? blk / bpc : 0;
+      const int j = blk < nblocks ? blk - cand * bpc : 0;
+      const int32_t* ids = token_ids + static_cast<size_t>(cand) * T + static_cast<size_t>(j) * TB;
+      const uint16_t* src[TB / 16];
+      uint32_t nbytes[TB / 16];
+#pragma unroll
+      for (int q = 0; q < TB / 16; ++q) {
+        const int rowi = q * 16 + r16;
+        int32_t id = -1;
+        if (rowi < valid) id = ids[rowi];
+        if (id >= vocab) {
+          atomicExch(dbg + 4, 1);
+          id = -1;
+        }
+        nbytes[q] = id >= 0 ? 16u : 0u;
+        src[q] = table + (id >= 0 ? static_cast<size_t>(id) * D : 0) + c * 8;
+      }
+      const uint32_t par_empty = (it & 1u) ^ 1u;
+#pragma unroll 1
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&tok_empty[kb], par_empty, dbg, 200 + kb);
+        const uint32_t dst = tok_base + kb * Tr::TOK_KB_BYTES + dst_off0;
+#pragma unroll
+        for (int q = 0; q < TB / 16; ++q) cp_async_16(dst + q * 2048, src[q] + kb * 64, nbytes[q]);
+        cp_async_commit();
+        if (kb >= LAG) {
+          cp_async_wait<LAG>();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_cluster(&tok_full[kb - LAG], 0); else mbar_arrive(&tok_full[kb - LAG]);
+          }
+        }
+      }
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int kb = KB - LAG; kb < KB; ++kb) {
+          if constexpr (CG == 2) mbar_arrive_cluster(&tok_full[kb], 0); else mbar_arrive(&tok_full[kb]);
+        }
+      }
+      ++it;
+    }
+  } else if (warp == 8) {
+    // ===================== W^T tile producer (TMA) =========================================
+    if (lane == 0) {
+      uint32_t wi = 0;
+      for (int item = group; item < nitems; item += ngroups) {
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < CG; ++s) any |= block_valid(lens, item * CG + s, nblocks, bpc, TB) > 0;
+        if (!any) continue;
+        for (int ft = 0; ft < NFT; ++ft) {
+          for (int kb = 0; kb < KB; ++kb, ++wi) {
+            const uint32_t s = wi % WS;
+            const uint32_t ph = (wi / WS) & 1u;
+            mbar_wait(&w_empty[s], ph ^ 1u, dbg, 300 + static_cast<int>(s));
+            void* dst = w_smem + s * Tr::W_STAGE_BYTES;
+            if constexpr (CG == 2) {
+              if (leader) mbar_expect_tx(&w_full[s], 2 * Tr::W_STAGE_BYTES);
+              tma_load_2d_pair(dst, &w_tmap, &w_full[s], kb * 64, ft * Tr::MT + static_cast<int>(rank) * 128);
+            } else {
+              mbar_expect_tx(&w_full[s], Tr::W_STAGE_BYTES);
+              tma_load_2d(dst, &w_tmap, &w_full[s], kb * 64, ft * Tr::MT);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== MMA issuer (leader CTA, one lane) ================================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(Tr::MT, UMMA_N);
+      const uint32_t w_base = smem_u32(w_smem);
+      const uint32_t tok_base = smem_u32(tok_smem);
+      uint32_t wi = 0, acc_iter = 0, it = 0;
+      for (int item = group; item < nitems; item += ngroups) {
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < CG; ++s) any |= block_valid(lens, item * CG + s, nblocks, bpc, TB) > 0;
+        if (!any) continue;
+        for (int ft = 0; ft < NFT; ++ft, ++acc_iter) {
+          const uint32_t as = acc_iter & 1u;
+          if constexpr (CG == 2) mbar_wait_cluster(&acc_empty[as], ((acc_iter >> 1) & 1u) ^ 1u, dbg, 400 + ft);
+          else mbar_wait(&acc_empty[as], ((acc_iter >> 1) & 1u) ^ 1u, dbg, 400 + ft);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + as * UMMA_N;
+          for (int kb = 0; kb < KB; ++kb, ++wi) {
+            if (ft == 0) {
+              if constexpr (CG == 2) mbar_wait_cluster(&tok_full[kb], it & 1u, dbg, 500 + kb);
+              else mbar_wait(&tok_full[kb], it & 1u, dbg, 500 + kb);
+            }
+            const uint32_t s = wi % WS;
+            mbar_wait(&w_full[s], (wi / WS) & 1u, dbg, 600 + static_cast<int>(s));
+            tcgen05_fence_after();
+            const uint64_t adesc = make_kmajor_sw128_desc(w_base + s * Tr::W_STAGE_BYTES);
+            const uint64_t bdesc = make_kmajor_sw128_desc(tok_base + kb * Tr::TOK_KB_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // +32 bytes per 16-element k step inside the 128-byte swizzle row (>>4 => +2)
+              umma_bf16<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit<CG>(&w_empty[s]);                       // W stage reusable once these MMAs retire
+            if (ft == NFT - 1) umma_commit<CG>(&tok_empty[kb]);  // token k-block free for the next gather
+          }
+          umma_commit<CG>(&acc_full[as]);
+        }
+        ++it;
+      }
+    }
+  }
+
+  // ---- teardown -----------------------------------------------------------------------
+  __syncwarp();  // single-lane roles (TMA producer, MMA issuer) rejoin their warp before the aligned barriers
+  tcgen05_fence_before();
+  if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+  if (warp == 9) {
+    tcgen05_fence_after();
+    tmem_dealloc<CG>(tmem_base, Tr::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+
+template <class Tr>
+static cudaError_t launch_encode_t(const EncoderLaunch& a) {
+  auto kern = qc_encode_kernel<Tr>;
+  static bool attr_set[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tr::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  const int bpc = (a.T + Tr::TB - 1) / Tr::TB;
+  int grid = a.num_sms;
+  if (Tr::CG == 2) grid &= ~1;
+  const long long nitems = (static_cast<long long>(a.R) * bpc + Tr::CG - 1) / Tr::CG;
+  if (nitems * Tr::CG < grid) grid = static_cast<int>(nitems * Tr::CG);
+  if (grid < Tr::CG) grid = Tr::CG;
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kEncThreads);
+  cfg.dynamicSmemBytes = Tr::SMEM_BYTES;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = Tr::CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, *a.w_tmap, a.table, a.token_ids, a.lens, a.part, a.err_flag, a.R, a.T,
+                            bpc, a.vocab);
+}
+
+int encoder_token_block(int dim) { return dim == 1536 ? 64 : 128; }
+
+int encoder_w_stages(int dim, int cta_group) {
+  (void)cta_group;
+  switch (dim) {
+    case 384: return EncTraits<384, 128, 1>::W_STAGES;
+    case 768: return EncTraits<768, 128, 1>::W_STAGES;
+    case 1536: return EncTraits<1536, 64, 1>::W_STAGES;
+    default: return 0;
+  }
+}
+
+bool encoder_supports(int dim, int cta_group) {
+  if (cta_group == 1) return dim == 384 || dim == 768 || dim == 1536;
+  if (cta_group == 2) return dim == 768 || dim == 1536;
+  return false;
+}
+
+cudaError_t launch_encode(const EncoderLaunch& a) {
+  if (a.cta_group == 2) {
+    if (a.dim == 768) return launch_encode_t<EncTraits<768, 128, 2>>(a);
+    if (a.dim == 1536) return launch_encode_t<EncTraits<1536, 64, 2>>(a);
+  } else {
+    if (a.dim == 384) return launch_encode_t<EncTraits<384, 128, 1>>(a);
+    if (a.dim == 768) return launch_encode_t<EncTraits<768, 128, 1>>(a);
+    if (a.dim == 1536) return launch_encode_t<EncTraits<1536, 64, 1>>(a);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace qc

@@ -1,0 +1,463 @@
+// qc_similarity.cu -- K2 (finalise embeddings), K3 (N x N cosine + verdicts), lesson first-match,
+// chunk mean.  All HBM-bandwidth-bound fp32 work: coalesced 16-byte loads, warp-shuffle reductions.
+//
+// K3 restates, per decision, the arithmetic of
+//   ConsensusRules.cosine_similarity/2      reference lib/quoracle/actions/consensus_rules.ex:189-210
+//   the row-0 threshold rule                reference lib/quoracle/actions/consensus_rules.ex:277-286
+// and adds the north-star medoid vote (argmax_i mean_j cos(e_i, e_j), lowest index on ties),
+// which has no reference counterpart.
+#include "qc_common.cuh"
+#include "ptx.cuh"
+
+namespace qc {
+
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// cos = dot / (|a| |b|), 0.0 when either norm is zero (reference consensus_rules.ex:205-209).
+__device__ __forceinline__ float cosine_from(float dot, float na, float nb) {
+  return (na == 0.f || nb == 0.f) ? 0.f : dot / (na * nb);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: part[r, j, :] (j < ceil(len/TB)) -> mean over tokens -> L2 normalise -> emb[r, :]
+// ------------------------------------------------------------------------------------------
+template <int PER>
+__global__ void __launch_bounds__(256) qc_finalize_kernel(const float* __restrict__ part,
+                                                          const int32_t* __restrict__ lens,
+                                                          float* __restrict__ emb, int R, int bpc, int TB, int D) {
+  const int r = blockIdx.x;
+  if (r >= R) return;
+  const int len = lens[r];
+  const int nb = (len + TB - 1) / TB;
+  const float* p = part + static_cast<size_t>(r) * bpc * D;
+  float v[PER];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int d = threadIdx.x + i * 256;
+    float s = 0.f;
+    if (d < D) {
+      for (int j = 0; j < nb; ++j) s += p[static_cast<size_t>(j) * D + d];  // fixed block order
+      s = len > 0 ? s / static_cast<float>(len) : 0.f;
+    }
+    v[i] = s;
+    ss += s * s;
+  }
+  __shared__ float red[8];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  const float nrm = sqrtf(tot);
+  const float inv = nrm > 0.f ? 1.f / nrm : 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int d = threadIdx.x + i * 256;
+    if (d < D) emb[static_cast<size_t>(r) * D + d] = v[i] * inv;
+  }
+}
+
+cudaError_t launch_finalize(const float* part, const int32_t* lens, float* emb, int R, int bpc, int TB, int dim,
+                            cudaStream_t stream) {
+  if (R <= 0) return cudaSuccess;
+  if (dim <= 512) qc_finalize_kernel<2><<<R, 256, 0, stream>>>(part, lens, emb, R, bpc, TB, dim);
+  else if (dim <= 1024) qc_finalize_kernel<4><<<R, 256, 0, stream>>>(part, lens, emb, R, bpc, TB, dim);
+  else if (dim <= 2048) qc_finalize_kernel<8><<<R, 256, 0, stream>>>(part, lens, emb, R, bpc, TB, dim);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Verdict tail shared by both K3 paths.  `c(i, j)` returns the cosine; runs on one thread.
+// ------------------------------------------------------------------------------------------
+template <class CosFn>
+__device__ __forceinline__ void verdict_tail(int N, float thr, CosFn c, int32_t* ref_ok, int32_t* medoid) {
+  int ok = 1;
+  for (int i = 1; i < N; ++i) ok &= (c(0, i) >= thr) ? 1 : 0;
+  int best = 0;
+  float best_mean = 0.f;
+  for (int i = 0; i < N; ++i) {
+    float s = 0.f;
+    for (int j = 0; j < N; ++j) s += c(i, j);  // j ascending, diagonal included
+    const float m = s / static_cast<float>(N);
+    if (i == 0 || m > best_mean) {
+      best_mean = m;
+      best = i;
+    }
+  }
+  if (ref_ok) *ref_ok = ok;
+  if (medoid) *medoid = best;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 path A: N <= 8.  One warp per decision; every lane streams 16-byte column chunks of all
+// N rows, keeps the N(N+1)/2 partial dot products in registers, one butterfly reduction at the end.
+// ------------------------------------------------------------------------------------------
+template <int N, bool VEC>
+__global__ void __launch_bounds__(256) qc_sim_small_kernel(const float* __restrict__ emb, int B, int D,
+                                                           const float* __restrict__ thr,
+                                                           int32_t* __restrict__ ref_ok,
+                                                           int32_t* __restrict__ medoid, float* __restrict__ cos) {
+  constexpr int P = N * (N + 1) / 2;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* x = emb + static_cast<size_t>(b) * N * D;
+  float acc[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) acc[p] = 0.f;
+
+  if constexpr (VEC) {
+    for (int col = lane * 4; col < D; col += 128) {
+      float4 v[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = ldg_stream4(x + static_cast<size_t>(i) * D + col);
+      int p = 0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = i; j < N; ++j, ++p) {
+          acc[p] = fmaf(v[i].x, v[j].x, acc[p]);
+          acc[p] = fmaf(v[i].y, v[j].y, acc[p]);
+          acc[p] = fmaf(v[i].z, v[j].z, acc[p]);
+          acc[p] = fmaf(v[i].w, v[j].w, acc[p]);
+        }
+      }
+    }
+  } else {
+    for (int col = lane; col < D; col += 32) {
+      float v[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = __ldg(x + static_cast<size_t>(i) * D + col);
+      int p = 0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = i; j < N; ++j, ++p) acc[p] = fmaf(v[i], v[j], acc[p]);
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < P; ++p) acc[p] = warp_sum(acc[p]);
+
+  // Full cosine matrix in registers (every lane holds the same values).
+  float nrm[N];
+  float cm[N][N];
+  {
+    int p = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      nrm[i] = sqrtf(acc[p]);
+      p += N - i;
+    }
+    p = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+      for (int j = i; j < N; ++j, ++p) {
+        const float c = cosine_from(acc[p], nrm[i], nrm[j]);
+        cm[i][j] = c;
+        cm[j][i] = c;
+      }
+    }
+  }
+  if (cos != nullptr) {
+    float* o = cos + static_cast<size_t>(b) * N * N;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        if (lane == ((i * N + j) & 31)) o[i * N + j] = cm[i][j];
+      }
+    }
+  }
+  if (lane == 0) {
+    int ok = 1;
+#pragma unroll
+    for (int i = 1; i < N; ++i) ok &= (cm[0][i] >= thr[b]) ? 1 : 0;
+    int best = 0;
+    float best_mean = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < N; ++j) s += cm[i][j];
+      const float m = s / static_cast<float>(N);
+      if (i == 0 || m > best_mean) {
+        best_mean = m;
+        best = i;
+      }
+    }
+    if (ref_ok) ref_ok[b] = ok;
+    if (medoid) medoid[b] = best;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 path B: 8 < N <= 64.  One CTA per decision.  Column chunks of all rows are staged in shared
+// memory with cp.async (double buffered); each thread owns a 4x4 tile of the upper-triangular Gram
+// matrix (rows interleaved by N/4 so the 16-byte shared loads are conflict free) and a k-slice.
+// ------------------------------------------------------------------------------------------
+constexpr int kSimDC = 128;             // columns per chunk
+constexpr int kSimRS = kSimDC + 4;      // padded row stride (floats): odd in 16-byte units
+constexpr int kSimThreads = 256;
+
+template <bool VEC>
+__device__ __forceinline__ void sim_load_chunk(float* buf, const float* x, int N, int Np, int D, int c0) {
+  constexpr int G = kSimDC / 4;
+  for (int idx = threadIdx.x; idx < Np * G; idx += kSimThreads) {
+    const int row = idx / G;
+    const int g = idx - row * G;
+    const int col = c0 + 4 * g;
+    float* dst = buf + row * kSimRS + 4 * g;
+    if constexpr (VEC) {
+      const bool in = (row < N) && (col < D);
+      ptx::cp_async_16(ptx::smem_u32(dst), in ? (x + static_cast<size_t>(row) * D + col) : x, in ? 16u : 0u);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool in = (row < N) && (col + e < D);
+        dst[e] = in ? __ldg(x + static_cast<size_t>(row) * D + col + e) : 0.f;
+      }
+    }
+  }
+  if constexpr (VEC) ptx::cp_async_commit();
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kSimThreads) qc_sim_large_kernel(const float* __restrict__ emb, int B, int N, int D,
+                                                                   const float* __restrict__ thr,
+                                                                   int32_t* __restrict__ ref_ok,
+                                                                   int32_t* __restrict__ medoid,
+                                                                   float* __restrict__ cos) {
+  extern __shared__ __align__(16) float sm[];
+  const int N4 = (N + 3) / 4;
+  const int Np = N4 * 4;
+  const int ntiles = N4 * (N4 + 1) / 2;
+  const int nks = kSimThreads / ntiles;
+  float* buf0 = sm;
+  float* buf1 = sm + 64 * kSimRS;
+  float* gram = sm + 2 * 64 * kSimRS;  // [64][65]
+
+  const int t = threadIdx.x;
+  const int tile = t % ntiles;
+  const int ks = t / ntiles;
+  const bool active = ks < nks;
+  // tile -> (ti <= tj)
+  int ti = 0, rem = tile;
+  while (rem >= N4 - ti) {
+    rem -= N4 - ti;
+    ++ti;
+  }
+  const int tj = ti + rem;
+
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const float* x = emb + static_cast<size_t>(b) * N * D;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+
+    const int nchunks = (D + kSimDC - 1) / kSimDC;
+    sim_load_chunk<VEC>(buf0, x, N, Np, D, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+      float* cur = (ch & 1) ? buf1 : buf0;
+      float* nxt = (ch & 1) ? buf0 : buf1;
+      if (ch + 1 < nchunks) {
+        sim_load_chunk<VEC>(nxt, x, N, Np, D, (ch + 1) * kSimDC);
+        if constexpr (VEC) ptx::cp_async_wait<1>();
+      } else {
+        if constexpr (VEC) ptx::cp_async_wait<0>();
+      }
+      __syncthreads();
+      if (active) {
+        for (int g = ks; g < kSimDC / 4; g += nks) {
+          float4 av[4], bv[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) av[a] = *reinterpret_cast<const float4*>(cur + (ti + a * N4) * kSimRS + 4 * g);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) bv[c] = *reinterpret_cast<const float4*>(cur + (tj + c * N4) * kSimRS + 4 * g);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              acc[a][c] = fmaf(av[a].x, bv[c].x, acc[a][c]);
+              acc[a][c] = fmaf(av[a].y, bv[c].y, acc[a][c]);
+              acc[a][c] = fmaf(av[a].z, bv[c].z, acc[a][c]);
+              acc[a][c] = fmaf(av[a].w, bv[c].w, acc[a][c]);
+            }
+        }
+      }
+      __syncthreads();
+    }
+    // reduce k-slices through shared memory (fixed order), build the symmetric Gram matrix
+    float* red = buf0;  // [nks][ntiles][16] <= 256*16 floats = 16 KB, fits in buf0 (64*132 floats)
+    if (active) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) red[(ks * ntiles + tile) * 16 + a * 4 + c] = acc[a][c];
+    }
+    __syncthreads();
+    for (int idx = t; idx < ntiles * 16; idx += kSimThreads) {
+      const int tl = idx >> 4, e = idx & 15;
+      float s = 0.f;
+      for (int k = 0; k < nks; ++k) s += red[(k * ntiles + tl) * 16 + e];
+      int ri = 0, rr = tl;
+      while (rr >= N4 - ri) {
+        rr -= N4 - ri;
+        ++ri;
+      }
+      const int rj = ri + rr;
+      const int i = ri + (e >> 2) * N4;
+      const int j = rj + (e & 3) * N4;
+      gram[i * 65 + j] = s;
+      gram[j * 65 + i] = s;
+    }
+    __syncthreads();
+    // cosine in place (needs the diagonal first): stash norms, then overwrite
+    float* nrm = buf1;  // Np floats
+    if (t < Np) nrm[t] = sqrtf(gram[t * 65 + t]);
+    __syncthreads();
+    for (int idx = t; idx < N * N; idx += kSimThreads) {
+      const int i = idx / N, j = idx - i * N;
+      const float c = cosine_from(gram[i * 65 + j], nrm[i], nrm[j]);
+      gram[i * 65 + j] = c;
+      if (cos != nullptr) cos[static_cast<size_t>(b) * N * N + idx] = c;
+    }
+    __syncthreads();
+    if (t == 0) {
+      verdict_tail(N, thr[b], [&](int i, int j) { return gram[i * 65 + j]; }, ref_ok ? ref_ok + b : nullptr,
+                   medoid ? medoid + b : nullptr);
+    }
+    __syncthreads();
+  }
+}
+
+constexpr int kSimLargeSmem = (2 * 64 * kSimRS + 64 * 65) * static_cast<int>(sizeof(float));
+
+template <int N>
+static cudaError_t launch_small(const float* emb, int B, int D, const float* thr, int32_t* ref_ok, int32_t* medoid,
+                                float* cos, bool vec, cudaStream_t stream) {
+  const int wpb = 8;
+  const int grid = (B + wpb - 1) / wpb;
+  if (vec) qc_sim_small_kernel<N, true><<<grid, wpb * 32, 0, stream>>>(emb, B, D, thr, ref_ok, medoid, cos);
+  else qc_sim_small_kernel<N, false><<<grid, wpb * 32, 0, stream>>>(emb, B, D, thr, ref_ok, medoid, cos);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_similarity(const float* emb, int B, int N, int D, const float* thr, int32_t* ref_ok,
+                              int32_t* medoid, float* cos, int num_sms, cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  if (N < 1 || N > 64 || D < 1) return cudaErrorInvalidValue;
+  const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(emb) & 15) == 0);
+  switch (N) {
+    case 1: return launch_small<1>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
+    case 2: return launch_small<2>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
+    case 3: return launch_small<3>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
+    case 4: return launch_small<4>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
+    case 5: return launch_small<5>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
+    case 6: return launch_small<6>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
+    case 7: return launch_small<7>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
+    case 8: return launch_small<8>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
+    default: break;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(qc_sim_large_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kSimLargeSmem);
+    cudaError_t e2 = cudaFuncSetAttribute(qc_sim_large_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kSimLargeSmem);
+    if (e1 != cudaSuccess) return e1;
+    if (e2 != cudaSuccess) return e2;
+    attr_set = true;
+  }
+  int grid = B < num_sms * 2 ? B : num_sms * 2;  // two resident CTAs per SM (84 KB each)
+  if (vec) qc_sim_large_kernel<true><<<grid, kSimThreads, kSimLargeSmem, stream>>>(emb, B, N, D, thr, ref_ok, medoid, cos);
+  else qc_sim_large_kernel<false><<<grid, kSimThreads, kSimLargeSmem, stream>>>(emb, B, N, D, thr, ref_ok, medoid, cos);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Lesson dedup (reference lib/quoracle/agent/lesson_manager.ex:150-173): first row m with
+// cos(query, row_m) >= thr.  One CTA per query, one warp per row (round robin).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qc_first_match_kernel(const float* __restrict__ query,
+                                                             const float* __restrict__ rows, int Q, int M, int D,
+                                                             const float* __restrict__ thr,
+                                                             int32_t* __restrict__ out_index,
+                                                             float* __restrict__ out_cos) {
+  __shared__ int first;
+  const int q = blockIdx.x;
+  if (q >= Q) return;
+  if (threadIdx.x == 0) first = 0x7fffffff;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* qv = query + static_cast<size_t>(q) * D;
+  const float th = thr[q];
+  for (int m = warp; m < M; m += 8) {
+    const float* rv = rows + (static_cast<size_t>(q) * M + m) * D;
+    float dot = 0.f, nq = 0.f, nr = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float a = __ldg(qv + d), b = __ldg(rv + d);
+      dot = fmaf(a, b, dot);
+      nq = fmaf(a, a, nq);
+      nr = fmaf(b, b, nr);
+    }
+    dot = warp_sum(dot);
+    nq = warp_sum(nq);
+    nr = warp_sum(nr);
+    const float c = cosine_from(dot, sqrtf(nq), sqrtf(nr));
+    if (lane == 0) {
+      if (out_cos) out_cos[static_cast<size_t>(q) * M + m] = c;
+      if (c >= th) atomicMin(&first, m);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) out_index[q] = first == 0x7fffffff ? -1 : first;
+}
+
+cudaError_t launch_first_match(const float* query, const float* rows, int Q, int M, int D, const float* thr,
+                               int32_t* out_index, float* out_cos, cudaStream_t stream) {
+  if (Q <= 0) return cudaSuccess;
+  qc_first_match_kernel<<<Q, 256, 0, stream>>>(query, rows, Q, M, D, thr, out_index, out_cos);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Chunk mean (reference lib/quoracle/models/embeddings.ex:371-383): element-wise unweighted mean,
+// chunks added in order, NOT re-normalised.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qc_chunk_mean_kernel(const float* __restrict__ chunks, int G, int C, int D,
+                                                            float* __restrict__ out) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(G) * D) return;
+  const size_t g = idx / D, d = idx - g * D;
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += chunks[(g * C + c) * D + d];
+  out[idx] = s / static_cast<float>(C);
+}
+
+cudaError_t launch_chunk_mean(const float* chunks, int G, int C, int D, float* out, cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(G) * D;
+  if (total == 0) return cudaSuccess;
+  qc_chunk_mean_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(chunks, G, C, D, out);
+  return cudaGetLastError();
+}
+
+}  // namespace qc

@@ -1,0 +1,314 @@
+"""ctypes binding of libqconsensus.so -- the only way this package reaches the GPU.
+
+There is no CPU fallback: if the shared library is missing or no sm_100 device is usable the calls
+raise.  The binding mirrors ``include/qconsensus.h`` one to one; array arguments are numpy arrays
+(host entry points) or integer device addresses (``*_dev`` entry points, e.g. ``tensor.data_ptr()``).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libqconsensus.so"
+_lib: Optional[ctypes.CDLL] = None
+
+QC_K_NAMES = ("encode", "finalize", "similarity", "first_match", "chunk_mean")
+QC_MAX_POOL = 64
+QC_MAX_TOKENS = 8192
+QC_PAD_TOKEN = -1
+
+# Every symbol include/qconsensus.h declares (checked by tests/test_abi_symbols.py).
+ABI_SYMBOLS = (
+    "qc_ctx_create", "qc_ctx_destroy", "qc_ctx_device", "qc_ctx_dim", "qc_ctx_synchronize",
+    "qc_host_alloc", "qc_host_free",
+    "qc_decide_batch", "qc_embed_batch", "qc_similarity_batch", "qc_first_match_batch", "qc_chunk_mean",
+    "qc_decide_batch_dev", "qc_embed_batch_dev", "qc_similarity_batch_dev",
+    "qc_strerror", "qc_status_atom", "qc_abi_version",
+    "qc_check_status", "qc_last_hang",
+    "qc_launch_count", "qc_profile_enable", "qc_profile_reset", "qc_kernel_stats",
+    "qc_encoder_info", "qc_encoder_set_cta_group",
+)
+
+
+class QcError(RuntimeError):
+    """A negative qc_status; ``atom`` is the Elixir error atom the status maps to."""
+
+    def __init__(self, status: int, message: str, atom: str):
+        super().__init__(f"libqconsensus: {message} (status {status}, :{atom})")
+        self.status = status
+        self.atom = atom
+
+
+class _EncCfg(ctypes.Structure):
+    _fields_ = [("vocab", ctypes.c_int32), ("dim", ctypes.c_int32),
+                ("table_bf16", ctypes.c_void_p), ("w_bf16", ctypes.c_void_p)]
+
+
+def load_library() -> ctypes.CDLL:
+    """Load the CUDA extension; raise loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python -m quoracle_b200.build` "
+            "(or __graft_entry__.build()).  quoracle_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(str(_LIB_PATH))
+    vp, i32, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    lib.qc_ctx_create.restype = i32
+    lib.qc_ctx_create.argtypes = [ctypes.POINTER(vp), i32, ctypes.POINTER(_EncCfg)]
+    lib.qc_ctx_destroy.restype = None
+    lib.qc_ctx_destroy.argtypes = [vp]
+    lib.qc_ctx_device.restype = i32
+    lib.qc_ctx_device.argtypes = [vp]
+    lib.qc_ctx_dim.restype = i32
+    lib.qc_ctx_dim.argtypes = [vp]
+    lib.qc_ctx_synchronize.restype = i32
+    lib.qc_ctx_synchronize.argtypes = [vp]
+    lib.qc_host_alloc.restype = vp
+    lib.qc_host_alloc.argtypes = [sz]
+    lib.qc_host_free.restype = None
+    lib.qc_host_free.argtypes = [vp]
+    lib.qc_decide_batch.restype = i32
+    lib.qc_decide_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.qc_embed_batch.restype = i32
+    lib.qc_embed_batch.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.qc_similarity_batch.restype = i32
+    lib.qc_similarity_batch.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.qc_first_match_batch.restype = i32
+    lib.qc_first_match_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.qc_chunk_mean.restype = i32
+    lib.qc_chunk_mean.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.qc_decide_batch_dev.restype = i32
+    lib.qc_decide_batch_dev.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.qc_embed_batch_dev.restype = i32
+    lib.qc_embed_batch_dev.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    lib.qc_similarity_batch_dev.restype = i32
+    lib.qc_similarity_batch_dev.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.qc_strerror.restype = ctypes.c_char_p
+    lib.qc_strerror.argtypes = [i32]
+    lib.qc_status_atom.restype = ctypes.c_char_p
+    lib.qc_status_atom.argtypes = [i32]
+    lib.qc_abi_version.restype = i32
+    lib.qc_abi_version.argtypes = []
+    lib.qc_check_status.restype = i32
+    lib.qc_check_status.argtypes = [vp]
+    lib.qc_last_hang.restype = i32
+    lib.qc_last_hang.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
+    lib.qc_launch_count.restype = ctypes.c_uint64
+    lib.qc_launch_count.argtypes = [vp]
+    lib.qc_profile_enable.restype = i32
+    lib.qc_profile_enable.argtypes = [vp, i32]
+    lib.qc_profile_reset.restype = i32
+    lib.qc_profile_reset.argtypes = [vp]
+    lib.qc_kernel_stats.restype = i32
+    lib.qc_kernel_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
+    lib.qc_encoder_info.restype = i32
+    lib.qc_encoder_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                    ctypes.POINTER(ctypes.c_int32)]
+    lib.qc_encoder_set_cta_group.restype = i32
+    lib.qc_encoder_set_cta_group.argtypes = [vp, i32]
+    _lib = lib
+    return lib
+
+
+def _check(status: int) -> None:
+    if status != 0:
+        lib = load_library()
+        raise QcError(status, lib.qc_strerror(status).decode(), lib.qc_status_atom(status).decode())
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _dev(addr) -> ctypes.c_void_p:
+    return ctypes.c_void_p(int(addr) if addr else 0)
+
+
+class PinnedArray:
+    """numpy view over qc_host_alloc memory (page-locked, so the library copies from it directly)."""
+
+    def __init__(self, shape, dtype):
+        lib = load_library()
+        self._dtype = np.dtype(dtype)
+        self._nbytes = int(np.prod(shape)) * self._dtype.itemsize
+        self._addr = lib.qc_host_alloc(max(self._nbytes, 1))
+        if not self._addr:
+            raise QcError(-5, "pinned allocation failed", "service_unavailable")
+        buf = (ctypes.c_char * max(self._nbytes, 1)).from_address(self._addr)
+        self.array = np.frombuffer(buf, dtype=self._dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        if self._addr:
+            self.array = None
+            load_library().qc_host_free(ctypes.c_void_p(self._addr))
+            self._addr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class DecideResult:
+    ref_ok: np.ndarray            # [B] int32, reference rule verdict (value_0 wins when 1)
+    medoid: np.ndarray            # [B] int32, north-star vote
+    cos: Optional[np.ndarray]     # [B, N, N] float32
+    emb: Optional[np.ndarray]     # [B, N, D] float32
+
+
+class Context:
+    """One libqconsensus context == one GPU (one process per GPU)."""
+
+    def __init__(self, device: int = 0, table_bf16: Optional[np.ndarray] = None,
+                 w_bf16: Optional[np.ndarray] = None):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        cfg = None
+        if (table_bf16 is None) != (w_bf16 is None):
+            raise ValueError("table_bf16 and w_bf16 must be given together")
+        if table_bf16 is not None:
+            table = np.ascontiguousarray(table_bf16, dtype=np.uint16)
+            w = np.ascontiguousarray(w_bf16, dtype=np.uint16)
+            if table.ndim != 2 or w.shape != (table.shape[1], table.shape[1]):
+                raise ValueError("table must be [vocab, dim] and w [dim, dim] (bf16 bit patterns)")
+            cfg = _EncCfg(table.shape[0], table.shape[1], table.ctypes.data, w.ctypes.data)
+            self._keep = (table, w)
+        _check(self._lib.qc_ctx_create(ctypes.byref(self._h), int(device),
+                                       ctypes.byref(cfg) if cfg is not None else None))
+        self.device = int(device)
+        self.dim = int(self._lib.qc_ctx_dim(self._h))
+        self._keep = None  # weights were copied to the device
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if self._h:
+            self._lib.qc_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self) -> None:
+        _check(self._lib.qc_ctx_synchronize(self._h))
+
+    # -- host entry points ---------------------------------------------------------------------
+    def decide_batch(self, token_ids: np.ndarray, lens: np.ndarray, thr: np.ndarray, want_cos: bool = True,
+                     want_emb: bool = False, out: Optional[DecideResult] = None) -> DecideResult:
+        token_ids = _as(token_ids, np.int32)
+        b, n, t = token_ids.shape
+        lens = _as(lens, np.int32).reshape(b, n)
+        thr = _as(thr, np.float32).reshape(b)
+        if out is None:
+            out = DecideResult(np.empty(b, np.int32), np.empty(b, np.int32),
+                               np.empty((b, n, n), np.float32) if want_cos else None,
+                               np.empty((b, n, self.dim), np.float32) if want_emb else None)
+        _check(self._lib.qc_decide_batch(self._h, _ptr(token_ids), _ptr(lens), b, n, t, _ptr(thr),
+                                         _ptr(out.ref_ok), _ptr(out.medoid), _ptr(out.cos), _ptr(out.emb)))
+        return out
+
+    def embed_batch(self, token_ids: np.ndarray, lens: np.ndarray) -> np.ndarray:
+        token_ids = _as(token_ids, np.int32)
+        r, t = token_ids.shape
+        lens = _as(lens, np.int32).reshape(r)
+        emb = np.empty((r, self.dim), np.float32)
+        _check(self._lib.qc_embed_batch(self._h, _ptr(token_ids), _ptr(lens), r, t, _ptr(emb)))
+        return emb
+
+    def similarity_batch(self, emb: np.ndarray, thr: np.ndarray, want_cos: bool = True):
+        emb = _as(emb, np.float32)
+        b, n, d = emb.shape
+        thr = _as(thr, np.float32).reshape(b)
+        ref_ok = np.empty(b, np.int32)
+        medoid = np.empty(b, np.int32)
+        cos = np.empty((b, n, n), np.float32) if want_cos else None
+        _check(self._lib.qc_similarity_batch(self._h, _ptr(emb), b, n, d, _ptr(thr), _ptr(ref_ok), _ptr(medoid),
+                                             _ptr(cos)))
+        return ref_ok, medoid, cos
+
+    def first_match_batch(self, query: np.ndarray, rows: np.ndarray, thr: np.ndarray, want_cos: bool = True):
+        query = _as(query, np.float32)
+        rows = _as(rows, np.float32)
+        q, d = query.shape
+        m = rows.shape[1]
+        assert rows.shape == (q, m, d)
+        thr = _as(thr, np.float32).reshape(q)
+        idx = np.empty(q, np.int32)
+        cos = np.empty((q, m), np.float32) if want_cos else None
+        _check(self._lib.qc_first_match_batch(self._h, _ptr(query), _ptr(rows) if m else None, q, m, d, _ptr(thr),
+                                              _ptr(idx), _ptr(cos) if m else None))
+        return idx, cos
+
+    def chunk_mean(self, chunks: np.ndarray) -> np.ndarray:
+        chunks = _as(chunks, np.float32)
+        g, c, d = chunks.shape
+        out = np.empty((g, d), np.float32)
+        _check(self._lib.qc_chunk_mean(self._h, _ptr(chunks), g, c, d, _ptr(out)))
+        return out
+
+    # -- device entry points (addresses of device buffers on this context's GPU) -------------
+    def decide_batch_dev(self, d_token_ids, d_lens, b: int, n: int, t: int, d_thr, d_ref_ok=0, d_medoid=0,
+                         d_cos=0, d_emb=0, stream=0) -> None:
+        _check(self._lib.qc_decide_batch_dev(self._h, _dev(d_token_ids), _dev(d_lens), b, n, t, _dev(d_thr),
+                                             _dev(d_ref_ok), _dev(d_medoid), _dev(d_cos), _dev(d_emb), _dev(stream)))
+
+    def embed_batch_dev(self, d_token_ids, d_lens, r: int, t: int, d_emb, stream=0) -> None:
+        _check(self._lib.qc_embed_batch_dev(self._h, _dev(d_token_ids), _dev(d_lens), r, t, _dev(d_emb), _dev(stream)))
+
+    def similarity_batch_dev(self, d_emb, b: int, n: int, d: int, d_thr, d_ref_ok=0, d_medoid=0, d_cos=0,
+                             stream=0) -> None:
+        _check(self._lib.qc_similarity_batch_dev(self._h, _dev(d_emb), b, n, d, _dev(d_thr), _dev(d_ref_ok),
+                                                 _dev(d_medoid), _dev(d_cos), _dev(stream)))
+
+    # -- introspection ---------------------------------------------------------------------------
+    def check_status(self) -> None:
+        """Synchronise and raise if an earlier asynchronous ``*_dev`` call flagged a device-side error."""
+        _check(self._lib.qc_check_status(self._h))
+
+    def last_hang(self) -> dict:
+        info = (ctypes.c_int32 * 4)()
+        _check(self._lib.qc_last_hang(self._h, info))
+        return {"flag": info[0], "tag": info[1], "block": info[2], "thread": info[3]}
+
+    def launch_count(self) -> int:
+        return int(self._lib.qc_launch_count(self._h))
+
+    def profile_enable(self, on: bool = True) -> None:
+        _check(self._lib.qc_profile_enable(self._h, 1 if on else 0))
+
+    def profile_reset(self) -> None:
+        _check(self._lib.qc_profile_reset(self._h))
+
+    def kernel_stats(self) -> dict:
+        ms = (ctypes.c_double * len(QC_K_NAMES))()
+        nl = (ctypes.c_uint64 * len(QC_K_NAMES))()
+        _check(self._lib.qc_kernel_stats(self._h, ms, nl))
+        return {name: {"ms": float(ms[i]), "launches": int(nl[i])} for i, name in enumerate(QC_K_NAMES)}
+
+    def encoder_info(self) -> dict:
+        cg, tb, ws = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        _check(self._lib.qc_encoder_info(self._h, ctypes.byref(cg), ctypes.byref(tb), ctypes.byref(ws)))
+        return {"cta_group": cg.value, "token_block": tb.value, "w_stages": ws.value}
+
+    def set_cta_group(self, cta_group: int) -> None:
+        _check(self._lib.qc_encoder_set_cta_group(self._h, int(cta_group)))
+
+
+def _as(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)

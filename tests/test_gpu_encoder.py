@@ -1,0 +1,154 @@
+"""K1+K2 parity through the C ABI: qc_embed_batch / qc_decide_batch vs the numpy f64 restatement of
+this build's encoder (oracle/encoder.py) and the oracle verdicts.  The reference has no local encoder
+(lib/quoracle/models/embeddings.ex:277-298 is an HTTP call), so embedding VALUES are parity-unpinned
+against the reference; everything downstream of the vectors is pinned (tests/test_gpu_similarity.py)."""
+import numpy as np
+import pytest
+
+from oracle import encoder as oenc
+from oracle import numeric
+from quoracle_b200 import native, synth
+
+pytestmark = pytest.mark.gpu
+EMB_TOL = 2e-4      # abs, on unit-norm rows (fp32 accumulate + tanh.approx vs f64 libm)
+COS_TOL = 1e-3      # north_star tolerance on cosines
+MARGIN = 5e-4       # verdict margin under which fp32 may flip an index (reported, not asserted)
+
+_enc_cache = {}
+
+
+def weights(dim, vocab=4096):
+    key = (dim, vocab)
+    if key not in _enc_cache:
+        _enc_cache[key] = synth.make_encoder(dim, vocab=vocab, seed=synth.BASE_SEED + dim)
+    return _enc_cache[key]
+
+
+def cta_groups(dim):
+    return [1] if dim == 384 else [1, 2]
+
+
+@pytest.mark.parametrize("dim", [384, 768, 1536])
+def test_embed_ragged_rows(dim):
+    """Empty, single-token, exactly-one-block, block+1, padded and full rows; both CTA-group variants."""
+    w = weights(dim)
+    t = 300
+    lens = np.array([0, 1, 5, 63, 64, 65, 127, 128, 129, 255, 256, 257, 299, 300, 17, 200], np.int32)
+    rng = np.random.default_rng(dim)
+    tok = rng.integers(0, 4096, (len(lens), t)).astype(np.int32)
+    tok[np.arange(t)[None, :] >= lens[:, None]] = -1
+    tok[13, 7] = -1                                   # a pad marker inside len contributes GELU(0) = 0
+    want = oenc.encode(w.table_bf16, w.w_bf16, tok, lens)
+    with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+        for cg in cta_groups(dim):
+            ctx.set_cta_group(cg)
+            got = ctx.embed_batch(tok, lens)
+            assert np.all(np.isfinite(got)), (dim, cg)
+            err = np.max(np.abs(got - want), axis=1)
+            assert np.all(err < EMB_TOL), (dim, cg, err)
+            assert np.all(got[0] == 0.0)              # len 0 -> zero vector -> cosine 0.0 downstream
+            nrm = np.linalg.norm(got[1:].astype(np.float64), axis=1)
+            assert np.max(np.abs(nrm - 1.0)) < 1e-5
+
+
+@pytest.mark.parametrize("dim", [384, 768, 1536])
+def test_embed_many_rows_multi_wave(dim):
+    """More blocks than CTAs so the persistent loop, phase bits and buffer reuse are exercised."""
+    w = weights(dim)
+    r, t = 700, 256
+    rng = np.random.default_rng(dim + 1)
+    lens = rng.integers(1, t + 1, r).astype(np.int32)
+    tok = rng.integers(0, 4096, (r, t)).astype(np.int32)
+    tok[np.arange(t)[None, :] >= lens[:, None]] = -1
+    want = oenc.encode(w.table_bf16, w.w_bf16, tok, lens)
+    with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+        for cg in cta_groups(dim):
+            ctx.set_cta_group(cg)
+            got = ctx.embed_batch(tok, lens)
+            assert np.max(np.abs(got - want)) < EMB_TOL, (dim, cg)
+            again = ctx.embed_batch(tok, lens)
+            assert np.array_equal(got, again)          # bit-reproducible run to run
+
+
+def test_config1_plumbing():
+    """BASELINE config 1 shape: 3-model pool, single agent, 64-token candidates (D=384 locally)."""
+    w = weights(384)
+    batch = synth.make_decisions(1, 3, 64, vocab=4096, seed=synth.BASE_SEED + 1)
+    with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+        res = ctx.decide_batch(batch.token_ids, batch.lens, batch.thr, want_cos=True, want_emb=True)
+    emb = oenc.encode(w.table_bf16, w.w_bf16, batch.token_ids.reshape(3, 64), batch.lens.reshape(3))
+    ok, med, cos, margins = numeric.decide_batch(emb.reshape(1, 3, -1), batch.thr)
+    assert np.max(np.abs(res.cos - cos)) < COS_TOL
+    if margins["thr"][0] > MARGIN:
+        assert res.ref_ok[0] == ok[0]
+    if margins["vote"][0] > MARGIN:
+        assert res.medoid[0] == med[0]
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("ragged", [False, True])
+def test_decide_mid_batch(cg, ragged):
+    """8-model pool, 512-token candidates, dim 768 (BASELINE config 2 shape at B=24) vs the oracle."""
+    w = weights(768, vocab=32768)
+    batch = synth.make_decisions(24, 8, 512, seed=synth.BASE_SEED + 2, ragged=ragged,
+                                 thresholds=(0.8, 0.85, 0.9, 0.95, 0.995, 0.9995))
+    with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+        ctx.set_cta_group(cg)
+        res = ctx.decide_batch(batch.token_ids, batch.lens, batch.thr, want_cos=True, want_emb=True)
+    emb = oenc.encode(w.table_bf16, w.w_bf16, batch.token_ids.reshape(-1, 512), batch.lens.reshape(-1))
+    assert np.max(np.abs(res.emb.reshape(-1, 768) - emb)) < EMB_TOL
+    ok, med, cos, margins = numeric.decide_batch(emb.reshape(24, 8, 768), batch.thr.astype(np.float64))
+    assert np.max(np.abs(res.cos - cos)) < COS_TOL
+    safe_t, safe_v = margins["thr"] > MARGIN, margins["vote"] > MARGIN
+    assert np.array_equal(res.ref_ok[safe_t], ok[safe_t])
+    assert np.array_equal(res.medoid[safe_v], med[safe_v])
+    assert safe_t.sum() >= 12 and safe_v.sum() >= 12   # the margin filter must not hollow out the test
+    assert len(set(res.ref_ok.tolist())) == 2          # both verdicts occur
+
+
+def test_full_config2_properties():
+    """BASELINE config 2 at full size (256 agents x 8 models x 512 tokens, dim 768): size-independent
+    properties -- duplicated candidates embed identically, permuting the pool permutes the outputs,
+    padding beyond len is inert -- plus the oracle on a 16-decision slice."""
+    w = weights(768, vocab=32768)
+    batch = synth.make_decisions(256, 8, 512, seed=synth.BASE_SEED + 2)
+    tok = batch.token_ids.copy()
+    tok[:, 5] = tok[:, 2]                                # duplicate a pool member in every decision
+    with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+        for cg in (1, 2):
+            ctx.set_cta_group(cg)
+            res = ctx.decide_batch(tok, batch.lens, batch.thr, want_cos=True, want_emb=True)
+            assert np.array_equal(res.emb[:, 5], res.emb[:, 2])
+            assert np.max(np.abs(res.cos[:, 5, 2] - 1.0)) < 1e-5
+            perm = np.array([3, 0, 7, 1, 6, 2, 5, 4])
+            res_p = ctx.decide_batch(tok[:, perm], batch.lens[:, perm], batch.thr, want_cos=True, want_emb=True)
+            assert np.array_equal(res_p.emb, res.emb[:, perm])
+            assert np.max(np.abs(res_p.cos - res.cos[:, perm][:, :, perm])) < 1e-6
+            # shorten every candidate to 300 tokens two ways: lens only vs lens + pad markers
+            lens300 = np.full_like(batch.lens, 300)
+            tok_pad = tok.copy()
+            tok_pad[:, :, 300:] = -1
+            a = ctx.decide_batch(tok, lens300, batch.thr, want_cos=False, want_emb=True)
+            b = ctx.decide_batch(tok_pad, lens300, batch.thr, want_cos=False, want_emb=True)
+            assert np.array_equal(a.emb, b.emb)
+            sl = slice(0, 16)
+            emb = oenc.encode(w.table_bf16, w.w_bf16, tok[sl].reshape(-1, 512), batch.lens[sl].reshape(-1))
+            assert np.max(np.abs(res.emb[sl].reshape(-1, 768) - emb)) < EMB_TOL, cg
+
+
+def test_token_range_and_limits():
+    w = weights(384)
+    with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+        tok = np.zeros((2, 8), np.int32)
+        tok[1, 3] = 4096                                  # == vocab: out of range
+        with pytest.raises(native.QcError) as e:
+            ctx.embed_batch(tok, np.array([8, 8], np.int32))
+        assert e.value.atom == "invalid_input"
+        with pytest.raises(native.QcError) as e:
+            ctx.embed_batch(np.zeros((1, 8193), np.int32), np.array([8193], np.int32))
+        assert e.value.atom == "context_length_exceeded"
+        with pytest.raises(native.QcError) as e:
+            ctx.embed_batch(np.zeros((1, 8), np.int32), np.array([9], np.int32))
+        assert e.value.atom == "invalid_input"
+        ok = ctx.embed_batch(np.zeros((1, 8), np.int32), np.array([8], np.int32))   # context still usable
+        assert np.isfinite(ok).all()

@@ -1,0 +1,138 @@
+"""K3 parity through the C ABI: qc_similarity_batch vs the oracle (f64 restatement of
+ConsensusRules.cosine_similarity/2 + the row-0 rule, reference consensus_rules.ex:189-210,277-286)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import numeric
+from quoracle_b200 import native, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = json.loads((Path(__file__).parent / "golden" / "reference_vectors.json").read_text())
+COS_TOL = 1e-3          # north_star: cosine values within 1e-3 (fp32 vs the reference's f64)
+TIGHT = 2e-5            # what fp32 accumulation actually achieves on these sizes
+MARGIN = 1e-4           # verdict margin below which an fp32 path may legitimately flip
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = native.Context(0)
+    yield c
+    c.close()
+
+
+def _check(ctx, emb, thr):
+    ref_ok, medoid, cos = ctx.similarity_batch(emb, thr)
+    o_ok, o_med, o_cos, margins = numeric.decide_batch(emb, thr)
+    assert np.all(np.isfinite(cos))
+    assert np.max(np.abs(cos - o_cos)) < TIGHT
+    safe_thr = margins["thr"] > MARGIN
+    safe_vote = margins["vote"] > MARGIN
+    assert np.array_equal(ref_ok[safe_thr], o_ok[safe_thr])
+    assert np.array_equal(medoid[safe_vote], o_med[safe_vote])
+    return int((~safe_thr).sum()), int((~safe_vote).sum())
+
+
+def test_reference_cosine_vectors(ctx):
+    """Every cosine known-answer vector of the reference's tests, as 2-row decisions."""
+    for case in GOLD["cosine"]:
+        a, b = np.array(case["a"], np.float32), np.array(case["b"], np.float32)
+        emb = np.stack([a, b])[None]
+        _, _, cos = ctx.similarity_batch(emb, np.array([0.9], np.float32))
+        got = float(cos[0, 0, 1])
+        if "equals" in case:
+            assert abs(got - case["equals"]) <= max(case.get("f32_tol", case.get("tol", 1e-6)), 1e-6), case["src"]
+        if "gt" in case:
+            assert got > case["gt"], case["src"]
+        if "lt" in case:
+            assert got < case["lt"], case["src"]
+        # and against the oracle itself
+        assert abs(got - numeric.cosine_similarity_rules(case["a"], case["b"])) < TIGHT
+
+
+def test_zero_vectors_give_zero_not_nan(ctx):
+    emb = np.zeros((2, 3, 3072), np.float32)
+    emb[1, 0, 5] = 1.0
+    ref_ok, medoid, cos = ctx.similarity_batch(emb, np.array([0.9, 0.9], np.float32))
+    assert np.all(cos[0] == 0.0)                 # reference: zero norm -> 0.0 (consensus_rules.ex:205-209)
+    assert cos[1, 0, 0] == 1.0 and cos[1, 0, 1] == 0.0 and cos[1, 1, 1] == 0.0
+    assert ref_ok.tolist() == [0, 0]
+    assert medoid.tolist() == [0, 0]
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("d", [3, 10, 32, 130, 384, 768, 3072])
+def test_small_pools(ctx, n, d):
+    emb = synth.make_embeddings(37, n, d, seed=synth.BASE_SEED + 100 * n + d)
+    thr = np.resize(np.array([0.8, 0.85, 0.9, 0.95, 0.3, 0.5], np.float32), 37)
+    _check(ctx, emb, thr)
+
+
+@pytest.mark.parametrize("n", [9, 12, 16, 17, 31, 32, 33, 48, 63, 64])
+@pytest.mark.parametrize("d", [5, 128, 200, 384, 768, 1536])
+def test_large_pools(ctx, n, d):
+    emb = synth.make_embeddings(9, n, d, seed=synth.BASE_SEED + 7 * n + d)
+    thr = np.resize(np.array([0.1, 0.3, 0.5, 0.85], np.float32), 9)
+    _check(ctx, emb, thr)
+
+
+def test_unnormalised_and_negative(ctx):
+    rng = np.random.default_rng(5)
+    emb = (rng.standard_normal((64, 8, 768)) * rng.uniform(0.01, 50.0, (64, 8, 1))).astype(np.float32)
+    emb[:, 3] = -emb[:, 2]                       # exact opposites -> -1
+    ref_ok, medoid, cos = ctx.similarity_batch(emb, np.full(64, 0.0, np.float32))
+    assert np.max(np.abs(cos[:, 2, 3] + 1.0)) < 1e-5
+    _check(ctx, emb, np.full(64, 0.0, np.float32))
+
+
+def test_config5_sweep_large_batch(ctx):
+    """BASELINE config 5 corner: batch 65536, pool 8, dim 384 -- verdicts vs oracle on every decision."""
+    emb = synth.make_embeddings(65536, 8, 384, seed=synth.BASE_SEED + 5)
+    thr = np.resize(np.array([0.3, 0.5, 0.7], np.float32), 65536)
+    bad_thr, bad_vote = _check(ctx, emb, thr)
+    assert bad_thr < 700 and bad_vote < 700      # margin rejections are reported, and rare
+
+
+def test_batch_independence(ctx):
+    """Size-independent property: a decision's result does not depend on its batch neighbours."""
+    emb = synth.make_embeddings(300, 8, 768, seed=11)
+    thr = np.full(300, 0.5, np.float32)
+    r1 = ctx.similarity_batch(emb, thr)
+    perm = np.random.default_rng(3).permutation(300)
+    r2 = ctx.similarity_batch(emb[perm], thr)
+    for a, b in zip(r1, r2):
+        assert np.array_equal(a[perm], b)
+
+
+def test_first_match_and_chunk_mean(ctx):
+    for case in GOLD["lesson_dedup"]:
+        q = np.array([case["new"]], np.float32)
+        rows = np.array([case["existing"]], np.float32)
+        idx, cos = ctx.first_match_batch(q, rows, np.array([case["threshold"]], np.float32))
+        assert int(idx[0]) == case["expect_index"], case["src"]
+    rng = np.random.default_rng(9)
+    q = rng.standard_normal((50, 256)).astype(np.float32)
+    rows = rng.standard_normal((50, 100, 256)).astype(np.float32)
+    rows[np.arange(50), rng.integers(0, 100, 50)] = q * 3.0     # plant an exact-direction match
+    thr = np.full(50, 0.9, np.float32)
+    idx, cos = ctx.first_match_batch(q, rows, thr)
+    for i in range(50):
+        assert idx[i] == numeric.first_match(q[i].astype(np.float64), rows[i].astype(np.float64), 0.9)
+    chunks = rng.standard_normal((7, 5, 3072)).astype(np.float32)
+    got = ctx.chunk_mean(chunks)
+    for g in range(7):
+        want = numeric.average_embeddings(chunks[g].astype(np.float64).tolist())
+        assert np.max(np.abs(got[g] - np.array(want))) < 1e-6
+    const = np.full((1, 4, 3072), 0.01, np.float32)              # reference: constant 0.01 chunks -> 0.01
+    assert np.allclose(ctx.chunk_mean(const), 0.01, atol=1e-9)
+
+
+def test_error_statuses(ctx):
+    with pytest.raises(native.QcError) as e:
+        ctx.similarity_batch(np.zeros((1, 65, 4), np.float32), np.zeros(1, np.float32))
+    assert e.value.atom == "bad_request"
+    with pytest.raises(native.QcError) as e:
+        ctx.embed_batch(np.zeros((1, 4), np.int32), np.array([4], np.int32))
+    assert e.value.atom == "not_configured"
