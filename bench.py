@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- consensus decisions/sec on B200 (BASELINE.json metric), one process per GPU.
+
+  python bench.py --gpus 1 --steps K --warmup W              # this build (CUDA, through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...    # CPU port of the reference path (rank 0 only)
+  torchrun ... bench.py --gpus N ...                         # N ranks, decisions sharded by agent
+
+A "step" is one pass of the hot path (K1 encode -> K2 finalise -> K3 similarity+vote) over one batch
+of 256 decisions per GPU (BASELINE config 2: 8-model pool, 512-token candidates, dim 768).  All inputs
+are synthetic (quoracle_b200/synth.py); the encoder is this build's definition with random weights.
+
+  value  : whole-job decisions/s with token ids already resident in HBM (CUDA events, max over ranks)
+  e2e    : the same metric through the host C-ABI call qc_decide_batch with pinned HOST buffers, the
+           host->device copy of the step's token ids and the device->host read of its verdicts inside
+           the timed region
+  roofline / cpu_baseline : see DESIGN.md "Measurement"
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "consensus decisions/sec (8-model, 512-tok)"
+UNIT = "decisions/s"
+POOL, TOKENS, DIM, VOCAB, AGENTS_PER_GPU = 8, 512, 768, 32768, 256
+ROTATE = 40                      # distinct input batches per rank: 40 x 4.2 MB = 168 MB > 126 MB L2
+E2E_ROTATE = 8
+WORKLOAD = (f"config 2: {POOL}-model pool, {AGENTS_PER_GPU} concurrent agents per GPU, {TOKENS}-token candidates, "
+            f"embedding dim {DIM}, vocab {VOCAB}, threshold 0.85")
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"bf16_burst": d.get("bf16_tflops"), "bf16_sustained": d.get("bf16_tflops_sustained"),
+                "hbm": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines: list[str] = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val.lower() == "active":
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU leg: the oracle's C port of the path (encoder + reference rule + N x N medoid), all host threads.
+# This is the ONLY place bench.py touches oracle/ (cpu_baseline and --impl reference).
+# ---------------------------------------------------------------------------------------------------
+def cpu_path(weights, token_ids, lens, thr, threads):
+    from oracle import cport
+    b, n, t = token_ids.shape
+    emb = cport.encode(weights.table_bf16, weights.w_bf16, token_ids.reshape(b * n, t), lens.reshape(b * n),
+                       threads=threads, f32=True, native=True)
+    ok, med, _ = cport.similarity_batch(emb.reshape(b, n, -1), thr.astype(np.float64), want_full=True,
+                                        threads=threads, want_cos=False, native=True)
+    return ok, med, emb
+
+
+def cpu_sim_only(emb, thr, threads):
+    from oracle import cport
+    t0 = time.perf_counter()
+    cport.similarity_batch(emb, thr.astype(np.float64), want_full=True, threads=threads, want_cos=False, native=True)
+    return time.perf_counter() - t0
+
+
+def cpu_threads() -> int:
+    from oracle import cport
+    return int(cport.max_threads(native=True))
+
+
+def calibrate_cpu_sample(weights, batch, threads, target_s):
+    """Pick how many decisions of the workload make ~target_s seconds of CPU work."""
+    t0 = time.perf_counter()
+    cpu_path(weights, batch.token_ids[:1], batch.lens[:1], batch.thr[:1], threads)   # also warms the library
+    t0 = time.perf_counter()
+    cpu_path(weights, batch.token_ids[:2], batch.lens[:2], batch.thr[:2], threads)
+    per = (time.perf_counter() - t0) / 2
+    return max(1, min(AGENTS_PER_GPU, int(target_s / max(per, 1e-6))))
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference path on the box's host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from quoracle_b200 import synth
+    weights = synth.make_encoder(DIM, VOCAB, seed=synth.BASE_SEED + 2)
+    batch = synth.make_decisions(AGENTS_PER_GPU, POOL, TOKENS, VOCAB, seed=synth.BASE_SEED + 2)
+    threads = cpu_threads()
+    sample = calibrate_cpu_sample(weights, batch, threads, target_s=1.0)
+    steps, warmup = args.steps, args.warmup
+    budget_s = 150.0                                   # keep the whole run within a few minutes
+    est = (steps + warmup) * 1.0                       # each step was sized to ~1 s
+    if est > budget_s:
+        sample = max(1, int(sample * budget_s / est))
+    for _ in range(warmup):
+        cpu_path(weights, batch.token_ids[:sample], batch.lens[:sample], batch.thr[:sample], threads)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        lo = (k * sample) % max(1, AGENTS_PER_GPU - sample + 1)
+        cpu_path(weights, batch.token_ids[lo:lo + sample], batch.lens[lo:lo + sample], batch.thr[lo:lo + sample], threads)
+    dt = time.perf_counter() - t0
+    value = sample * steps / dt
+    desc = (f"{sample} decisions per step ({sample * POOL} candidates x {TOKENS} tokens) of the same workload; "
+            f"C port of the path (f32 encoder + f64 reference rule + N x N medoid), OpenMP over candidates")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 encoder / f64 cosine", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "the reference's own Elixir path cannot run here (no BEAM); "
+                   "its embed step is a remote HTTP call with no local arithmetic, so the CPU arm times this "
+                   "build's encoder definition ported to C plus the restated reference rule"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU leg
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from quoracle_b200 import native, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+
+    weights = synth.make_encoder(DIM, VOCAB, seed=synth.BASE_SEED + 2)
+    ctx = native.Context(local, weights.table_bf16, weights.w_bf16)
+    if args.cta_group:
+        ctx.set_cta_group(args.cta_group)
+    b, n, t = AGENTS_PER_GPU, POOL, TOKENS
+
+    # Decisions shard by agent: rank r owns its own agents' decisions; no data-path collective.
+    batches = [synth.make_decisions(b, n, t, VOCAB, seed=synth.BASE_SEED + 2 + 1000 * rank + i) for i in range(ROTATE)]
+    d_tok = [torch.from_numpy(x.token_ids).to(dev) for x in batches]
+    d_len = [torch.from_numpy(x.lens).to(dev) for x in batches]
+    d_thr = [torch.from_numpy(x.thr).to(dev) for x in batches]
+    d_ok = torch.empty(b, dtype=torch.int32, device=dev)
+    d_med = torch.empty(b, dtype=torch.int32, device=dev)
+    # A dedicated non-default stream: handle 0 (torch's default stream) would mean "context stream" to
+    # the C ABI, and the CUDA events below must sit on the stream the kernels are launched on.
+    tstream = torch.cuda.Stream(device=dev)
+    stream = tstream.cuda_stream
+
+    def step(i):
+        j = i % ROTATE
+        ctx.decide_batch_dev(d_tok[j].data_ptr(), d_len[j].data_ptr(), b, n, t, d_thr[j].data_ptr(),
+                             d_ok.data_ptr(), d_med.data_ptr(), 0, 0, stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    ctx.check_status()
+    ctx.profile_reset()
+    ctx.profile_enable(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(tstream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record(tstream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count()
+    ctx.profile_enable(False)
+    stats = ctx.kernel_stats()
+    ctx.check_status()
+
+    # ---- e2e: host buffers through the C-ABI host entry point --------------------------------------
+    pinned_tok = [native.PinnedArray((b, n, t), np.int32) for _ in range(E2E_ROTATE)]
+    for k, pa in enumerate(pinned_tok):
+        pa.array[...] = batches[k].token_ids
+    pin_len = native.PinnedArray((b, n), np.int32)
+    pin_len.array[...] = batches[0].lens
+    pin_thr = native.PinnedArray((b,), np.float32)
+    pin_thr.array[...] = batches[0].thr
+    pin_ok = native.PinnedArray((b,), np.int32)
+    pin_med = native.PinnedArray((b,), np.int32)
+    out = native.DecideResult(pin_ok.array, pin_med.array, None, None)
+    e2e_steps = args.steps
+    for i in range(min(3, args.warmup)):
+        ctx.decide_batch(pinned_tok[i % E2E_ROTATE].array, pin_len.array, pin_thr.array, want_cos=False, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        ctx.decide_batch(pinned_tok[i % E2E_ROTATE].array, pin_len.array, pin_thr.array, want_cos=False, out=out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+    gpu_ok0, gpu_med0 = None, None
+    if rank == 0:
+        r0 = ctx.decide_batch(batches[0].token_ids, batches[0].lens, batches[0].thr, want_cos=False)
+        gpu_ok0, gpu_med0 = r0.ref_ok.copy(), r0.medoid.copy()
+
+    # ---- max over ranks ---------------------------------------------------------------------------
+    if world > 1:
+        tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(tt[0]), float(tt[1])
+    value = world * b * args.steps / (ms * 1e-3)
+    e2e_value = world * b * e2e_steps / e2e_s
+
+    if rank == 0:
+        peaks = measured_peaks()
+        k1 = stats["encode"]
+        k1_ms = k1["ms"] / max(1, k1["launches"])
+        flops = 2.0 * b * n * t * DIM * DIM                      # algorithmic encoder flops per launch
+        achieved = flops / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else 0.0
+        long_run = ms > 2000.0
+        peak = peaks["bf16_sustained"] if long_run else peaks["bf16_burst"]
+        traffic = None
+        tp = ROOT / "profiles" / "k1_traffic.json"
+        if tp.exists():
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        step_ms = ms / args.steps
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 (fp32 accumulate; fp32 similarity)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "decisions_per_gpu_per_step": b,
+                       "l2": f"inputs rotate over {ROTATE} batches per rank ({ROTATE * b * n * t * 4 / 1e6:.0f} MB "
+                             "> 126 MB L2); encoder table+weights (52 MB) are persistent state",
+                       "parallelism": f"agents sharded over {world} GPU(s), no data-path collective",
+                       "encoder": ctx.encoder_info(), "seed": synth.BASE_SEED + 2},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": b * n * t * 4 + b * n * 4 + b * 4,
+                    "d2h_bytes_per_step": 2 * b * 4, "steps": e2e_steps,
+                    "api": "qc_decide_batch (host C ABI), pinned host buffers, wall clock"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "qc_encode_kernel (K1)", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "peak_kind": ("sustained" if long_run else "burst") + ", " + peaks["source"],
+                         "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / step_ms if step_ms else None,
+                         "flops_per_launch": flops},
+            "kernels_ms_per_launch": {k: (v["ms"] / v["launches"] if v["launches"] else None) for k, v in stats.items()},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = cpu_threads()
+            sample = calibrate_cpu_sample(weights, batches[0], threads, target_s=args.cpu_seconds)
+            t0 = time.perf_counter()
+            ok, med, emb = cpu_path(weights, batches[0].token_ids[:sample], batches[0].lens[:sample],
+                                    batches[0].thr[:sample], threads)
+            dt = time.perf_counter() - t0
+            sim_dt = cpu_sim_only(emb.reshape(sample, n, -1), batches[0].thr[:sample], 1)
+            line["cpu_baseline"] = {
+                "value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"first {sample} decisions of batch 0 ({sample * n} candidates x {t} tokens), C port of the "
+                          f"whole path, {dt:.1f} s",
+                "similarity_only_1thread_decisions_per_s": sample / sim_dt if sim_dt > 0 else None,
+                "index_mismatch_vs_gpu": {"ref_ok": int((ok != gpu_ok0[:sample]).sum()),
+                                          "medoid": int((med != gpu_med0[:sample]).sum()), "checked": int(sample)},
+            }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--cta-group", type=int, default=0, help="force the K1 variant (1 or 2); 0 = library default")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="size of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
