@@ -180,8 +180,18 @@ int qc_profile_reset(qc_ctx* ctx);
 int qc_kernel_stats(qc_ctx* ctx, double ms[QC_K_COUNT], uint64_t launches[QC_K_COUNT]);
 /* Encoder tiling in use: cta_group (1|2), token block, W stages. Returns QC_OK / NOT_CONFIGURED. */
 int qc_encoder_info(const qc_ctx* ctx, int32_t* cta_group, int32_t* token_block, int32_t* w_stages);
+/*
+ * Tuning aid for K1: when enabled, every encoder launch records, per CTA, the cycles each warp role
+ * spent in total and blocked on its barriers; a call with out != NULL returns the per-CTA averages of
+ * the LAST launch: [0] MMA issuer total, [1] waiting for W tiles, [2] waiting for gathered tokens,
+ * [3] waiting for a free accumulator, [4] epilogue total, [5] waiting for accumulators, [6] gather
+ * total, [7] waiting for free token buffers, [8] W producer total, [9] waiting for free W stages.
+ */
+int qc_encoder_stall_profile(qc_ctx* ctx, int enable, double out[16]);
 /* Test hook: force the encoder variant (cta_group 1 or 2) for subsequent launches. */
 int qc_encoder_set_cta_group(qc_ctx* ctx, int cta_group);
+/* Test/tuning hook: select the K1 tiling (tokens per resident block, CTAs per MMA group, W stage k-width). */
+int qc_encoder_set_variant(qc_ctx* ctx, int token_block, int cta_group, int w_bk);
 
 #ifdef __cplusplus
 }

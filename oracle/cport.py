@@ -29,7 +29,10 @@ def build(native: bool = False, force: bool = False) -> Path:
         return out
     march = "native" if native else "x86-64-v3"
     tmp = out.with_suffix(f".{os.getpid()}.tmp")
-    cmd = [_GCC, "-O3", f"-march={march}", "-fopenmp", "-fPIC", "-shared", "-o", str(tmp), str(src), "-lm"]
+    # -ffp-contract=off: BEAM never fuses a*b+c, so the f64 restatements must not either (the timed f32
+    # encoder re-enables contraction with a function attribute)
+    cmd = [_GCC, "-O3", f"-march={march}", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-o", str(tmp),
+           str(src), "-lm"]
     subprocess.run(cmd, check=True, capture_output=True)
     os.replace(tmp, out)
     return out

@@ -182,6 +182,7 @@ void qo_encode_f64(const uint16_t* table, const uint16_t* w, int vocab, int D, c
 
 /* Timed CPU baseline version: f32, 4-token register/L1 blocking, vectorisable inner loops, tanhf.
  * Same function as qo_encode_f64 up to f32 rounding.  out f32 [R x D]. */
+__attribute__((optimize("fp-contract=fast")))
 void qo_encode_f32(const uint16_t* table, const uint16_t* w, int vocab, int D, const int32_t* token_ids,
                    const int32_t* lens, int R, int T, int threads, float* out) {
   float* wf = (float*)aligned_alloc(64, sizeof(float) * (size_t)D * D);

@@ -86,12 +86,14 @@ __device__ __forceinline__ bool hang_check(int32_t* dbg, long long t0, int tag) 
   }
   return false;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int32_t* dbg, int tag) {
-  if (mbar_try_wait(bar, parity)) return;
+// Returns the cycles spent waiting (0 when the phase had already completed).
+__device__ __forceinline__ long long mbar_wait(uint64_t* bar, uint32_t parity, int32_t* dbg, int tag) {
+  if (mbar_try_wait(bar, parity)) return 0;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (hang_check(dbg, t0, tag)) return;
+    if (hang_check(dbg, t0, tag)) break;
   }
+  return clock64() - t0;
 }
 // Acquire at cluster scope (needed when the arrivals come from the peer CTA).
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
@@ -107,12 +109,13 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int32_t* dbg, int tag) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
+__device__ __forceinline__ long long mbar_wait_cluster(uint64_t* bar, uint32_t parity, int32_t* dbg, int tag) {
+  if (mbar_try_wait_cluster(bar, parity)) return 0;
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (hang_check(dbg, t0, tag)) return;
+    if (hang_check(dbg, t0, tag)) break;
   }
+  return clock64() - t0;
 }
 
 // ---- cluster ------------------------------------------------------------------------
@@ -209,6 +212,16 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;          // SWIZZLE_128B
   return d;
 }
+// Same, SWIZZLE_64B: 32 bf16 (=64 B) per row, 8-row groups 512 B apart (layout code 4).
+__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;   // SBO: 8 rows * 64 B
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;          // SWIZZLE_64B
+  return d;
+}
 
 // Instruction descriptor for kind::f16: bf16 x bf16 -> f32, both operands K-major.
 //   [4,6) c_format=1 (f32) | [7,10) a_format=1 (bf16) | [10,13) b_format=1 | [15] a_major=0 | [16] b_major=0
@@ -269,6 +282,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }

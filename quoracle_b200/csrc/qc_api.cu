@@ -69,14 +69,16 @@ struct qc_ctx {
   cudaStream_t stream = nullptr;
   // encoder
   bool has_encoder = false;
-  int dim = 0, vocab = 0, cta_group = 1;
+  int dim = 0, vocab = 0;
+  qc::EncoderVariant variant{0, 0, 0};
   uint16_t* d_table = nullptr;
   uint16_t* d_wt = nullptr;  // W^T [dim(out) x dim(in)] bf16
-  CUtensorMap w_tmap;
+  CUtensorMap w_tmap64, w_tmap32;
   int32_t* d_err = nullptr;   // int32[8] device status words
   int32_t hang[4] = {};
   // workspaces
-  DevBuf part, emb, tok, lens, thr, cosm, refok, medoid, q, rows, idx;
+  DevBuf part, emb, tok, lens, thr, cosm, refok, medoid, q, rows, idx, stall;
+  bool stall_on = false;
   HostBuf h_in, h_out;
   // counters / profiling
   uint64_t launches = 0;
@@ -176,11 +178,16 @@ int make_w_tmap(qc_ctx* c) {
   EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(c->dim), static_cast<cuuint64_t>(c->dim)};  // {k, feature}
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(c->dim) * 2};
-  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t box64[2] = {64, 128};
+  const cuuint32_t box32[2] = {32, 128};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(&c->w_tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->d_wt, gdim, gstride, box, estr,
+  CUresult r = enc(&c->w_tmap64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->d_wt, gdim, gstride, box64, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return QC_ERR_CUDA;
+  r = enc(&c->w_tmap32, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->d_wt, gdim, gstride, box32, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? QC_OK : QC_ERR_CUDA;
 }
 
@@ -230,23 +237,25 @@ int d2h(qc_ctx* c, void* user, const void* dsrc, size_t bytes, size_t* stage_off
 size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
 
 int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, int T, float* d_emb, cudaStream_t s) {
-  const int TB = qc::encoder_token_block(c->dim);
+  const int TB = c->variant.token_block;
   const int bpc = (T + TB - 1) / TB;
   QC_CUDA(c->part.ensure(static_cast<size_t>(R) * bpc * c->dim * sizeof(float)));
   {
     KernelScope ks(c, QC_K_ENCODE, s);
     qc::EncoderLaunch a;
-    a.w_tmap = &c->w_tmap;
+    a.w_tmap64 = &c->w_tmap64;
+    a.w_tmap32 = &c->w_tmap32;
     a.table = c->d_table;
     a.token_ids = d_tok;
     a.lens = d_lens;
     a.part = static_cast<float*>(c->part.p);
     a.err_flag = c->d_err;
+    a.stall = c->stall_on ? static_cast<unsigned long long*>(c->stall.p) : nullptr;
     a.R = R;
     a.T = T;
     a.dim = c->dim;
     a.vocab = c->vocab;
-    a.cta_group = c->cta_group;
+    a.variant = c->variant;
     a.num_sms = c->num_sms;
     a.stream = s;
     QC_CUDA(qc::launch_encode(a));
@@ -342,7 +351,7 @@ int qc_ctx_create(qc_ctx** out, int device_id, const qc_encoder_cfg* enc) {
   if (prop.major != 10) return QC_ERR_NO_DEVICE;  // kernels are sm_100a only
   if (enc != nullptr) {
     if (enc->table_bf16 == nullptr || enc->w_bf16 == nullptr || enc->vocab <= 0) return QC_ERR_INVALID_INPUT;
-    if (!qc::encoder_supports(enc->dim, 1)) return QC_ERR_UNSUPPORTED;
+    if (qc::encoder_default_variant(enc->dim).token_block == 0) return QC_ERR_UNSUPPORTED;
   }
   qc_ctx* c = new (std::nothrow) qc_ctx();
   if (c == nullptr) return QC_ERR_OUT_OF_MEMORY;
@@ -368,9 +377,7 @@ int qc_ctx_create(qc_ctx** out, int device_id, const qc_encoder_cfg* enc) {
       if ((st = cuda_status(cudaMemcpy(c->d_wt, wt.data(), wb, cudaMemcpyHostToDevice))) != QC_OK) break;
       if ((st = make_w_tmap(c)) != QC_OK) break;
       c->has_encoder = true;
-      c->cta_group = 1;
-      const char* cg = getenv("QC_CTA_GROUP");
-      if (cg != nullptr && cg[0] == '2' && qc::encoder_supports(c->dim, 2)) c->cta_group = 2;
+      c->variant = qc::encoder_default_variant(c->dim);
     }
   } while (false);
   if (st != QC_OK) {
@@ -398,6 +405,7 @@ void qc_ctx_destroy(qc_ctx* c) {
   c->q.release();
   c->rows.release();
   c->idx.release();
+  c->stall.release();
   c->h_in.release();
   c->h_out.release();
   if (c->d_table) cudaFree(c->d_table);
@@ -465,17 +473,57 @@ int qc_kernel_stats(qc_ctx* c, double ms[QC_K_COUNT], uint64_t launches[QC_K_COU
 int qc_encoder_info(const qc_ctx* c, int32_t* cta_group, int32_t* token_block, int32_t* w_stages) {
   if (c == nullptr) return QC_ERR_INVALID_INPUT;
   if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
-  if (cta_group) *cta_group = c->cta_group;
-  if (token_block) *token_block = qc::encoder_token_block(c->dim);
-  if (w_stages) *w_stages = qc::encoder_w_stages(c->dim, c->cta_group);
+  if (cta_group) *cta_group = c->variant.cta_group;
+  if (token_block) *token_block = c->variant.token_block;
+  if (w_stages) *w_stages = qc::encoder_variant_w_stages(c->dim, c->variant);
+  return QC_OK;
+}
+
+int qc_encoder_stall_profile(qc_ctx* c, int enable, double out[16]) {
+  if (c == nullptr) return QC_ERR_INVALID_INPUT;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  DeviceGuard g(c->device);
+  const size_t n = static_cast<size_t>(c->num_sms) * 16;
+  QC_CUDA(cudaDeviceSynchronize());
+  if (out != nullptr && c->stall.p != nullptr) {
+    std::vector<unsigned long long> h(n);
+    QC_CUDA(cudaMemcpy(h.data(), c->stall.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    int cnt[16] = {};
+    for (int k = 0; k < 16; ++k) out[k] = 0.0;
+    for (int b = 0; b < c->num_sms; ++b) {
+      for (int k = 0; k < 16; ++k) {
+        const int total_slot = k < 4 ? 0 : (k < 6 ? 4 : (k < 8 ? 6 : (k < 10 ? 8 : k)));
+        if (h[b * 16 + total_slot] == 0) continue;   // role did not run in this CTA (e.g. MMA in the peer CTA)
+        out[k] += static_cast<double>(h[b * 16 + k]);
+        cnt[k]++;
+      }
+    }
+    for (int k = 0; k < 16; ++k) out[k] = cnt[k] ? out[k] / cnt[k] : 0.0;
+  }
+  if (enable) {
+    QC_CUDA(c->stall.ensure(n * sizeof(unsigned long long)));
+    QC_CUDA(cudaMemset(c->stall.p, 0, n * sizeof(unsigned long long)));
+  }
+  c->stall_on = enable != 0;
   return QC_OK;
 }
 
 int qc_encoder_set_cta_group(qc_ctx* c, int cta_group) {
   if (c == nullptr) return QC_ERR_INVALID_INPUT;
   if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
-  if (!qc::encoder_supports(c->dim, cta_group)) return QC_ERR_UNSUPPORTED;
-  c->cta_group = cta_group;
+  qc::EncoderVariant v = c->variant;
+  v.cta_group = cta_group;
+  if (!qc::encoder_variant_supported(c->dim, v)) return QC_ERR_UNSUPPORTED;
+  c->variant = v;
+  return QC_OK;
+}
+
+int qc_encoder_set_variant(qc_ctx* c, int token_block, int cta_group, int w_bk) {
+  if (c == nullptr) return QC_ERR_INVALID_INPUT;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  const qc::EncoderVariant v{token_block, cta_group, w_bk};
+  if (!qc::encoder_variant_supported(c->dim, v)) return QC_ERR_UNSUPPORTED;
+  c->variant = v;
   return QC_OK;
 }
 

@@ -6,22 +6,32 @@
 
 namespace qc {
 
+// K1 tiling variant: tokens per resident block, CTAs per MMA group (1 | 2), k-width of a streamed W stage.
+struct EncoderVariant {
+  int token_block;
+  int cta_group;
+  int w_bk;
+};
+
 struct EncoderLaunch {
-  const CUtensorMap* w_tmap;   // host copy, passed by value as a __grid_constant__ parameter
+  const CUtensorMap* w_tmap64; // W^T, box 64 x 128, 128-byte swizzle (host copy; passed __grid_constant__)
+  const CUtensorMap* w_tmap32; // W^T, box 32 x 128, 64-byte swizzle
   const uint16_t* table;       // device, bf16 [vocab x dim]
   const int32_t* token_ids;    // device [R x T]
   const int32_t* lens;         // device [R]
   float* part;                 // device [R x ceil(T/TB) x dim]
   int32_t* err_flag;           // device int32[8]: [0..3] watchdog record, [4] token-range flag
-  int R, T, dim, vocab, cta_group, num_sms;
+  unsigned long long* stall;   // device [grid x 16] per-role stall cycles, or nullptr
+  int R, T, dim, vocab, num_sms;
+  EncoderVariant variant;
   cudaStream_t stream;
 };
 
 // K1
 cudaError_t launch_encode(const EncoderLaunch& a);
-int encoder_token_block(int dim);
-int encoder_w_stages(int dim, int cta_group);
-bool encoder_supports(int dim, int cta_group);
+bool encoder_variant_supported(int dim, const EncoderVariant& v);
+int encoder_variant_w_stages(int dim, const EncoderVariant& v);
+EncoderVariant encoder_default_variant(int dim);
 
 // K2: emb[r, :] = L2normalise( (sum_j part[r, j, :]) / len[r] ), j < ceil(len/TB); len == 0 -> zeros.
 cudaError_t launch_finalize(const float* part, const int32_t* lens, float* emb, int R, int bpc, int TB, int dim,

@@ -2,10 +2,10 @@
 //
 // Computes, for every candidate row r and every block j of TB consecutive token slots,
 //   part[r, j, d] = sum_{t in block j, t < len[r]} GELU_tanh( sum_k E[tok[r,t], k] * W[k, d] )
-// K2 (qc_finalize.cu) adds the blocks in a fixed order, divides by len and L2-normalises.
-// This is the local stand-in for the provider call behind Embeddings.get_embedding/2
-// (reference lib/quoracle/models/embeddings.ex:277-298); the encoder definition is this
-// build's, the reference fixes none.
+// K2 (qc_similarity.cu: qc_finalize_kernel) adds the blocks in a fixed order, divides by len and
+// L2-normalises.  This is the local stand-in for the provider call behind
+// Embeddings.get_embedding/2 (reference lib/quoracle/models/embeddings.ex:277-298); the encoder
+// definition is this build's, the reference fixes none.
 //
 // Tiling (DESIGN.md "K1"): the GEMM is issued TRANSPOSED -- M = output features (TMEM lanes),
 // N = tokens (TMEM columns) -- so that the token mean is a per-thread sum over the columns a
@@ -13,13 +13,18 @@
 //   * the TB x D bf16 token rows of one block are gathered from the embedding table with
 //     cp.async (16 B chunks, written in the 128-byte-swizzled K-major layout tcgen05 expects)
 //     and stay RESIDENT in shared memory: KB = D/64 k-blocks of TB x 128 B;
-//   * W^T tiles (128 features x 64 k, 16 KB) stream through a W_STAGES-deep TMA ring;
+//   * W^T tiles (128 features x WBK k) stream through a W_STAGES-deep TMA ring (WBK = 64 with
+//     128-byte swizzle, or 32 with 64-byte swizzle for a finer-grained, deeper ring);
 //   * D/128 (or D/256 for a CTA pair) feature tiles reuse the resident tokens; the k-block
 //     buffers are released one by one during the last feature tile so the next block's gather
 //     overlaps the tail of this one;
 //   * accumulators live in TMEM (2 stages), read back by 4 epilogue warps with tcgen05.ld.
 // CG == 2 runs a CTA pair (cta_group::2): M = 256 features split across the pair, N = 2*TB
 // tokens (each CTA's resident block is half of the B operand), one MMA issuer in the leader.
+//
+// Shared-memory bandwidth is the co-limiter (ncu: l1tex tc wavefronts == tensor active): each
+// K=16 MMA reads (M + N) x 32 B of operands, and streamed W bytes are also WRITTEN once, so the
+// pair variant (half the W bytes per CTA per flop) is the fast one.
 //
 // Warp roles (320 threads): 0-3 epilogue (TMEM lane quadrant = warp id), 4-7 gather,
 // 8 W-tile TMA producer, 9 MMA issuer + TMEM allocator.
@@ -30,30 +35,35 @@ namespace qc {
 
 using namespace ptx;
 
-template <int D_, int TB_, int CG_>
+template <int D_, int TB_, int CG_, int WBK_>
 struct EncTraits {
   static constexpr int D = D_;
   static constexpr int TB = TB_;
   static constexpr int CG = CG_;
-  static constexpr int BK = 64;                   // bf16 elements per 128-byte swizzle row
-  static constexpr int KB = D / BK;               // resident k-blocks
+  static constexpr int WBK = WBK_;                // k elements per streamed W stage
+  static constexpr int BK = 64;                   // bf16 elements per 128-byte swizzle row (token tiles)
+  static constexpr int KB = D / BK;               // resident token k-blocks
+  static constexpr int NWS = D / WBK;             // W stages per feature tile
   static constexpr int MT = 128 * CG;             // features per MMA tile over the CTA group
   static constexpr int NFT = D / MT;              // feature tiles
   static constexpr int UMMA_N = TB * CG;          // tokens per MMA tile
   static constexpr int TOK_KB_BYTES = TB * 128;
   static constexpr int TOK_BYTES = KB * TOK_KB_BYTES;
-  static constexpr int W_STAGE_BYTES = 128 * 128;
+  static constexpr int TOK_BYTES_PAD = (TOK_BYTES + 1023) & ~1023;
+  static constexpr int W_STAGE_BYTES = 128 * WBK * 2;
   static constexpr int BAR_BYTES = 1024;
   static constexpr int SMEM_MAX = 232448;         // 227 KB opt-in limit
-  static constexpr int W_STAGES_FIT = (SMEM_MAX - 1024 - BAR_BYTES - TOK_BYTES) / W_STAGE_BYTES;
+  static constexpr int W_STAGES_FIT = (SMEM_MAX - 1024 - BAR_BYTES - TOK_BYTES_PAD) / W_STAGE_BYTES;
   static constexpr int W_STAGES = W_STAGES_FIT > 8 ? 8 : W_STAGES_FIT;
   static constexpr int ACC_STAGES = 2;
-  static constexpr int TMEM_COLS = ACC_STAGES * UMMA_N;  // 128 / 256 / 512: powers of two >= 32
-  static constexpr int SMEM_BYTES = 1024 + TOK_BYTES + W_STAGES * W_STAGE_BYTES + BAR_BYTES;
+  static constexpr int ACC_COLS = UMMA_N <= 64 ? 64 : (UMMA_N <= 128 ? 128 : 256);
+  static constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;   // 128 / 256 / 512: powers of two >= 32
+  static constexpr int SMEM_BYTES = 1024 + TOK_BYTES_PAD + W_STAGES * W_STAGE_BYTES + BAR_BYTES;
   static constexpr int GATHER_LAG = 4;            // cp.async groups in flight per gather thread
+  static_assert(WBK == 64 || WBK == 32, "W stage width is 64 (SW128) or 32 (SW64)");
   static_assert(D % MT == 0, "feature tiles must cover D");
   static_assert(D % BK == 0, "k-blocks must cover D");
-  static_assert(TB % 32 == 0 && UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid UMMA N");
+  static_assert(TB % 16 == 0 && UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid token block");
   static_assert(W_STAGES >= 2, "need at least two W stages");
   static_assert(KB > GATHER_LAG, "gather lag must be below the k-block count");
   static_assert((2 * W_STAGES + 2 * KB + 2 * ACC_STAGES) * 8 + 8 <= BAR_BYTES, "barrier region too small");
@@ -79,22 +89,52 @@ __device__ __forceinline__ int block_valid(const int32_t* __restrict__ lens, int
   return v > TB ? TB : v;
 }
 
+// Sum of GELU over NCOL consecutive TMEM columns of this thread's lane, software-pipelined:
+// the next 32-column load is in flight while the current one is consumed.
+template <int NCOL>
+__device__ __forceinline__ float gelu_sum_columns(uint32_t taddr) {
+  static_assert(NCOL % 16 == 0, "column count must be a multiple of 16");
+  constexpr int FULL = NCOL / 32;
+  constexpr bool TAIL = (NCOL % 32) != 0;
+  float sum = 0.f;
+  uint32_t va[32], vb[32];
+  if constexpr (FULL > 0) tmem_ld_32x32b_x32(taddr, va);
+#pragma unroll
+  for (int c = 0; c < FULL; ++c) {
+    tmem_ld_wait();
+    if (c + 1 < FULL) {
+      if (c & 1) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, va); else tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sum += gelu_tanh(__uint_as_float((c & 1) ? vb[i] : va[i]));
+  }
+  if constexpr (TAIL) {
+    uint32_t vt[16];
+    tmem_ld_32x32b_x16(taddr + FULL * 32, vt);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sum += gelu_tanh(__uint_as_float(vt[i]));
+  }
+  return sum;
+}
+
 template <class Tr>
 __global__ void __launch_bounds__(kEncThreads, 1)
-qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D x D] bf16, box 64 x 128, SW128
+qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D x D] bf16, box WBK x 128
                  const uint16_t* __restrict__ table,                   // E [vocab x D] bf16
                  const int32_t* __restrict__ token_ids,                // [R x T]
                  const int32_t* __restrict__ lens,                     // [R]
                  float* __restrict__ part,                             // [R x bpc x D]
                  int32_t* __restrict__ dbg,                            // [0..3] watchdog, [4] token-range flag
+                 unsigned long long* __restrict__ stall,               // optional [grid x 16] per-role stall cycles
                  int R, int T, int bpc, int vocab) {
-  constexpr int D = Tr::D, TB = Tr::TB, CG = Tr::CG, KB = Tr::KB, NFT = Tr::NFT;
-  constexpr int UMMA_N = Tr::UMMA_N, WS = Tr::W_STAGES, LAG = Tr::GATHER_LAG;
+  constexpr int D = Tr::D, TB = Tr::TB, CG = Tr::CG, KB = Tr::KB, NFT = Tr::NFT, WBK = Tr::WBK, NWS = Tr::NWS;
+  constexpr int UMMA_N = Tr::UMMA_N, WS = Tr::W_STAGES, LAG = Tr::GATHER_LAG, ACC_COLS = Tr::ACC_COLS;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* tok_smem = smem;                                  // KB x (TB x 128 B), 1024-aligned each
-  uint8_t* w_smem = smem + Tr::TOK_BYTES;                    // WS x 16 KB
+  uint8_t* tok_smem = smem;                                  // KB x (TB x 128 B)
+  uint8_t* w_smem = smem + Tr::TOK_BYTES_PAD;                // WS x W_STAGE_BYTES, 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + WS * Tr::W_STAGE_BYTES);
   uint64_t* w_full = bars;
   uint64_t* w_empty = w_full + WS;
@@ -144,6 +184,8 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
     const int row = warp * 32 + lane;                         // feature row inside this CTA's tile half
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
     uint32_t acc_iter = 0;
+    long long st_wait = 0;
+    const long long st_t0 = clock64();
     for (int item = group; item < nitems; item += ngroups) {
       int valid[CG];
       bool any = false;
@@ -155,30 +197,29 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
       if (!any) continue;
       for (int ft = 0; ft < NFT; ++ft, ++acc_iter) {
         const uint32_t as = acc_iter & 1u;
-        mbar_wait(&acc_full[as], (acc_iter >> 1) & 1u, dbg, 100 + ft);
+        st_wait += mbar_wait(&acc_full[as], (acc_iter >> 1) & 1u, dbg, 100 + ft);
         tcgen05_fence_after();
+        float sums[CG];
 #pragma unroll
-        for (int s = 0; s < CG; ++s) {
-          float sum = 0.f;
-#pragma unroll 1
-          for (int c0 = 0; c0 < TB; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_base + lane_addr + as * UMMA_N + s * TB + c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sum += gelu_tanh(__uint_as_float(v[i]));
-          }
-          if (valid[s] > 0) {
-            const size_t blk = static_cast<size_t>(item) * CG + s;
-            part[blk * D + ft * Tr::MT + rank * 128 + row] = sum;
-          }
-        }
+        for (int s = 0; s < CG; ++s) sums[s] = gelu_sum_columns<TB>(tmem_base + lane_addr + as * ACC_COLS + s * TB);
+        // the accumulator stage is free as soon as its columns are in registers
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
           if constexpr (CG == 2) mbar_arrive_cluster(&acc_empty[as], 0); else mbar_arrive(&acc_empty[as]);
         }
+#pragma unroll
+        for (int s = 0; s < CG; ++s) {
+          if (valid[s] > 0) {
+            const size_t blk = static_cast<size_t>(item) * CG + s;
+            part[blk * D + ft * Tr::MT + rank * 128 + row] = sums[s];
+          }
+        }
       }
+    }
+    if (stall != nullptr && threadIdx.x == 0) {
+      stall[blockIdx.x * 16 + 4] = static_cast<unsigned long long>(clock64() - st_t0);
+      stall[blockIdx.x * 16 + 5] = static_cast<unsigned long long>(st_wait);
     }
   } else if (warp < 8) {
     // ===================== gather: table rows -> swizzled resident token tiles ==============
@@ -189,6 +230,8 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
     // swizzle: chunk index XOR (row mod 8); rows of one thread are congruent mod 16 so it is constant
     const uint32_t dst_off0 = static_cast<uint32_t>(r16 * 128 + ((c ^ (r16 & 7)) << 4));
     uint32_t it = 0;
+    long long st_wait = 0;
+    const long long st_t0 = clock64();
     for (int item = group; item < nitems; item += ngroups) {
       bool any = false;
 #pragma unroll
@@ -216,7 +259,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
       const uint32_t par_empty = (it & 1u) ^ 1u;
 #pragma unroll 1
       for (int kb = 0; kb < KB; ++kb) {
-        mbar_wait(&tok_empty[kb], par_empty, dbg, 200 + kb);
+        st_wait += mbar_wait(&tok_empty[kb], par_empty, dbg, 200 + kb);
         const uint32_t dst = tok_base + kb * Tr::TOK_KB_BYTES + dst_off0;
 #pragma unroll
         for (int q = 0; q < TB / 16; ++q) cp_async_16(dst + q * 2048, src[q] + kb * 64, nbytes[q]);
@@ -241,39 +284,52 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
       }
       ++it;
     }
+    if (stall != nullptr && threadIdx.x == 128) {
+      stall[blockIdx.x * 16 + 6] = static_cast<unsigned long long>(clock64() - st_t0);
+      stall[blockIdx.x * 16 + 7] = static_cast<unsigned long long>(st_wait);
+    }
   } else if (warp == 8) {
     // ===================== W^T tile producer (TMA) =========================================
     if (lane == 0) {
       uint32_t wi = 0;
+      long long st_wait = 0;
+      const long long st_t0 = clock64();
       for (int item = group; item < nitems; item += ngroups) {
         bool any = false;
 #pragma unroll
         for (int s = 0; s < CG; ++s) any |= block_valid(lens, item * CG + s, nblocks, bpc, TB) > 0;
         if (!any) continue;
         for (int ft = 0; ft < NFT; ++ft) {
-          for (int kb = 0; kb < KB; ++kb, ++wi) {
+          for (int ws = 0; ws < NWS; ++ws, ++wi) {
             const uint32_t s = wi % WS;
             const uint32_t ph = (wi / WS) & 1u;
-            mbar_wait(&w_empty[s], ph ^ 1u, dbg, 300 + static_cast<int>(s));
+            st_wait += mbar_wait(&w_empty[s], ph ^ 1u, dbg, 300 + static_cast<int>(s));
             void* dst = w_smem + s * Tr::W_STAGE_BYTES;
             if constexpr (CG == 2) {
               if (leader) mbar_expect_tx(&w_full[s], 2 * Tr::W_STAGE_BYTES);
-              tma_load_2d_pair(dst, &w_tmap, &w_full[s], kb * 64, ft * Tr::MT + static_cast<int>(rank) * 128);
+              tma_load_2d_pair(dst, &w_tmap, &w_full[s], ws * WBK, ft * Tr::MT + static_cast<int>(rank) * 128);
             } else {
               mbar_expect_tx(&w_full[s], Tr::W_STAGE_BYTES);
-              tma_load_2d(dst, &w_tmap, &w_full[s], kb * 64, ft * Tr::MT);
+              tma_load_2d(dst, &w_tmap, &w_full[s], ws * WBK, ft * Tr::MT);
             }
           }
         }
+      }
+      if (stall != nullptr) {
+        stall[blockIdx.x * 16 + 8] = static_cast<unsigned long long>(clock64() - st_t0);
+        stall[blockIdx.x * 16 + 9] = static_cast<unsigned long long>(st_wait);
       }
     }
   } else {
     // ===================== MMA issuer (leader CTA, one lane) ================================
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(Tr::MT, UMMA_N);
+      constexpr int WPK = 64 / WBK;                              // W stages per token k-block
       const uint32_t w_base = smem_u32(w_smem);
       const uint32_t tok_base = smem_u32(tok_smem);
       uint32_t wi = 0, acc_iter = 0, it = 0;
+      long long st_w = 0, st_tok = 0, st_acc = 0;
+      const long long st_t0 = clock64();
       for (int item = group; item < nitems; item += ngroups) {
         bool any = false;
 #pragma unroll
@@ -281,31 +337,41 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
         if (!any) continue;
         for (int ft = 0; ft < NFT; ++ft, ++acc_iter) {
           const uint32_t as = acc_iter & 1u;
-          if constexpr (CG == 2) mbar_wait_cluster(&acc_empty[as], ((acc_iter >> 1) & 1u) ^ 1u, dbg, 400 + ft);
-          else mbar_wait(&acc_empty[as], ((acc_iter >> 1) & 1u) ^ 1u, dbg, 400 + ft);
+          if constexpr (CG == 2) st_acc += mbar_wait_cluster(&acc_empty[as], ((acc_iter >> 1) & 1u) ^ 1u, dbg, 400 + ft);
+          else st_acc += mbar_wait(&acc_empty[as], ((acc_iter >> 1) & 1u) ^ 1u, dbg, 400 + ft);
           tcgen05_fence_after();
-          const uint32_t tmem_d = tmem_base + as * UMMA_N;
-          for (int kb = 0; kb < KB; ++kb, ++wi) {
-            if (ft == 0) {
-              if constexpr (CG == 2) mbar_wait_cluster(&tok_full[kb], it & 1u, dbg, 500 + kb);
-              else mbar_wait(&tok_full[kb], it & 1u, dbg, 500 + kb);
+          const uint32_t tmem_d = tmem_base + as * ACC_COLS;
+          for (int ws = 0; ws < NWS; ++ws, ++wi) {
+            const int kb = ws / WPK;                              // token k-block this W stage multiplies
+            const int sub = ws % WPK;                             // which WBK-wide part of it
+            if (ft == 0 && sub == 0) {
+              if constexpr (CG == 2) st_tok += mbar_wait_cluster(&tok_full[kb], it & 1u, dbg, 500 + kb);
+              else st_tok += mbar_wait(&tok_full[kb], it & 1u, dbg, 500 + kb);
             }
             const uint32_t s = wi % WS;
-            mbar_wait(&w_full[s], (wi / WS) & 1u, dbg, 600 + static_cast<int>(s));
+            st_w += mbar_wait(&w_full[s], (wi / WS) & 1u, dbg, 600 + static_cast<int>(s));
             tcgen05_fence_after();
-            const uint64_t adesc = make_kmajor_sw128_desc(w_base + s * Tr::W_STAGE_BYTES);
-            const uint64_t bdesc = make_kmajor_sw128_desc(tok_base + kb * Tr::TOK_KB_BYTES);
+            const uint64_t adesc = (WBK == 64) ? make_kmajor_sw128_desc(w_base + s * Tr::W_STAGE_BYTES)
+                                               : make_kmajor_sw64_desc(w_base + s * Tr::W_STAGE_BYTES);
+            // token tile: 128-byte rows; this stage covers bytes [sub*WBK*2, +WBK*2) of each row
+            const uint64_t bdesc = make_kmajor_sw128_desc(tok_base + kb * Tr::TOK_KB_BYTES) + sub * (WBK * 2 / 16);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // +32 bytes per 16-element k step inside the 128-byte swizzle row (>>4 => +2)
-              umma_bf16<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < WBK / 16; ++k) {
+              // +32 bytes per 16-element k step inside the swizzle row (descriptor units of 16 B => +2)
+              umma_bf16<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ws | k) != 0 ? 1u : 0u);
             }
-            umma_commit<CG>(&w_empty[s]);                       // W stage reusable once these MMAs retire
-            if (ft == NFT - 1) umma_commit<CG>(&tok_empty[kb]);  // token k-block free for the next gather
+            umma_commit<CG>(&w_empty[s]);                         // W stage reusable once these MMAs retire
+            if (ft == NFT - 1 && sub == WPK - 1) umma_commit<CG>(&tok_empty[kb]);   // token k-block free
           }
           umma_commit<CG>(&acc_full[as]);
         }
         ++it;
+      }
+      if (stall != nullptr) {
+        stall[blockIdx.x * 16 + 0] = static_cast<unsigned long long>(clock64() - st_t0);
+        stall[blockIdx.x * 16 + 1] = static_cast<unsigned long long>(st_w);
+        stall[blockIdx.x * 16 + 2] = static_cast<unsigned long long>(st_tok);
+        stall[blockIdx.x * 16 + 3] = static_cast<unsigned long long>(st_acc);
       }
     }
   }
@@ -354,37 +420,48 @@ static cudaError_t launch_encode_t(const EncoderLaunch& a) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, *a.w_tmap, a.table, a.token_ids, a.lens, a.part, a.err_flag, a.R, a.T,
-                            bpc, a.vocab);
+  const CUtensorMap* tm = Tr::WBK == 64 ? a.w_tmap64 : a.w_tmap32;
+  return cudaLaunchKernelEx(&cfg, kern, *tm, a.table, a.token_ids, a.lens, a.part, a.err_flag, a.stall, a.R, a.T, bpc,
+                            a.vocab);
 }
 
-int encoder_token_block(int dim) { return dim == 1536 ? 64 : 128; }
+// The instantiated variants.  {dim, token block, cta group, W stage width}
+#define QC_ENC_VARIANTS(X)                                                                       \
+  X(384, 128, 1, 64)  X(384, 128, 1, 32)                                                          \
+  X(768, 128, 1, 64)  X(768, 128, 1, 32)  X(768, 128, 2, 64)  X(768, 128, 2, 32)                  \
+  X(768, 112, 2, 64)  X(768, 112, 2, 32)  X(768, 96, 2, 64)   X(768, 96, 2, 32)                   \
+  X(1536, 64, 1, 64)  X(1536, 64, 2, 64)  X(1536, 64, 2, 32)  X(1536, 48, 2, 64)  X(1536, 48, 2, 32)
 
-int encoder_w_stages(int dim, int cta_group) {
-  (void)cta_group;
-  switch (dim) {
-    case 384: return EncTraits<384, 128, 1>::W_STAGES;
-    case 768: return EncTraits<768, 128, 1>::W_STAGES;
-    case 1536: return EncTraits<1536, 64, 1>::W_STAGES;
-    default: return 0;
-  }
-}
-
-bool encoder_supports(int dim, int cta_group) {
-  if (cta_group == 1) return dim == 384 || dim == 768 || dim == 1536;
-  if (cta_group == 2) return dim == 768 || dim == 1536;
+bool encoder_variant_supported(int dim, const EncoderVariant& v) {
+#define X(D, TB, CG, WBK) if (dim == D && v.token_block == TB && v.cta_group == CG && v.w_bk == WBK) return true;
+  QC_ENC_VARIANTS(X)
+#undef X
   return false;
 }
 
-cudaError_t launch_encode(const EncoderLaunch& a) {
-  if (a.cta_group == 2) {
-    if (a.dim == 768) return launch_encode_t<EncTraits<768, 128, 2>>(a);
-    if (a.dim == 1536) return launch_encode_t<EncTraits<1536, 64, 2>>(a);
-  } else {
-    if (a.dim == 384) return launch_encode_t<EncTraits<384, 128, 1>>(a);
-    if (a.dim == 768) return launch_encode_t<EncTraits<768, 128, 1>>(a);
-    if (a.dim == 1536) return launch_encode_t<EncTraits<1536, 64, 1>>(a);
+int encoder_variant_w_stages(int dim, const EncoderVariant& v) {
+#define X(D, TB, CG, WBK) \
+  if (dim == D && v.token_block == TB && v.cta_group == CG && v.w_bk == WBK) return EncTraits<D, TB, CG, WBK>::W_STAGES;
+  QC_ENC_VARIANTS(X)
+#undef X
+  return 0;
+}
+
+EncoderVariant encoder_default_variant(int dim) {
+  switch (dim) {
+    case 384: return EncoderVariant{128, 1, 64};
+    case 768: return EncoderVariant{128, 2, 64};
+    case 1536: return EncoderVariant{64, 2, 64};
+    default: return EncoderVariant{0, 0, 0};
   }
+}
+
+cudaError_t launch_encode(const EncoderLaunch& a) {
+#define X(D, TB, CG, WBK)                                                                                      \
+  if (a.dim == D && a.variant.token_block == TB && a.variant.cta_group == CG && a.variant.w_bk == WBK)         \
+    return launch_encode_t<EncTraits<D, TB, CG, WBK>>(a);
+  QC_ENC_VARIANTS(X)
+#undef X
   return cudaErrorInvalidValue;
 }
 

@@ -30,7 +30,7 @@ ABI_SYMBOLS = (
     "qc_strerror", "qc_status_atom", "qc_abi_version",
     "qc_check_status", "qc_last_hang",
     "qc_launch_count", "qc_profile_enable", "qc_profile_reset", "qc_kernel_stats",
-    "qc_encoder_info", "qc_encoder_set_cta_group",
+    "qc_encoder_info", "qc_encoder_set_cta_group", "qc_encoder_set_variant", "qc_encoder_stall_profile",
 )
 
 
@@ -110,6 +110,10 @@ def load_library() -> ctypes.CDLL:
     lib.qc_encoder_info.restype = i32
     lib.qc_encoder_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                     ctypes.POINTER(ctypes.c_int32)]
+    lib.qc_encoder_set_variant.restype = i32
+    lib.qc_encoder_set_variant.argtypes = [vp, i32, i32, i32]
+    lib.qc_encoder_stall_profile.restype = i32
+    lib.qc_encoder_stall_profile.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]
     lib.qc_encoder_set_cta_group.restype = i32
     lib.qc_encoder_set_cta_group.argtypes = [vp, i32]
     _lib = lib
@@ -305,6 +309,20 @@ class Context:
         cg, tb, ws = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         _check(self._lib.qc_encoder_info(self._h, ctypes.byref(cg), ctypes.byref(tb), ctypes.byref(ws)))
         return {"cta_group": cg.value, "token_block": tb.value, "w_stages": ws.value}
+
+    STALL_FIELDS = ("mma_total", "mma_wait_w", "mma_wait_tokens", "mma_wait_acc", "epi_total", "epi_wait_acc",
+                    "gather_total", "gather_wait_free", "wprod_total", "wprod_wait_free")
+
+    def stall_profile(self, enable: bool = True, read: bool = False):
+        """K1 tuning aid: per-role barrier stall cycles of the last encoder launch (averaged over CTAs)."""
+        out = (ctypes.c_double * 16)() if read else None
+        _check(self._lib.qc_encoder_stall_profile(self._h, 1 if enable else 0, out))
+        if out is None:
+            return None
+        return {name: float(out[i]) for i, name in enumerate(self.STALL_FIELDS)}
+
+    def set_variant(self, token_block: int, cta_group: int, w_bk: int = 64) -> None:
+        _check(self._lib.qc_encoder_set_variant(self._h, int(token_block), int(cta_group), int(w_bk)))
 
     def set_cta_group(self, cta_group: int) -> None:
         _check(self._lib.qc_encoder_set_cta_group(self._h, int(cta_group)))

@@ -52,7 +52,10 @@ def make_decisions(b: int, n: int, t: int, vocab: int = VOCAB, seed: int = BASE_
     rng = np.random.default_rng(seed)
     base = rng.integers(0, vocab, size=(b, 1, t), dtype=np.int32)
     fresh = rng.integers(0, vocab, size=(b, n, t), dtype=np.int32)
-    p = np.array([RESAMPLE_PROBS[k % len(RESAMPLE_PROBS)] for k in range(n)], dtype=np.float32)
+    # identical / near / far / unrelated, nudged by 0.03 per wrap so no two pool members are exact
+    # duplicates (exact duplicates tie the medoid vote to the last ulp, which no float path can pin)
+    p = np.array([min(1.0, RESAMPLE_PROBS[k % len(RESAMPLE_PROBS)] + 0.03 * (k // len(RESAMPLE_PROBS)))
+                  for k in range(n)], dtype=np.float32)
     # shuffle which pool member is identical / near / far / unrelated so index 0 is not special
     perm = np.stack([rng.permutation(n) for _ in range(b)])
     p_b = p[perm]                                            # [B, N]

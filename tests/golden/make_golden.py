@@ -84,68 +84,106 @@ constant_embedding_rule = {"src": f"{RULES}:487-552; {RESULT}:839-884",
                            "values": ["first phrasing", "second phrasing", "third phrasing"],
                            "threshold": 0.8, "expect": "first phrasing"}
 
-# Rule-level known answers (filled in by the rule oracle's tests): see RULE_VECTORS below.
+# Rule-level known answers, transcribed test by test.  Atoms are written as strings.
 rule_vectors = {
-    "exact_match": [
-        {"src": f"{RULES}:16-49", "values": ["a", "a", "a"], "expect": ["ok", "a"]},
-        {"src": f"{RULES}:16-49", "values": ["a", "b", "a"], "expect": ["error", "no_consensus"]},
-        {"src": "lib/quoracle/actions/consensus_rules.ex:49", "values": [], "expect": ["error", "no_values"]},
-        {"src": "lib/quoracle/actions/consensus_rules.ex:50", "values": [42], "expect": ["ok", 42]},
+    "apply_rule": [
+        {"src": f"{RULES}:22-25", "rule": ["exact_match"], "values": ["command1", "command1", "command1"], "expect": ["ok", "command1"]},
+        {"src": f"{RULES}:27-30", "rule": ["exact_match"], "values": ["command1", "command2"], "expect": ["error", "no_consensus"]},
+        {"src": f"{RULES}:32-34", "rule": ["exact_match"], "values": [], "expect": ["error", "no_values"]},
+        {"src": f"{RULES}:36-38", "rule": ["exact_match"], "values": ["value"], "expect": ["ok", "value"]},
+        {"src": f"{RULES}:52-56", "rule": ["semantic_similarity", 0.95], "values": ["exact", "exact", "exact"], "expect": ["ok", "exact"]},
+        {"src": f"{RULES}:58-62", "rule": ["semantic_similarity", 0.95], "values": ["", "", ""], "expect": ["ok", ""]},
+        {"src": f"{RULES}:64-72", "rule": ["semantic_similarity", 0.99], "values": ["Process data", "Beautiful sunset", "Pizza recipe"],
+         "expect": ["error", "no_consensus"], "note": "embeddings unavailable"},
+        {"src": f"{RULES}:76-79", "rule": ["mode_selection"], "values": ["get", "get", "post", "get"], "expect": ["ok", "get"]},
+        {"src": f"{RULES}:81-84", "rule": ["mode_selection"], "values": ["get", "post", "get", "post"], "expect": ["ok", "get"],
+         "note": "tie: first in map (term) order"},
+        {"src": f"{RULES}:86-89", "rule": ["mode_selection"], "values": ["atom1", "atom1", "atom2"], "expect": ["ok", "atom1"]},
+        {"src": f"{RULES}:91-94", "rule": ["mode_selection"], "values": ["a", "b", "a", "a"], "expect": ["ok", "a"]},
+        {"src": f"{RULES}:96-98", "rule": ["mode_selection"], "values": ["single"], "expect": ["ok", "single"]},
+        {"src": f"{RULES}:114-117", "rule": ["union_merge"], "values": [["a", "b"], ["c"], ["d"]], "expect": ["ok", ["a", "b", "c", "d"]]},
+        {"src": f"{RULES}:119-122", "rule": ["union_merge"], "values": [[], ["a"], []], "expect": ["ok", ["a"]]},
+        {"src": f"{RULES}:108-112", "rule": ["union_merge"], "values": [["a", "a"], ["b", "b"], ["a", "b"]], "expect": ["ok", ["a", "b"]]},
+        {"src": f"{RULES}:131-134", "rule": ["structural_merge"], "values": [{"a": 1}, {"b": 2}, {"c": 3}], "expect": ["ok", {"a": 1, "b": 2, "c": 3}]},
+        {"src": f"{RULES}:136-139", "rule": ["structural_merge"], "values": [{"a": 1}, {"a": 2}, {"a": 3}], "expect": ["ok", {"a": 3}]},
+        {"src": f"{RULES}:141-149", "rule": ["structural_merge"], "values": [{"outer": {"inner": 1}}, {"outer": {"other": 2}}],
+         "expect": ["ok", {"outer": {"inner": 1, "other": 2}}]},
+        {"src": f"{RULES}:151-154", "rule": ["structural_merge"], "values": [{}, {"a": 1}, {}], "expect": ["ok", {"a": 1}]},
+        {"src": f"{RULES}:164-167", "rule": ["percentile", 50], "values": [100, 200, 300, 400, 500], "expect": ["ok", 300]},
+        {"src": f"{RULES}:169-172", "rule": ["percentile", 75], "values": [100, 200, 300, 400], "expect": ["ok", 325]},
+        {"src": f"{RULES}:174-176", "rule": ["percentile", 50], "values": [42], "expect": ["ok", 42]},
+        {"src": f"{RULES}:178-181", "rule": ["percentile", 50], "values": [10, 20, 30, 40], "expect": ["ok", 25]},
+        {"src": f"{RULES}:183-187", "rule": ["percentile", 50], "values": [10, 20, 30, 40, 50], "expect": ["ok", 30]},
+        {"src": f"{RULES}:304-307", "rule": ["wait_parameter"], "values": [False, False, False], "expect": ["ok", False]},
+        {"src": f"{RULES}:309-312", "rule": ["wait_parameter"], "values": [True, True, True], "expect": ["ok", True]},
+        {"src": f"{RULES}:314-321", "rule": ["wait_parameter"], "values": [True, False, True], "expect": ["ok", True]},
+        {"src": f"{RULES}:314-321", "rule": ["wait_parameter"], "values": [False, True, True, True, True], "expect": ["ok", True]},
+        {"src": f"{RULES}:314-321", "rule": ["wait_parameter"], "values": [False, False, True], "expect": ["ok", True]},
+        {"src": f"{RULES}:323-328", "rule": ["wait_parameter"], "values": [10, 20, 30], "expect": ["ok", 20]},
+        {"src": f"{RULES}:323-328", "rule": ["wait_parameter"], "values": [5, 10, 15, 20, 25], "expect": ["ok", 15]},
+        {"src": f"{RULES}:330-332", "rule": ["wait_parameter"], "values": [42], "expect": ["ok", 42]},
+        {"src": f"{RULES}:334-337", "rule": ["wait_parameter"], "values": [False, 10, 20], "expect": ["ok", 10]},
+        {"src": f"{RULES}:339-342", "rule": ["wait_parameter"], "values": [True, 10, 20], "expect": ["ok", 20]},
+        {"src": f"{RULES}:344-347", "rule": ["wait_parameter"], "values": [True, False], "expect": ["ok", 15]},
+        {"src": f"{RULES}:349-352", "rule": ["wait_parameter"], "values": [10, 20, 30, 40], "expect": ["ok", 25]},
+        {"src": f"{RULES}:354-357", "rule": ["wait_parameter"], "values": [0, False, 0], "expect": ["ok", 0]},
     ],
-    "semantic_identical": [
-        {"src": f"{RULES}:52-72", "values": ["same", "same", "same"], "threshold": 0.9, "expect": ["ok", "same"],
-         "embedding_calls": 0},
-        {"src": f"{RULES}:428-458", "values": ["", "", ""], "threshold": 0.9, "expect": ["ok", ""], "embedding_calls": 0},
-        {"src": f"{RULES}:555-575", "values": ["alpha text", "beta text"], "threshold": 0.9, "embedding": "fail",
-         "expect": ["error", "no_consensus"]},
-    ],
-    "mode_selection": [
-        {"src": f"{RULES}:76-99", "values": ["get", "post", "get", "post"], "expect": ["ok", "get"],
-         "note": "atoms :get/:post; tie -> first in term order"},
-        {"src": f"{RULES}:76-99", "values": ["a", "b", "a", "a"], "expect": ["ok", "a"]},
-        {"src": f"{RESULT}:895-919", "values": ["aa", "b", "b", "ccccc"], "expect": ["ok", "b"],
-         "note": "orient fallback is the MODE, not median length"},
-    ],
-    "percentile": [
-        {"src": "lib/quoracle/actions/consensus_rules.ex:355", "p": 75, "values": [100, 200, 300, 400], "expect": 325},
-        {"src": f"{RULES}:164-188", "p": 50, "values": [10, 20, 30], "expect": 20},
-        {"src": f"{RULES}:164-188", "p": 50, "values": [10, 20, 30, 40], "expect": 25},
-        {"src": f"{RULES}:164-188", "p": 100, "values": [5, 50, 20], "expect": 50},
-    ],
-    "wait_parameter": [
-        {"src": f"{RULES}:303-367", "values": [False, False, False], "expect": False},
-        {"src": f"{RULES}:303-367", "values": [True, True, True], "expect": True},
-        {"src": f"{RULES}:303-367", "values": [True, False, False], "expect": True,
-         "note": ">= 3 booleans with any true -> true"},
-        {"src": f"{RULES}:303-367", "values": [10, 20, 30], "expect": 20},
-        {"src": f"{RULES}:303-367", "values": [10, 20], "expect": 15},
-        {"src": f"{RULES}:303-367", "values": [True, False], "expect": 15, "note": "true -> 30, false -> 0, median 15"},
-        {"src": f"{RULES}:303-367", "values": [False, 10, 20], "expect": 10},
-        {"src": f"{RULES}:303-367", "values": [True, 10, 20], "expect": 20, "note": "true -> max int"},
+    "merge_params": [
+        {"src": f"{RULES}:191-196", "action": "spawn_child", "param": "task_description",
+         "values": ["Process data", "Process data", "Process data"], "expect": ["ok", "Process data"]},
+        {"src": f"{RULES}:198-201", "action": "wait", "param": "wait", "values": [1000, 2000, 3000, 4000, 5000], "expect": ["ok", 3000]},
+        {"src": f"{RULES}:203-206", "action": "send_message", "param": "to", "values": ["parent", "parent", "parent"], "expect": ["ok", "parent"]},
+        {"src": f"{RULES}:208-213", "action": "spawn_child", "param": "unknown", "values": ["value1", "value2"], "expect": ["error", "unknown_param"]},
+        {"src": f"{RULES}:215-220", "action": "spawn_child", "param": "models", "values": [["model1"], ["model2"]], "expect": ["error", "unknown_param"]},
+        {"src": f"{RULES}:222-225", "action": "execute_shell", "param": "command", "values": ["ls -la", "ls -la", "ls -la"], "expect": ["ok", "ls -la"]},
+        {"src": f"{RULES}:227-233", "action": "execute_shell", "param": "command", "values": ["ls -la", "rm -rf"], "expect": ["error", "no_consensus"]},
+        {"src": f"{RULES}:361-364", "action": "orient", "param": "wait", "values": [True, False, True], "expect": ["ok", True]},
     ],
     "wait_score": [
-        {"src": f"{RESULT}:12-36", "value": True, "expect": [0, 0]},
-        {"src": f"{RESULT}:12-36", "value": None, "expect": [0, 1]},
-        {"src": f"{RESULT}:12-36", "value": 5, "expect": [0, 6]},
-        {"src": f"{RESULT}:12-36", "value": 0, "expect": [1, 0]},
-        {"src": f"{RESULT}:12-36", "value": False, "expect": [1, 0]},
+        {"src": f"{RESULT}:6-8", "value": True, "expect": [0, 0]},
+        {"src": f"{RESULT}:10-12", "value": None, "expect": [0, 1]},
+        {"src": f"{RESULT}:14-19", "value": 1, "expect": [0, 2]},
+        {"src": f"{RESULT}:14-19", "value": 5, "expect": [0, 6]},
+        {"src": f"{RESULT}:14-19", "value": 100, "expect": [0, 101]},
+        {"src": f"{RESULT}:14-19", "value": 10000, "expect": [0, 10001]},
+        {"src": f"{RESULT}:21-24", "value": False, "expect": [1, 0]},
+        {"src": f"{RESULT}:21-24", "value": 0, "expect": [1, 0]},
+    ],
+    "cluster_wait_score": [
+        {"src": f"{RESULT}:28-38", "waits": [False, 5, True], "expect": [1, 6]},
+        {"src": f"{RESULT}:40-49", "waits": [False, "__missing__"], "expect": [1, 1]},
+        {"src": f"{RESULT}:51-60", "waits": [False, False], "expect": [2, 0]},
+        {"src": f"{RESULT}:62-71", "waits": [True, True], "expect": [0, 0]},
+    ],
+    "break_tie": [
+        {"src": f"{RESULT}:585-594", "actions": ["spawn_child", "orient"], "expect": "orient"},
+        {"src": f"{RESULT}:596-606", "actions": ["execute_shell", "spawn_child", "send_message"], "expect": "send_message"},
+        {"src": f"{RESULT}:608-615", "actions": ["orient", "orient"], "expect_index": 0, "note": "returns first when all scores tie"},
     ],
     "confidence": [
-        {"src": f"{RESULT}:711-778", "count": 3, "total": 3, "round": 1, "gt": 0.9},
-        {"src": f"{RESULT}:711-778", "count": 3, "total": 3, "round": 1, "equals": 1.0},
-        {"src": f"{RESULT}:711-778", "count": 2, "total": 3, "round": 1, "equals": 2 / 3 + 0.10},
-        {"src": f"{RESULT}:711-778", "count": 3, "total": 3, "round": 6, "equals": 0.8,
-         "note": "two rounds beyond max 4: 1.0 + .15 - .2 -> clamp(0.95)?  computed: 1.15 - 0.2 = 0.95 -> 0.95",
-         "skip": True},
-        {"src": f"{RESULT}:711-778", "count": 1, "total": 10, "round": 20, "equals": 0.1, "note": "clamped at 0.1"},
+        {"src": f"{RESULT}:712-716", "count": 5, "total": 5, "round": 1, "gt": 0.9},
+        {"src": f"{RESULT}:718-723", "count": 3, "total": 5, "round": 2, "max_rounds": 2, "gt_other": {"round": 3, "max_rounds": 2}},
+        {"src": f"{RESULT}:725-730", "count": 3, "total": 5, "round": 4, "max_rounds": 2, "minus_other": {"round": 5, "max_rounds": 2}, "equals": 0.1, "tol": 1e-6},
+        {"src": f"{RESULT}:732-737", "count": 3, "total": 5, "round": 1, "same_as": {"round": 4}},
+        {"src": f"{RESULT}:739-744", "count": 3, "total": 5, "round": 1, "max_rounds": 0, "lt_other": {"round": 1, "max_rounds": 4}},
+        {"src": f"{RESULT}:746-755", "count": 1, "total": 10, "round": 5, "ge": 0.1, "le": 1.0},
+        {"src": f"{RESULT}:757-763", "count": 4, "total": 5, "round": 1, "gt_other": {"count": 3}},
+    ],
+    "format_result": [
+        {"src": f"{RESULT}:766-779", "clusters": [["spawn_child", 2], ["wait", 2], ["orient", 1]], "total": 5, "round": 1,
+         "expect_kind": "forced_decision", "expect_action": "wait"},
+        {"src": f"{RESULT}:781-801", "clusters": [["spawn_child", 1], ["execute_shell", 1], ["call_api", 1]], "total": 3, "round": 1,
+         "expect_kind": "forced_decision", "expect_action": "call_api"},
+    ],
+    "mode_fallback": [
+        {"src": f"{RESULT}:895-919", "action": "orient", "param": "current_situation", "values": ["aa", "b", "b", "ccccc"],
+         "embedding": "fail", "expect": "b", "note": "embeddings unavailable -> MODE, not median length"},
     ],
     "majority": [
         {"src": f"{AGG}:174-275", "counts": [3], "total": 3, "round": 1, "expect": "majority"},
-        {"src": f"{AGG}:174-275", "counts": [2, 1], "total": 3, "round": 1, "expect": "no_majority",
-         "note": "round 1 needs unanimity"},
+        {"src": f"{AGG}:174-275", "counts": [2, 1], "total": 3, "round": 1, "expect": "no_majority", "note": "round 1 needs unanimity"},
         {"src": f"{AGG}:174-275", "counts": [2, 1], "total": 3, "round": 2, "expect": "majority"},
-        {"src": f"{AGG}:174-275", "counts": [2, 2], "total": 4, "round": 2, "expect": "no_majority",
-         "note": "exactly 50% is not a majority"},
+        {"src": f"{AGG}:174-275", "counts": [2, 2], "total": 4, "round": 2, "expect": "no_majority", "note": "exactly 50% is not a majority"},
     ],
 }
 
