@@ -86,12 +86,14 @@ __device__ __forceinline__ bool hang_check(int32_t* dbg, long long t0, int tag) 
   }
   return false;
 }
-// Returns the cycles spent waiting (0 when the phase had already completed).
+// Returns the cycles spent in the wait.  try_wait itself suspends the thread for a bounded,
+// implementation-defined time, so the clock brackets the whole call; the watchdog (a global-memory
+// read) is consulted only every 32 timed-out attempts to keep it off the wake-up path.
 __device__ __forceinline__ long long mbar_wait(uint64_t* bar, uint32_t parity, int32_t* dbg, int tag) {
-  if (mbar_try_wait(bar, parity)) return 0;
   const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (hang_check(dbg, t0, tag)) break;
+    if ((++spins & 31u) == 0 && hang_check(dbg, t0, tag)) break;
   }
   return clock64() - t0;
 }
@@ -110,10 +112,10 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
   return ok != 0;
 }
 __device__ __forceinline__ long long mbar_wait_cluster(uint64_t* bar, uint32_t parity, int32_t* dbg, int tag) {
-  if (mbar_try_wait_cluster(bar, parity)) return 0;
   const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (hang_check(dbg, t0, tag)) break;
+    if ((++spins & 31u) == 0 && hang_check(dbg, t0, tag)) break;
   }
   return clock64() - t0;
 }
@@ -173,6 +175,30 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tma
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// TMA gather4: four rows (row indices r0..r3) x one box width of a 2D tensor land as four consecutive
+// 128-byte rows at smem_dst; out-of-range row indices are zero-filled.  CG == 2: the transaction
+// bytes are credited to the barrier at the same offset in the pair's leader CTA.
+template <int CG>
+__device__ __forceinline__ void tma_gather4(uint32_t smem_dst, const void* tmap, uint64_t* bar, int32_t col,
+                                            int32_t r0, int32_t r1, int32_t r2, int32_t r3) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_dst),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+        : "memory");
+  } else {
+    uint32_t leader_bar, dst;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(leader_bar) : "r"(smem_u32(bar)), "r"(0));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(smem_dst), "r"(cluster_ctarank()));
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::2 "
+        "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"(tmap), "r"(leader_bar), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+        : "memory");
+  }
 }
 
 // ---- TMEM allocation ---------------------------------------------------------------------
@@ -293,6 +319,12 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

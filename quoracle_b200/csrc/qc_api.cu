@@ -70,10 +70,10 @@ struct qc_ctx {
   // encoder
   bool has_encoder = false;
   int dim = 0, vocab = 0;
-  qc::EncoderVariant variant{0, 0, 0};
+  qc::EncoderVariant variant{0, 0, 0, 0};
   uint16_t* d_table = nullptr;
   uint16_t* d_wt = nullptr;  // W^T [dim(out) x dim(in)] bf16
-  CUtensorMap w_tmap64, w_tmap32;
+  CUtensorMap w_tmap64, w_tmap32, e_tmap;
   int32_t* d_err = nullptr;   // int32[8] device status words
   int32_t hang[4] = {};
   // workspaces
@@ -188,6 +188,14 @@ int make_w_tmap(qc_ctx* c) {
   r = enc(&c->w_tmap32, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->d_wt, gdim, gstride, box32, estr,
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return QC_ERR_CUDA;
+  // embedding table for TMA gather4: one 128-byte (64 x bf16) row segment per gathered row
+  const cuuint64_t edim[2] = {static_cast<cuuint64_t>(c->dim), static_cast<cuuint64_t>(c->vocab)};
+  const cuuint64_t estride[1] = {static_cast<cuuint64_t>(c->dim) * 2};
+  const cuuint32_t ebox[2] = {64, 1};
+  r = enc(&c->e_tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->d_table, edim, estride, ebox, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? QC_OK : QC_ERR_CUDA;
 }
 
@@ -245,6 +253,7 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
     qc::EncoderLaunch a;
     a.w_tmap64 = &c->w_tmap64;
     a.w_tmap32 = &c->w_tmap32;
+    a.e_tmap = &c->e_tmap;
     a.table = c->d_table;
     a.token_ids = d_tok;
     a.lens = d_lens;
@@ -492,7 +501,7 @@ int qc_encoder_stall_profile(qc_ctx* c, int enable, double out[16]) {
     for (int k = 0; k < 16; ++k) out[k] = 0.0;
     for (int b = 0; b < c->num_sms; ++b) {
       for (int k = 0; k < 16; ++k) {
-        const int total_slot = k < 4 ? 0 : (k < 6 ? 4 : (k < 8 ? 6 : (k < 10 ? 8 : k)));
+        const int total_slot = k < 4 ? 0 : (k < 6 ? 4 : (k < 8 ? 6 : (k < 10 ? 8 : (k == 10 ? 6 : (k < 13 ? 0 : (k == 13 ? 6 : k))))));
         if (h[b * 16 + total_slot] == 0) continue;   // role did not run in this CTA (e.g. MMA in the peer CTA)
         out[k] += static_cast<double>(h[b * 16 + k]);
         cnt[k]++;
@@ -511,17 +520,22 @@ int qc_encoder_stall_profile(qc_ctx* c, int enable, double out[16]) {
 int qc_encoder_set_cta_group(qc_ctx* c, int cta_group) {
   if (c == nullptr) return QC_ERR_INVALID_INPUT;
   if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  // keep the default tiling of this dim when it exists for the requested group size, else the
+  // baseline cp.async tiling (every dim has one for cta_group 1; 768/1536 also for 2)
   qc::EncoderVariant v = c->variant;
   v.cta_group = cta_group;
-  if (!qc::encoder_variant_supported(c->dim, v)) return QC_ERR_UNSUPPORTED;
+  if (!qc::encoder_variant_supported(c->dim, v)) {
+    v = qc::EncoderVariant{c->dim == 1536 ? 64 : 128, cta_group, 64, 0};
+    if (!qc::encoder_variant_supported(c->dim, v)) return QC_ERR_UNSUPPORTED;
+  }
   c->variant = v;
   return QC_OK;
 }
 
-int qc_encoder_set_variant(qc_ctx* c, int token_block, int cta_group, int w_bk) {
+int qc_encoder_set_variant(qc_ctx* c, int token_block, int cta_group, int w_bk, int gather_mode) {
   if (c == nullptr) return QC_ERR_INVALID_INPUT;
   if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
-  const qc::EncoderVariant v{token_block, cta_group, w_bk};
+  const qc::EncoderVariant v{token_block, cta_group, w_bk, gather_mode};
   if (!qc::encoder_variant_supported(c->dim, v)) return QC_ERR_UNSUPPORTED;
   c->variant = v;
   return QC_OK;

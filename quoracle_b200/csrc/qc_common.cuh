@@ -11,11 +11,13 @@ struct EncoderVariant {
   int token_block;
   int cta_group;
   int w_bk;
+  int gather;   // 0 = cp.async (LDGSTS) gather, 1 = TMA gather4
 };
 
 struct EncoderLaunch {
   const CUtensorMap* w_tmap64; // W^T, box 64 x 128, 128-byte swizzle (host copy; passed __grid_constant__)
   const CUtensorMap* w_tmap32; // W^T, box 32 x 128, 64-byte swizzle
+  const CUtensorMap* e_tmap;   // E [vocab x dim], box 64 x 1, 128-byte swizzle (gather4)
   const uint16_t* table;       // device, bf16 [vocab x dim]
   const int32_t* token_ids;    // device [R x T]
   const int32_t* lens;         // device [R]

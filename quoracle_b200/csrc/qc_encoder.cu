@@ -35,12 +35,13 @@ namespace qc {
 
 using namespace ptx;
 
-template <int D_, int TB_, int CG_, int WBK_>
+template <int D_, int TB_, int CG_, int WBK_, int GM_>
 struct EncTraits {
   static constexpr int D = D_;
   static constexpr int TB = TB_;
   static constexpr int CG = CG_;
   static constexpr int WBK = WBK_;                // k elements per streamed W stage
+  static constexpr int GM = GM_;                  // gather mode: 0 = cp.async (LDGSTS), 1 = TMA gather4
   static constexpr int BK = 64;                   // bf16 elements per 128-byte swizzle row (token tiles)
   static constexpr int KB = D / BK;               // resident token k-blocks
   static constexpr int NWS = D / WBK;             // W stages per feature tile
@@ -59,13 +60,13 @@ struct EncTraits {
   static constexpr int ACC_COLS = UMMA_N <= 64 ? 64 : (UMMA_N <= 128 ? 128 : 256);
   static constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;   // 128 / 256 / 512: powers of two >= 32
   static constexpr int SMEM_BYTES = 1024 + TOK_BYTES_PAD + W_STAGES * W_STAGE_BYTES + BAR_BYTES;
-  static constexpr int GATHER_LAG = 4;            // cp.async groups in flight per gather thread
+  static constexpr int GATHER_GROUP = (KB % 4 == 0) ? 4 : 3;   // k-blocks per cp.async group / proxy fence
   static_assert(WBK == 64 || WBK == 32, "W stage width is 64 (SW128) or 32 (SW64)");
   static_assert(D % MT == 0, "feature tiles must cover D");
   static_assert(D % BK == 0, "k-blocks must cover D");
-  static_assert(TB % 16 == 0 && UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid token block");
+  static_assert(TB % 8 == 0 && UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid token block");
   static_assert(W_STAGES >= 2, "need at least two W stages");
-  static_assert(KB > GATHER_LAG, "gather lag must be below the k-block count");
+  static_assert(KB % GATHER_GROUP == 0 && KB / GATHER_GROUP >= 2, "gather groups must tile the k-blocks");
   static_assert((2 * W_STAGES + 2 * KB + 2 * ACC_STAGES) * 8 + 8 <= BAR_BYTES, "barrier region too small");
 };
 
@@ -93,9 +94,9 @@ __device__ __forceinline__ int block_valid(const int32_t* __restrict__ lens, int
 // the next 32-column load is in flight while the current one is consumed.
 template <int NCOL>
 __device__ __forceinline__ float gelu_sum_columns(uint32_t taddr) {
-  static_assert(NCOL % 16 == 0, "column count must be a multiple of 16");
+  static_assert(NCOL % 8 == 0, "column count must be a multiple of 8");
   constexpr int FULL = NCOL / 32;
-  constexpr bool TAIL = (NCOL % 32) != 0;
+  constexpr int REM = NCOL % 32;
   float sum = 0.f;
   uint32_t va[32], vb[32];
   if constexpr (FULL > 0) tmem_ld_32x32b_x32(taddr, va);
@@ -108,12 +109,19 @@ __device__ __forceinline__ float gelu_sum_columns(uint32_t taddr) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) sum += gelu_tanh(__uint_as_float((c & 1) ? vb[i] : va[i]));
   }
-  if constexpr (TAIL) {
+  if constexpr (REM >= 16) {
     uint32_t vt[16];
     tmem_ld_32x32b_x16(taddr + FULL * 32, vt);
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 16; ++i) sum += gelu_tanh(__uint_as_float(vt[i]));
+  }
+  if constexpr (REM % 16 == 8) {
+    uint32_t vt[8];
+    tmem_ld_32x32b_x8(taddr + FULL * 32 + (REM >= 16 ? 16 : 0), vt);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += gelu_tanh(__uint_as_float(vt[i]));
   }
   return sum;
 }
@@ -121,6 +129,7 @@ __device__ __forceinline__ float gelu_sum_columns(uint32_t taddr) {
 template <class Tr>
 __global__ void __launch_bounds__(kEncThreads, 1)
 qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D x D] bf16, box WBK x 128
+                 const __grid_constant__ CUtensorMap e_tmap,          // E [vocab x D] bf16, box 64 x 1 (gather4)
                  const uint16_t* __restrict__ table,                   // E [vocab x D] bf16
                  const int32_t* __restrict__ token_ids,                // [R x T]
                  const int32_t* __restrict__ lens,                     // [R]
@@ -129,7 +138,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
                  unsigned long long* __restrict__ stall,               // optional [grid x 16] per-role stall cycles
                  int R, int T, int bpc, int vocab) {
   constexpr int D = Tr::D, TB = Tr::TB, CG = Tr::CG, KB = Tr::KB, NFT = Tr::NFT, WBK = Tr::WBK, NWS = Tr::NWS;
-  constexpr int UMMA_N = Tr::UMMA_N, WS = Tr::W_STAGES, LAG = Tr::GATHER_LAG, ACC_COLS = Tr::ACC_COLS;
+  constexpr int UMMA_N = Tr::UMMA_N, WS = Tr::W_STAGES, ACC_COLS = Tr::ACC_COLS;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -146,7 +155,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;   // position in the CTA pair
+  const uint32_t rank = (CG == 2) ? (blockIdx.x & 1u) : 0u;    // position in the CTA pair (cluster dim x = 2)
   const bool leader = (rank == 0);
   const int group = blockIdx.x / CG;                           // CTA (pair) index
   const int ngroups = gridDim.x / CG;
@@ -156,12 +165,14 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
   // ---- one-time setup -----------------------------------------------------------------
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&w_tmap);
+    if (Tr::GM == 1) tma_prefetch_desc(&e_tmap);
     for (int s = 0; s < WS; ++s) {
       mbar_init(&w_full[s], 1);   // leader's producer arrive.expect_tx (TMA bytes of the whole group)
       mbar_init(&w_empty[s], 1);  // tcgen05.commit
     }
     for (int k = 0; k < KB; ++k) {
-      mbar_init(&tok_full[k], 4 * CG);  // one arrival per gather warp of each CTA in the group
+      // cp.async gather: one arrival per gather warp of each CTA; TMA gather: the leader's expect_tx
+      mbar_init(&tok_full[k], Tr::GM == 0 ? 4 * CG : 1);
       mbar_init(&tok_empty[k], 1);      // tcgen05.commit
     }
     for (int a = 0; a < Tr::ACC_STAGES; ++a) {
@@ -221,6 +232,59 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
       stall[blockIdx.x * 16 + 4] = static_cast<unsigned long long>(clock64() - st_t0);
       stall[blockIdx.x * 16 + 5] = static_cast<unsigned long long>(st_wait);
     }
+  } else if (warp < 8 && Tr::GM == 1) {
+    // ===================== gather (TMA gather4) ===================================================
+    // Row group rg = (warp-4)*8 + lane (lanes 0..7 of each gather warp) owns rows 4rg..4rg+3: eight
+    // gather4 issues per warp per k-block (the per-lane operands force the compiler's one-lane-at-a-time
+    // issue loop, so the work is spread over the four gather warps).
+    {
+      const int rg = (warp - 4) * 8 + lane;
+      const bool active = lane < 8 && rg * 4 < TB;
+      const uint32_t tok_base = smem_u32(tok_smem);
+      uint32_t it = 0;
+      long long st_wait = 0;
+      const long long st_t0 = clock64();
+      for (int item = group; item < nitems; item += ngroups) {
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < CG; ++s) any |= block_valid(lens, item * CG + s, nblocks, bpc, TB) > 0;
+        if (!any) continue;
+        const int blk = item * CG + static_cast<int>(rank);
+        const int valid = block_valid(lens, blk, nblocks, bpc, TB);
+        const int cand = blk < nblocks ? blk / bpc : 0;
+        const int j = blk < nblocks ? blk - cand * bpc : 0;
+        const int32_t* ids = token_ids + static_cast<size_t>(cand) * T + static_cast<size_t>(j) * TB;
+        int32_t rid[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int rowi = rg * 4 + q;
+          int32_t id = -1;
+          if (active && rowi < valid) id = ids[rowi];
+          if (id >= vocab) {
+            atomicExch(dbg + 4, 1);
+            id = -1;
+          }
+          rid[q] = id >= 0 ? id : vocab;          // out-of-range row -> TMA zero fill
+        }
+        const uint32_t par_empty = (it & 1u) ^ 1u;
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb) {
+          if (lane == 0) {
+            st_wait += mbar_wait(&tok_empty[kb], par_empty, dbg, 200 + kb);
+            if (warp == 4 && leader) mbar_expect_tx(&tok_full[kb], CG * Tr::TOK_KB_BYTES);
+          }
+          __syncwarp();
+          if (active)
+            tma_gather4<CG>(tok_base + kb * Tr::TOK_KB_BYTES + rg * 512, &e_tmap, &tok_full[kb], kb * 64, rid[0], rid[1],
+                            rid[2], rid[3]);
+        }
+        ++it;
+      }
+      if (stall != nullptr && threadIdx.x == 128) {
+        stall[blockIdx.x * 16 + 6] = static_cast<unsigned long long>(clock64() - st_t0);
+        stall[blockIdx.x * 16 + 7] = static_cast<unsigned long long>(st_wait);
+      }
+    }
   } else if (warp < 8) {
     // ===================== gather: table rows -> swizzled resident token tiles ==============
     const int p = threadIdx.x - 128;           // 0..127
@@ -230,7 +294,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
     // swizzle: chunk index XOR (row mod 8); rows of one thread are congruent mod 16 so it is constant
     const uint32_t dst_off0 = static_cast<uint32_t>(r16 * 128 + ((c ^ (r16 & 7)) << 4));
     uint32_t it = 0;
-    long long st_wait = 0;
+    long long st_wait = 0, st_ld = 0, st_fence = 0;
     const long long st_t0 = clock64();
     for (int item = group; item < nitems; item += ngroups) {
       bool any = false;
@@ -242,10 +306,11 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
       const int cand = blk < nblocks ? blk / bpc : 0;
       const int j = blk < nblocks ? blk - cand * bpc : 0;
       const int32_t* ids = token_ids + static_cast<size_t>(cand) * T + static_cast<size_t>(j) * TB;
-      const uint16_t* src[TB / 16];
-      uint32_t nbytes[TB / 16];
+      constexpr int QN = (TB + 15) / 16;
+      const uint16_t* src[QN];
+      uint32_t nbytes[QN];
 #pragma unroll
-      for (int q = 0; q < TB / 16; ++q) {
+      for (int q = 0; q < QN; ++q) {
         const int rowi = q * 16 + r16;
         int32_t id = -1;
         if (rowi < valid) id = ids[rowi];
@@ -257,28 +322,54 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
         src[q] = table + (id >= 0 ? static_cast<size_t>(id) * D : 0) + c * 8;
       }
       const uint32_t par_empty = (it & 1u) ^ 1u;
+      // k-blocks are fetched in groups of GG: one cp.async group, one generic->async proxy fence and one
+      // round of barrier arrivals per group (the fence is the expensive part: it drains behind the MMA and
+      // TMA traffic of the async proxy, so one per k-block throttled the gather).
+      constexpr int GG = Tr::GATHER_GROUP;
+      constexpr int NG = KB / GG;
 #pragma unroll 1
-      for (int kb = 0; kb < KB; ++kb) {
-        st_wait += mbar_wait(&tok_empty[kb], par_empty, dbg, 200 + kb);
-        const uint32_t dst = tok_base + kb * Tr::TOK_KB_BYTES + dst_off0;
+      for (int g = 0; g < NG; ++g) {
 #pragma unroll
-        for (int q = 0; q < TB / 16; ++q) cp_async_16(dst + q * 2048, src[q] + kb * 64, nbytes[q]);
+        for (int kk = 0; kk < GG; ++kk) {
+          const int kb = g * GG + kk;
+          st_wait += mbar_wait(&tok_empty[kb], par_empty, dbg, 200 + kb);
+          const uint32_t dst = tok_base + kb * Tr::TOK_KB_BYTES + dst_off0;
+#pragma unroll
+          for (int q = 0; q < QN; ++q) {
+            if (q * 16 + r16 < TB) cp_async_16(dst + q * 2048, src[q] + kb * 64, nbytes[q]);
+          }
+        }
         cp_async_commit();
-        if (kb >= LAG) {
-          cp_async_wait<LAG>();
+        if (g >= 1) {
+          const long long tl = clock64();
+          cp_async_wait<1>();
+          const long long tf = clock64();
           fence_proxy_async_smem();
+          st_ld += tf - tl;
+          st_fence += clock64() - tf;
           __syncwarp();
           if (lane == 0) {
-            if constexpr (CG == 2) mbar_arrive_cluster(&tok_full[kb - LAG], 0); else mbar_arrive(&tok_full[kb - LAG]);
+#pragma unroll
+            for (int kk = 0; kk < GG; ++kk) {
+              const int kb = (g - 1) * GG + kk;
+              if constexpr (CG == 2) mbar_arrive_cluster(&tok_full[kb], 0); else mbar_arrive(&tok_full[kb]);
+            }
           }
         }
       }
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
+      {
+        const long long tl = clock64();
+        cp_async_wait<0>();
+        const long long tf = clock64();
+        fence_proxy_async_smem();
+        st_ld += tf - tl;
+        st_fence += clock64() - tf;
+      }
       __syncwarp();
       if (lane == 0) {
 #pragma unroll
-        for (int kb = KB - LAG; kb < KB; ++kb) {
+        for (int kk = 0; kk < GG; ++kk) {
+          const int kb = (NG - 1) * GG + kk;
           if constexpr (CG == 2) mbar_arrive_cluster(&tok_full[kb], 0); else mbar_arrive(&tok_full[kb]);
         }
       }
@@ -287,10 +378,12 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
     if (stall != nullptr && threadIdx.x == 128) {
       stall[blockIdx.x * 16 + 6] = static_cast<unsigned long long>(clock64() - st_t0);
       stall[blockIdx.x * 16 + 7] = static_cast<unsigned long long>(st_wait);
+      stall[blockIdx.x * 16 + 10] = static_cast<unsigned long long>(st_ld);
+      stall[blockIdx.x * 16 + 13] = static_cast<unsigned long long>(st_fence);
     }
   } else if (warp == 8) {
-    // ===================== W^T tile producer (TMA) =========================================
-    if (lane == 0) {
+    // ===================== W^T tile producer (TMA), warp-convergent like the MMA issuer ============
+    {
       uint32_t wi = 0;
       long long st_wait = 0;
       const long long st_t0 = clock64();
@@ -298,35 +391,43 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
         bool any = false;
 #pragma unroll
         for (int s = 0; s < CG; ++s) any |= block_valid(lens, item * CG + s, nblocks, bpc, TB) > 0;
-        if (!any) continue;
+        if (!__any_sync(0xffffffffu, any)) continue;
         for (int ft = 0; ft < NFT; ++ft) {
           for (int ws = 0; ws < NWS; ++ws, ++wi) {
             const uint32_t s = wi % WS;
             const uint32_t ph = (wi / WS) & 1u;
             st_wait += mbar_wait(&w_empty[s], ph ^ 1u, dbg, 300 + static_cast<int>(s));
             void* dst = w_smem + s * Tr::W_STAGE_BYTES;
-            if constexpr (CG == 2) {
-              if (leader) mbar_expect_tx(&w_full[s], 2 * Tr::W_STAGE_BYTES);
-              tma_load_2d_pair(dst, &w_tmap, &w_full[s], ws * WBK, ft * Tr::MT + static_cast<int>(rank) * 128);
-            } else {
-              mbar_expect_tx(&w_full[s], Tr::W_STAGE_BYTES);
-              tma_load_2d(dst, &w_tmap, &w_full[s], ws * WBK, ft * Tr::MT);
+            if (elect_one()) {
+              if constexpr (CG == 2) {
+                if (leader) mbar_expect_tx(&w_full[s], 2 * Tr::W_STAGE_BYTES);
+                tma_load_2d_pair(dst, &w_tmap, &w_full[s], ws * WBK, ft * Tr::MT + static_cast<int>(rank) * 128);
+              } else {
+                mbar_expect_tx(&w_full[s], Tr::W_STAGE_BYTES);
+                tma_load_2d(dst, &w_tmap, &w_full[s], ws * WBK, ft * Tr::MT);
+              }
             }
+            __syncwarp();
           }
         }
       }
-      if (stall != nullptr) {
+      if (stall != nullptr && lane == 0) {
         stall[blockIdx.x * 16 + 8] = static_cast<unsigned long long>(clock64() - st_t0);
         stall[blockIdx.x * 16 + 9] = static_cast<unsigned long long>(st_wait);
       }
     }
   } else {
-    // ===================== MMA issuer (leader CTA, one lane) ================================
-    if (leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA) ===========================================
+    // The whole warp runs the loop in convergent control flow (barrier waits are warp-wide); only the
+    // tcgen05.mma / tcgen05.commit instructions sit under elect_one().  Issuing from a divergent
+    // `lane == 0` branch makes the compiler wrap every UTCHMMA in an ELECT/R2UR waterfall loop
+    // (~70 cycles per MMA), which left the tensor pipe issue-starved.
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(Tr::MT, UMMA_N);
       constexpr int WPK = 64 / WBK;                              // W stages per token k-block
       const uint32_t w_base = smem_u32(w_smem);
       const uint32_t tok_base = smem_u32(tok_smem);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t wi = 0, acc_iter = 0, it = 0;
       long long st_w = 0, st_tok = 0, st_acc = 0;
       const long long st_t0 = clock64();
@@ -334,13 +435,13 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
         bool any = false;
 #pragma unroll
         for (int s = 0; s < CG; ++s) any |= block_valid(lens, item * CG + s, nblocks, bpc, TB) > 0;
-        if (!any) continue;
+        if (!__any_sync(0xffffffffu, any)) continue;
         for (int ft = 0; ft < NFT; ++ft, ++acc_iter) {
           const uint32_t as = acc_iter & 1u;
           if constexpr (CG == 2) st_acc += mbar_wait_cluster(&acc_empty[as], ((acc_iter >> 1) & 1u) ^ 1u, dbg, 400 + ft);
           else st_acc += mbar_wait(&acc_empty[as], ((acc_iter >> 1) & 1u) ^ 1u, dbg, 400 + ft);
           tcgen05_fence_after();
-          const uint32_t tmem_d = tmem_base + as * ACC_COLS;
+          const uint32_t tmem_d = tmem_u + as * ACC_COLS;
           for (int ws = 0; ws < NWS; ++ws, ++wi) {
             const int kb = ws / WPK;                              // token k-block this W stage multiplies
             const int sub = ws % WPK;                             // which WBK-wide part of it
@@ -355,19 +456,22 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
                                                : make_kmajor_sw64_desc(w_base + s * Tr::W_STAGE_BYTES);
             // token tile: 128-byte rows; this stage covers bytes [sub*WBK*2, +WBK*2) of each row
             const uint64_t bdesc = make_kmajor_sw128_desc(tok_base + kb * Tr::TOK_KB_BYTES) + sub * (WBK * 2 / 16);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < WBK / 16; ++k) {
-              // +32 bytes per 16-element k step inside the swizzle row (descriptor units of 16 B => +2)
-              umma_bf16<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ws | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < WBK / 16; ++k) {
+                // +32 bytes per 16-element k step inside the swizzle row (descriptor units of 16 B => +2)
+                umma_bf16<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ws | k) != 0 ? 1u : 0u);
+              }
+              umma_commit<CG>(&w_empty[s]);                         // W stage reusable once these MMAs retire
+              if (ft == NFT - 1 && sub == WPK - 1) umma_commit<CG>(&tok_empty[kb]);   // token k-block free
+              if (ws == NWS - 1) umma_commit<CG>(&acc_full[as]);
             }
-            umma_commit<CG>(&w_empty[s]);                         // W stage reusable once these MMAs retire
-            if (ft == NFT - 1 && sub == WPK - 1) umma_commit<CG>(&tok_empty[kb]);   // token k-block free
+            __syncwarp();
           }
-          umma_commit<CG>(&acc_full[as]);
         }
         ++it;
       }
-      if (stall != nullptr) {
+      if (stall != nullptr && lane == 0) {
         stall[blockIdx.x * 16 + 0] = static_cast<unsigned long long>(clock64() - st_t0);
         stall[blockIdx.x * 16 + 1] = static_cast<unsigned long long>(st_w);
         stall[blockIdx.x * 16 + 2] = static_cast<unsigned long long>(st_tok);
@@ -421,27 +525,31 @@ static cudaError_t launch_encode_t(const EncoderLaunch& a) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const CUtensorMap* tm = Tr::WBK == 64 ? a.w_tmap64 : a.w_tmap32;
-  return cudaLaunchKernelEx(&cfg, kern, *tm, a.table, a.token_ids, a.lens, a.part, a.err_flag, a.stall, a.R, a.T, bpc,
+  return cudaLaunchKernelEx(&cfg, kern, *tm, *a.e_tmap, a.table, a.token_ids, a.lens, a.part, a.err_flag, a.stall, a.R, a.T, bpc,
                             a.vocab);
 }
 
-// The instantiated variants.  {dim, token block, cta group, W stage width}
-#define QC_ENC_VARIANTS(X)                                                                       \
-  X(384, 128, 1, 64)  X(384, 128, 1, 32)                                                          \
-  X(768, 128, 1, 64)  X(768, 128, 1, 32)  X(768, 128, 2, 64)  X(768, 128, 2, 32)                  \
-  X(768, 112, 2, 64)  X(768, 112, 2, 32)  X(768, 96, 2, 64)   X(768, 96, 2, 32)                   \
-  X(1536, 64, 1, 64)  X(1536, 64, 2, 64)  X(1536, 64, 2, 32)  X(1536, 48, 2, 64)  X(1536, 48, 2, 32)
+// The instantiated variants.  {dim, token block, cta group, W stage width, gather mode}
+#define QC_ENC_VARIANTS(X)                                                                                   \
+  X(384, 128, 1, 64, 0)  X(384, 128, 1, 32, 0)  X(384, 128, 1, 64, 1)                                         \
+  X(768, 128, 1, 64, 0)  X(768, 128, 1, 32, 0)  X(768, 128, 2, 64, 0)  X(768, 128, 2, 32, 0)                   \
+  X(768, 112, 2, 64, 0)  X(768, 104, 2, 64, 0)  X(768, 96, 2, 64, 0)                                           \
+  X(768, 128, 1, 64, 1)  X(768, 128, 2, 64, 1)  X(768, 128, 2, 32, 1)  X(768, 112, 2, 64, 1)  X(768, 104, 2, 64, 1)  X(768, 96, 2, 64, 1) \
+  X(1536, 64, 1, 64, 0)  X(1536, 64, 2, 64, 0)  X(1536, 48, 2, 64, 0)                                          \
+  X(1536, 64, 1, 64, 1)  X(1536, 64, 2, 64, 1)  X(1536, 56, 2, 64, 1)  X(1536, 48, 2, 64, 1)
+
+#define QC_MATCH(D, TB, CG, WBK, GM) \
+  (dim == D && v.token_block == TB && v.cta_group == CG && v.w_bk == WBK && v.gather == GM)
 
 bool encoder_variant_supported(int dim, const EncoderVariant& v) {
-#define X(D, TB, CG, WBK) if (dim == D && v.token_block == TB && v.cta_group == CG && v.w_bk == WBK) return true;
+#define X(D, TB, CG, WBK, GM) if (QC_MATCH(D, TB, CG, WBK, GM)) return true;
   QC_ENC_VARIANTS(X)
 #undef X
   return false;
 }
 
 int encoder_variant_w_stages(int dim, const EncoderVariant& v) {
-#define X(D, TB, CG, WBK) \
-  if (dim == D && v.token_block == TB && v.cta_group == CG && v.w_bk == WBK) return EncTraits<D, TB, CG, WBK>::W_STAGES;
+#define X(D, TB, CG, WBK, GM) if (QC_MATCH(D, TB, CG, WBK, GM)) return EncTraits<D, TB, CG, WBK, GM>::W_STAGES;
   QC_ENC_VARIANTS(X)
 #undef X
   return 0;
@@ -449,17 +557,18 @@ int encoder_variant_w_stages(int dim, const EncoderVariant& v) {
 
 EncoderVariant encoder_default_variant(int dim) {
   switch (dim) {
-    case 384: return EncoderVariant{128, 1, 64};
-    case 768: return EncoderVariant{128, 2, 64};
-    case 1536: return EncoderVariant{64, 2, 64};
-    default: return EncoderVariant{0, 0, 0};
+    // fastest measured on B200 (tools/gpu_tune.py, profiles/k1_variants_r1.md)
+    case 384: return EncoderVariant{128, 1, 64, 0};
+    case 768: return EncoderVariant{128, 2, 64, 1};
+    case 1536: return EncoderVariant{56, 2, 64, 1};
+    default: return EncoderVariant{0, 0, 0, 0};
   }
 }
 
 cudaError_t launch_encode(const EncoderLaunch& a) {
-#define X(D, TB, CG, WBK)                                                                                      \
-  if (a.dim == D && a.variant.token_block == TB && a.variant.cta_group == CG && a.variant.w_bk == WBK)         \
-    return launch_encode_t<EncTraits<D, TB, CG, WBK>>(a);
+  const int dim = a.dim;
+  const EncoderVariant& v = a.variant;
+#define X(D, TB, CG, WBK, GM) if (QC_MATCH(D, TB, CG, WBK, GM)) return launch_encode_t<EncTraits<D, TB, CG, WBK, GM>>(a);
   QC_ENC_VARIANTS(X)
 #undef X
   return cudaErrorInvalidValue;

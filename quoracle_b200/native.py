@@ -111,7 +111,7 @@ def load_library() -> ctypes.CDLL:
     lib.qc_encoder_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                     ctypes.POINTER(ctypes.c_int32)]
     lib.qc_encoder_set_variant.restype = i32
-    lib.qc_encoder_set_variant.argtypes = [vp, i32, i32, i32]
+    lib.qc_encoder_set_variant.argtypes = [vp, i32, i32, i32, i32]
     lib.qc_encoder_stall_profile.restype = i32
     lib.qc_encoder_stall_profile.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]
     lib.qc_encoder_set_cta_group.restype = i32
@@ -311,7 +311,7 @@ class Context:
         return {"cta_group": cg.value, "token_block": tb.value, "w_stages": ws.value}
 
     STALL_FIELDS = ("mma_total", "mma_wait_w", "mma_wait_tokens", "mma_wait_acc", "epi_total", "epi_wait_acc",
-                    "gather_total", "gather_wait_free", "wprod_total", "wprod_wait_free")
+                    "gather_total", "gather_wait_free", "wprod_total", "wprod_wait_free", "gather_wait_loads", "mma_issue", "mma_commit", "gather_fence")
 
     def stall_profile(self, enable: bool = True, read: bool = False):
         """K1 tuning aid: per-role barrier stall cycles of the last encoder launch (averaged over CTAs)."""
@@ -321,8 +321,8 @@ class Context:
             return None
         return {name: float(out[i]) for i, name in enumerate(self.STALL_FIELDS)}
 
-    def set_variant(self, token_block: int, cta_group: int, w_bk: int = 64) -> None:
-        _check(self._lib.qc_encoder_set_variant(self._h, int(token_block), int(cta_group), int(w_bk)))
+    def set_variant(self, token_block: int, cta_group: int, w_bk: int = 64, gather: int = 0) -> None:
+        _check(self._lib.qc_encoder_set_variant(self._h, int(token_block), int(cta_group), int(w_bk), int(gather)))
 
     def set_cta_group(self, cta_group: int) -> None:
         _check(self._lib.qc_encoder_set_cta_group(self._h, int(cta_group)))

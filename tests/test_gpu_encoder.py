@@ -28,10 +28,11 @@ def cta_groups(dim):
     return [1] if dim == 384 else [1, 2]
 
 
-VARIANTS = {384: [(128, 1, 64), (128, 1, 32)],
-            768: [(128, 1, 64), (128, 1, 32), (128, 2, 64), (128, 2, 32), (112, 2, 64), (112, 2, 32), (96, 2, 64),
-                  (96, 2, 32)],
-            1536: [(64, 1, 64), (64, 2, 64), (64, 2, 32), (48, 2, 64), (48, 2, 32)]}
+VARIANTS = {384: [(128, 1, 64, 0), (128, 1, 32, 0), (128, 1, 64, 1)],
+            768: [(128, 1, 64, 0), (128, 1, 32, 0), (128, 2, 64, 0), (128, 2, 32, 0), (112, 2, 64, 0), (104, 2, 64, 0),
+                  (96, 2, 64, 0), (128, 1, 64, 1), (128, 2, 64, 1), (128, 2, 32, 1), (112, 2, 64, 1), (104, 2, 64, 1), (96, 2, 64, 1)],
+            1536: [(64, 1, 64, 0), (64, 2, 64, 0), (48, 2, 64, 0), (64, 1, 64, 1), (64, 2, 64, 1), (56, 2, 64, 1),
+                   (48, 2, 64, 1)]}
 
 
 @pytest.mark.parametrize("dim", [384, 768, 1536])
@@ -45,10 +46,10 @@ def test_every_tiling_variant_matches_oracle(dim):
     tok[np.arange(t)[None, :] >= lens[:, None]] = -1
     want = oenc.encode(w.table_bf16, w.w_bf16, tok, lens)
     with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
-        for (tb, cg, wbk) in VARIANTS[dim]:
-            ctx.set_variant(tb, cg, wbk)
+        for (tb, cg, wbk, gm) in VARIANTS[dim]:
+            ctx.set_variant(tb, cg, wbk, gm)
             got = ctx.embed_batch(tok, lens)
-            assert np.max(np.abs(got - want)) < EMB_TOL, (dim, tb, cg, wbk)
+            assert np.max(np.abs(got - want)) < EMB_TOL, (dim, tb, cg, wbk, gm)
 
 
 @pytest.mark.parametrize("dim", [384, 768, 1536])
