@@ -1,0 +1,57 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/qconsensus.h declares."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+from quoracle_b200 import native
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "qconsensus.h").read_text()
+
+
+def declared_functions():
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    return sorted(set(re.findall(r"\b(qc_[a-z0-9_]+)\s*\(", body)))
+
+
+def test_header_and_binding_list_agree():
+    assert declared_functions() == sorted(native.ABI_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = native.load_library()
+    for name in declared_functions():
+        assert hasattr(lib, name), name
+
+
+def test_status_strings_and_atoms():
+    lib = native.load_library()
+    assert lib.qc_abi_version() == 1
+    atoms = {0: "ok", -1: "invalid_input", -2: "not_configured", -3: "service_unavailable", -4: "service_unavailable",
+             -5: "service_unavailable", -6: "context_length_exceeded", -7: "bad_request", -8: "invalid_input",
+             -9: "service_unavailable"}
+    for code, atom in atoms.items():
+        assert lib.qc_status_atom(code).decode() == atom
+        assert lib.qc_strerror(code).decode() != "unknown status"
+    assert lib.qc_strerror(-99).decode() == "unknown status"
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    """On a box without an sm_100 device the context cannot be created: the product has no CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; covered by the -m gpu tests")
+    with pytest.raises(native.QcError) as e:
+        native.Context(0)
+    assert e.value.status == -3 and e.value.atom == "service_unavailable"
+
+
+def test_null_arguments_are_rejected_not_dereferenced():
+    lib = native.load_library()
+    assert lib.qc_ctx_create(None, 0, None) == -1
+    assert lib.qc_ctx_synchronize(None) == -1
+    assert lib.qc_similarity_batch(None, None, 1, 2, 3, None, None, None, None) == -1
+    assert lib.qc_launch_count(None) == 0
+    lib.qc_ctx_destroy(None)

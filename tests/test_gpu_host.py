@@ -1,0 +1,82 @@
+"""The host-side mirror on a real B200: the GPU rule / collector / lesson dedup agree with the oracle's
+restatement of the reference rule evaluated on the same embedding vectors (what an `:embedding_fn` returns)."""
+import numpy as np
+import pytest
+
+from oracle import consensus_rules as orules
+from oracle import lesson_manager as olm
+from quoracle_b200 import consensus_rules, lesson_manager, native, synth
+from quoracle_b200.collector import DecisionCollector
+from quoracle_b200.embeddings import Embeddings
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def emb():
+    w = synth.make_encoder(768, vocab=32768, seed=synth.BASE_SEED + 9)
+    ctx = native.Context(0, w.table_bf16, w.w_bf16)
+    yield Embeddings(ctx, vocab=32768, model_token_limit=600)
+    ctx.close()
+
+
+def oracle_fn(emb):
+    def fn(value, opts):
+        r = emb.get_embedding(value)
+        return ("ok", {"embedding": r[1]["embedding"].astype(np.float64).tolist()}) if r[0] == "ok" else r
+    return fn
+
+
+SENTENCES = ["deploy the new build to production tonight", "deploy new build to production this evening",
+             "roll back the release and page the on-call engineer", "summarise the quarterly revenue figures",
+             "deploy the new build to production tonight please", "ship it"]
+
+
+def test_rule_on_gpu_matches_oracle_rule(emb):
+    fn = oracle_fn(emb)
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        n = int(rng.integers(2, 9))
+        values = [SENTENCES[int(i)] for i in rng.integers(0, len(SENTENCES), n)]
+        thr = float(rng.choice([0.8, 0.85, 0.9, 0.95, 0.99, 0.999]))
+        want = orules.apply_rule(("semantic_similarity", thr), values, {"embedding_fn": fn})
+        got = consensus_rules.apply_rule(emb, values, thr)
+        # guard the f32/f64 threshold edge: recompute the margin with the oracle cosine
+        if len(set(values)) > 1:
+            e = [fn(v, {})[1]["embedding"] for v in values]
+            margin = min(abs(orules.cosine_similarity(e[0], x) - thr) for x in e[1:])
+            if margin < 2e-5:
+                continue
+        assert got == want, (values, thr)
+
+
+def test_long_text_is_chunked_and_mean_is_unnormalised(emb):
+    long_text = " ".join(f"token{i % 97}" for i in range(1500))          # > 540 tokens -> 3 chunks
+    r = emb.get_embedding(long_text, {"cache_ttl": 0})
+    assert r[0] == "ok" and r[1]["chunks"] == 3
+    assert np.linalg.norm(r[1]["embedding"]) <= 1.0 + 1e-5
+    r2 = emb.get_embedding(long_text)
+    r3 = emb.get_embedding(long_text)
+    assert r3[1]["cached"] is True and np.array_equal(r2[1]["embedding"], r3[1]["embedding"])
+
+
+def test_collector_one_gpu_call_for_the_tree(emb):
+    col = DecisionCollector(emb)
+    before = emb.ctx.launch_count()
+    calls = emb.gpu_calls
+    for a in range(64):
+        col.submit(f"a{a}", "content", [f"{SENTENCES[a % 3]} run {a}", f"{SENTENCES[a % 3]} run {a} now", SENTENCES[3]], 0.9)
+    out = col.flush()
+    assert emb.gpu_calls == calls + 1                                     # one embed call for 192 values
+    assert emb.ctx.launch_count() - before == 3                           # K1 + K2 + one K3
+    assert len(out) == 64 and all(v["content"]["medoid"] in (0, 1, 2) for v in out.values())
+
+
+def test_lesson_dedup_matches_oracle(emb):
+    fn1 = lambda t: oracle_fn(emb)(t, {})                                 # noqa: E731
+    existing = [{"type": "factual", "content": s, "confidence": i + 1} for i, s in enumerate(SENTENCES[:4])]
+    for new, thr in [(SENTENCES[4], 0.9), ("completely unrelated words about zebras", 0.9999), (SENTENCES[0], 0.9)]:
+        lesson = {"type": "factual", "content": new, "confidence": 1}
+        want = olm.deduplicate_lesson(lesson, existing, {"embedding_fn": fn1, "similarity_threshold": thr})
+        got = lesson_manager.deduplicate_lesson(emb, lesson, existing, thr)
+        assert got == want

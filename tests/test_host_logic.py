@@ -1,0 +1,112 @@
+"""CPU tests of the host-side mirror (tokenizer, Embeddings, consensus rule, collector, lesson manager,
+sharding maths) with a fake context whose arithmetic is the oracle's."""
+import numpy as np
+
+from oracle import consensus_rules as orules
+from oracle import embeddings as oemb
+from quoracle_b200 import consensus_rules, lesson_manager, sharding, synth, tokenizer
+from quoracle_b200.collector import DecisionCollector
+from quoracle_b200.embeddings import Embeddings, chunk_text_by_tokens
+from tests.fake_ctx import FakeContext
+
+W = synth.make_encoder(384, vocab=4096, seed=7)
+
+
+def make_emb(**kw):
+    ctx = FakeContext(W.table_bf16, W.w_bf16)
+    return Embeddings(ctx, vocab=4096, **kw), ctx
+
+
+def test_tokenizer_is_fnv1a_and_stable():
+    assert tokenizer.fnv1a32(b"") == 0x811C9DC5
+    assert tokenizer.fnv1a32(b"a") == 0xE40C292C
+    assert tokenizer.fnv1a32(b"foobar") == 0xBF9CF968
+    ids, lens = tokenizer.pack(["deploy the build", "", "one"], vocab=4096)
+    assert lens.tolist() == [3, 0, 1] and ids.shape == (3, 3)
+    assert ids[0].tolist() == tokenizer.tokenize("deploy the build", 4096) and (ids[1] == -1).all()
+    assert all(0 <= t < 4096 for t in ids[0])
+
+
+def test_chunker_matches_the_oracle_restatement():
+    text = " ".join(f"w{i}" for i in range(57))
+    for limit in (1, 4, 9, 56, 57, 100):
+        assert chunk_text_by_tokens(text, limit) == oemb.chunk_text_by_tokens(text, limit)
+
+
+def test_embeddings_cache_dedup_chunks_and_shapes():
+    emb, ctx = make_emb(model_token_limit=10)
+    r = emb.get_embeddings(["alpha beta", "alpha beta", "", "gamma", {"k": [1, 2]}])
+    assert ctx.calls["embed"] == 1                                  # one GPU call for the whole batch
+    assert r[2] == ("error", "invalid_input")
+    assert r[0][0] == "ok" and r[0][1]["cached"] is False and np.array_equal(r[0][1]["embedding"], r[1][1]["embedding"])
+    again = emb.get_embeddings(["alpha beta"])
+    assert again[0][1]["cached"] is True and ctx.calls["embed"] == 1
+    long_text = " ".join(f"w{i}" for i in range(40))
+    lr = emb.get_embedding(long_text)
+    assert lr[0] == "ok" and lr[1]["chunks"] > 2 and ctx.calls["chunk_mean"] == 1
+    # the chunk mean is unweighted and NOT re-normalised (embeddings.ex:371-383)
+    assert np.linalg.norm(lr[1]["embedding"]) < 1.0 + 1e-6
+    # accumulator shape: 3-tuple when not cached, 2-tuple when cached
+    acc = orules.Accumulator()
+    a = emb.get_embedding("fresh text", {"cost_accumulator": acc})
+    b = emb.get_embedding("fresh text", {"cost_accumulator": acc})
+    assert len(a) == 3 and a[2].count() == 1 and len(b) == 2 and b[1]["cached"] is True
+    assert emb.get_embedding("bypass", {"cache_ttl": 0})[1]["cached"] is False
+    assert emb.get_embedding("bypass", {"cache_ttl": 0})[1]["cached"] is False
+
+
+def test_rule_mirror_agrees_with_the_oracle_rule_for_the_same_embedding_function():
+    emb, ctx = make_emb()
+    fn = emb.embedding_fn()
+    ofn = lambda v, o: (lambda r: ("ok", {"embedding": r[1]["embedding"].astype(np.float64).tolist()}) if r[0] == "ok" else r)(fn(v, {}))  # noqa: E731
+    cases = [(["same", "same", "same"], 0.9), (["deploy build now", "deploy build now please"], 0.5),
+             (["red green blue", "quantum flux capacitor"], 0.999999), ([], 0.9), (["only"], 0.9),
+             (["a b c d", "a b c e", "a b c f", "zzz yyy"], 0.9999)]
+    for values, thr in cases:
+        want = orules.apply_rule(("semantic_similarity", thr), values, {"embedding_fn": ofn})
+        got = consensus_rules.apply_rule(emb, values, thr)
+        if values == []:
+            assert got == ("error", "no_values") and want == ("error", "no_consensus")   # private vs public mapping
+        else:
+            assert got == want, (values, thr)
+    before = ctx.calls["embed"]
+    assert consensus_rules.apply_rule(emb, ["x", "x"], 0.9) == ("ok", "x") and ctx.calls["embed"] == before
+
+
+def test_collector_batches_a_whole_tree_into_one_call():
+    emb, ctx = make_emb()
+    col = DecisionCollector(emb)
+    for a in range(20):
+        col.submit(f"agent-{a}", "content", [f"send report {a}", f"send the report {a}", f"send report {a} now"], 0.5)
+        col.submit(f"agent-{a}", "task_description", ["same", "same", "same"], 0.95)
+    out = col.flush()
+    assert ctx.calls["embed"] == 1 and ctx.calls["similarity"] == 1
+    assert len(out) == 20 and out["agent-3"]["task_description"]["result"] == ("ok", "same")
+    assert out["agent-3"]["content"]["result"][0] in ("ok", "error") and out["agent-3"]["content"]["medoid"] in (0, 1, 2)
+    assert col.flush() == {}
+
+
+def test_lesson_manager_mirror():
+    emb, ctx = make_emb()
+    ex = [{"type": "factual", "content": "API requires bearer auth", "confidence": 2}]
+    ok, out = lesson_manager.accumulate_lessons(emb, ex, [{"type": "factual", "content": "API requires bearer auth", "confidence": 1}])
+    assert out == [{"type": "factual", "content": "API requires bearer auth", "confidence": 3}]
+    ok, out = lesson_manager.accumulate_lessons(emb, ex, [{"type": "factual", "content": "zebra xylophone quartz", "confidence": 1}],
+                                                threshold=0.9999)
+    assert len(out) == 2
+    assert [l["confidence"] for l in lesson_manager.prune_lessons(
+        [{"content": str(i), "confidence": c} for i, c in enumerate([1, 5, 2])], 2)] == [5, 2]
+
+
+def test_sharding_maths():
+    for n, w in [(256, 1), (4096, 8), (10, 3), (7, 8)]:
+        blocks = [sharding.shard_range(n, r, w) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        assert max(hi - lo for lo, hi in blocks) - min(hi - lo for lo, hi in blocks) <= 1
+    order = sharding.tree_agent_order(4, 8)
+    assert len(order) == 8 + 64 + 512 + 4096 and order[0] == (0,) and order[1] == (0, 0)
+    assert sum(1 for p in order if len(p) == 4) == 4096                      # BASELINE config 3 leaves
+    parts = [sharding.shard_tree(4, 8, r, 8) for r in range(8)]
+    assert sum(len(p) for p in parts) == len(order)
+    assert all(p[0][0] == r for r, p in enumerate(parts))                     # a top-level subtree per GPU

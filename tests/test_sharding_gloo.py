@@ -1,0 +1,59 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: verdict gathering and the split-pool
+all-gather path.  The similarity function is injected (the oracle here, K3 on GPUs)."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(ROOT))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import numeric
+    from quoracle_b200 import sharding, synth
+
+    # 1. shard by agent, no collective on the data path; gather verdicts afterwards
+    b, n, d = 37, 8, 64
+    emb = synth.make_embeddings(b, n, d, seed=5)
+    thr = np.full(b, 0.5, np.float32)
+    lo, hi = sharding.shard_range(b, rank, world)
+    ok, med, _, _ = numeric.decide_batch(emb[lo:hi], thr[lo:hi])
+    all_ok = sharding.gather_verdicts(ok, b)
+    all_med = sharding.gather_verdicts(med, b)
+    ref_ok, ref_med, _, _ = numeric.decide_batch(emb, thr)
+    assert np.array_equal(all_ok, ref_ok) and np.array_equal(all_med, ref_med)
+
+    # 2. one agent's pool spans the two ranks: all-gather of the local rows, then the similarity kernel
+    n_local = n // world
+    local = torch.from_numpy(emb[:, rank * n_local:(rank + 1) * n_local].copy())
+
+    def sim(full, t):
+        o, m, _, _ = numeric.decide_batch(full.numpy(), t)
+        return o, m
+
+    (ok2, med2), full = sharding.decide_split_pool(local, thr, sim)
+    assert full.shape == (b, n, d) and np.array_equal(full.numpy(), emb)
+    assert np.array_equal(ok2, ref_ok) and np.array_equal(med2, ref_med)
+    Path(out_dir, f"ok{rank}").write_text("ok")
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
