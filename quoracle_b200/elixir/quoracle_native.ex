@@ -1,0 +1,193 @@
+defmodule Quoracle.Native do
+  @moduledoc """
+  Elixir side of the B200 consensus hot path: NIF stubs (qconsensus_nif.c over libqconsensus.so), the
+  hashing tokenizer, binary packing, an `:embedding_fn`-compatible closure and the cross-agent collector.
+
+  NOT COMPILED OR RUN IN THE BUILD REPOSITORY (no BEAM in its image); the executable specification of
+  this module is the Python mirror (`quoracle_b200/{tokenizer,embeddings,consensus_rules,collector}.py`)
+  and its tests.  Wiring into Quoracle is described in INTEGRATION.md.
+  """
+
+  @on_load :load_nif
+  @vocab 32_768
+  @fnv_offset 0x811C9DC5
+  @fnv_prime 0x01000193
+
+  def load_nif do
+    path = :filename.join(:code.priv_dir(:quoracle), ~c"qconsensus_nif")
+    :erlang.load_nif(path, 0)
+  end
+
+  # ---- NIF stubs (dirty CPU-bound; replaced at load) -------------------------------------------------
+  def ctx_create(_device, _vocab, _dim, _table_bf16, _w_bf16), do: :erlang.nif_error(:nif_not_loaded)
+  def decide_batch(_ctx, _tok, _lens, _b, _n, _t, _thr, _want_cos), do: :erlang.nif_error(:nif_not_loaded)
+  def embed_batch(_ctx, _tok, _lens, _r, _t), do: :erlang.nif_error(:nif_not_loaded)
+  def similarity_batch(_ctx, _emb, _b, _n, _d, _thr), do: :erlang.nif_error(:nif_not_loaded)
+  def first_match_batch(_ctx, _query, _rows, _q, _m, _d, _thr), do: :erlang.nif_error(:nif_not_loaded)
+  def chunk_mean(_ctx, _chunks, _g, _c, _d), do: :erlang.nif_error(:nif_not_loaded)
+  def launch_count(_ctx), do: :erlang.nif_error(:nif_not_loaded)
+
+  # ---- tokenizer: FNV-1a-32 of whitespace words, mod vocab (same function as tokenizer.py) -----------
+  @spec tokenize(String.t()) :: [non_neg_integer()]
+  def tokenize(text) do
+    text |> String.split() |> Enum.map(&(rem(fnv1a32(&1), @vocab)))
+  end
+
+  defp fnv1a32(word) do
+    import Bitwise
+
+    word
+    |> :binary.bin_to_list()
+    |> Enum.reduce(@fnv_offset, fn byte, h -> band(bxor(h, byte) * @fnv_prime, 0xFFFFFFFF) end)
+  end
+
+  @doc "Pack token id lists into the NIF's little-endian int32 layout: {ids_bin, lens_bin, t}."
+  def pack(token_lists) do
+    t = token_lists |> Enum.map(&length/1) |> Enum.max(fn -> 1 end) |> max(1)
+
+    ids =
+      for toks <- token_lists, into: <<>> do
+        pad = List.duplicate(-1, t - length(toks))
+        for id <- toks ++ pad, into: <<>>, do: <<id::little-signed-32>>
+      end
+
+    lens = for toks <- token_lists, into: <<>>, do: <<length(toks)::little-signed-32>>
+    {ids, lens, t}
+  end
+
+  defp floats(bin), do: for(<<f::little-float-32 <- bin>>, do: f)
+  defp ints(bin), do: for(<<i::little-signed-32 <- bin>>, do: i)
+
+  # ---- `:embedding_fn` seam (lib/quoracle/actions/consensus_rules.ex:22,325-327) ---------------------
+  @doc """
+  Returns a 2-arity closure with the reference's `:embedding_fn` contract: `fn value, opts ->
+  {:ok, %{embedding: [float]}} | {:ok, %{embedding: [float]}, acc} | {:error, atom}`.  Non-binary values
+  are JSON-encoded and `""` is `{:error, :invalid_input}` as in Embeddings.get_embedding/2
+  (lib/quoracle/models/embeddings.ex:46-50).  A local embedding costs nothing, so a supplied
+  `:cost_accumulator` is handed back untouched in the 3-tuple.
+  """
+  def embedding_fn(ctx) do
+    fn value, opts ->
+      text = if is_binary(value), do: value, else: Jason.encode!(value)
+
+      if text == "" do
+        {:error, :invalid_input}
+      else
+        {ids, lens, t} = pack([tokenize(text)])
+
+        case embed_batch(ctx, ids, lens, 1, t) do
+          {:ok, emb} ->
+            result = %{embedding: floats(emb), cached: false, chunks: 1}
+
+            case Map.get(opts, :cost_accumulator) do
+              nil -> {:ok, result}
+              acc -> {:ok, result, acc}
+            end
+
+          {:error, reason} ->
+            {:error, reason}
+        end
+      end
+    end
+  end
+
+  # ---- the rule on the GPU: all N values of a parameter in one call -----------------------------------
+  @doc """
+  `{:semantic_similarity, threshold: t}` for many merges at once.  `merges :: [{values, threshold}]`.
+  Returns one `{:ok, value_0} | {:error, :no_consensus}` per merge -- the results
+  ConsensusRules.apply_rule/3 would give (consensus_rules.ex:249-299), identical values short-circuiting
+  without touching the GPU (:251-256).
+  """
+  def decide_many(ctx, dim, merges) do
+    {trivial, pending} =
+      merges
+      |> Enum.with_index()
+      |> Enum.split_with(fn {{values, _thr}, _i} -> length(Enum.uniq(values)) <= 1 end)
+
+    trivial_results =
+      Enum.map(trivial, fn
+        {{[], _}, i} -> {i, {:error, :no_values}}
+        {{[v | _], _}, i} -> {i, {:ok, v}}
+      end)
+
+    gpu_results =
+      pending
+      |> Enum.group_by(fn {{values, _}, _} -> length(values) end)
+      |> Enum.flat_map(fn {n, group} ->
+        texts = Enum.flat_map(group, fn {{values, _}, _} -> Enum.map(values, &stringify/1) end)
+        {ids, lens, t} = pack(Enum.map(texts, &tokenize/1))
+        thr = for {{_, th}, _} <- group, into: <<>>, do: <<th::little-float-32>>
+        b = length(group)
+
+        with {:ok, emb} <- embed_batch(ctx, ids, lens, b * n, t),
+             {:ok, ref_ok, _medoid, _cos} <- similarity_batch(ctx, emb, b, n, dim, thr) do
+          Enum.zip(group, ints(ref_ok))
+          |> Enum.map(fn
+            {{{[v0 | _], _}, i}, 1} -> {i, {:ok, v0}}
+            {{_, i}, _} -> {i, {:error, :no_consensus}}
+          end)
+        else
+          {:error, _reason} -> Enum.map(group, fn {_, i} -> {i, {:error, :no_consensus}} end)
+        end
+      end)
+
+    (trivial_results ++ gpu_results) |> Enum.sort_by(&elem(&1, 0)) |> Enum.map(&elem(&1, 1))
+  end
+
+  defp stringify(v) when is_binary(v), do: v
+  defp stringify(v), do: Jason.encode!(v)
+end
+
+defmodule Quoracle.Native.Collector do
+  @moduledoc """
+  Cross-agent batching GenServer: agents `submit/4` their semantic-parameter merges and block on the
+  reply; the collector flushes when `max_pending` merges are queued or `max_wait_ms` after the first one,
+  whichever comes first, with ONE `Quoracle.Native.decide_many/3` call (one dirty-scheduler NIF entry per
+  pool size), and replies to every caller.  Bounded wait keeps single-agent latency near today's
+  cache-hit path (SURVEY.md section 7, "Latency vs batching").  Started under the application supervisor next to
+  `Quoracle.Models.EmbeddingCache` (lib/quoracle/application.ex:38-61); the pid is passed in opts (no named
+  processes, per the repo's Credo concurrency checks).
+  """
+  use GenServer
+
+  def start_link(opts), do: GenServer.start_link(__MODULE__, opts)
+
+  @doc "Blocking: returns `{:ok, value_0} | {:error, :no_consensus}` for one parameter merge."
+  def submit(collector, values, threshold, timeout \\ 30_000) do
+    GenServer.call(collector, {:submit, values, threshold}, timeout)
+  end
+
+  @impl true
+  def init(opts) do
+    {:ok,
+     %{
+       ctx: Keyword.fetch!(opts, :ctx),
+       dim: Keyword.fetch!(opts, :dim),
+       max_pending: Keyword.get(opts, :max_pending, 4096),
+       max_wait_ms: Keyword.get(opts, :max_wait_ms, 2),
+       queue: [],
+       timer: nil
+     }}
+  end
+
+  @impl true
+  def handle_call({:submit, values, threshold}, from, state) do
+    queue = [{from, values, threshold} | state.queue]
+    timer = state.timer || Process.send_after(self(), :flush, state.max_wait_ms)
+    state = %{state | queue: queue, timer: timer}
+    if length(queue) >= state.max_pending, do: {:noreply, flush(state)}, else: {:noreply, state}
+  end
+
+  @impl true
+  def handle_info(:flush, state), do: {:noreply, flush(state)}
+
+  defp flush(%{queue: []} = state), do: %{state | timer: nil}
+
+  defp flush(state) do
+    if state.timer, do: Process.cancel_timer(state.timer)
+    batch = Enum.reverse(state.queue)
+    results = Quoracle.Native.decide_many(state.ctx, state.dim, Enum.map(batch, fn {_, v, t} -> {v, t} end))
+    Enum.zip(batch, results) |> Enum.each(fn {{from, _, _}, r} -> GenServer.reply(from, r) end)
+    %{state | queue: [], timer: nil}
+  end
+end
