@@ -125,8 +125,14 @@ def cpu_sim_only(emb, thr, threads):
 
 
 def cpu_threads() -> int:
+    """All host threads this process may use.  torchrun exports OMP_NUM_THREADS=1, which would silently turn
+    the CPU arm into a single-core run, so the count comes from the affinity mask, not from OpenMP."""
     from oracle import cport
-    return int(cport.max_threads(native=True))
+    cport.load(native=True)
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def calibrate_cpu_sample(weights, batch, threads, target_s):

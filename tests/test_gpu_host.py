@@ -51,9 +51,11 @@ def test_rule_on_gpu_matches_oracle_rule(emb):
 
 
 def test_long_text_is_chunked_and_mean_is_unnormalised(emb):
-    long_text = " ".join(f"token{i % 97}" for i in range(1500))          # > 540 tokens -> 3 chunks
+    from oracle import embeddings as oemb
+    long_text = " ".join(f"token{i % 97}" for i in range(1500))          # limit trunc(600 * 0.9) = 540
+    want_chunks = len(oemb.chunk_text_by_tokens(long_text, 540))          # words cost 1 + 1 per separator -> 6
     r = emb.get_embedding(long_text, {"cache_ttl": 0})
-    assert r[0] == "ok" and r[1]["chunks"] == 3
+    assert r[0] == "ok" and r[1]["chunks"] == want_chunks == 6
     assert np.linalg.norm(r[1]["embedding"]) <= 1.0 + 1e-5
     r2 = emb.get_embedding(long_text)
     r3 = emb.get_embedding(long_text)
