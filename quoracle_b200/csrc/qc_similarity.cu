@@ -104,101 +104,110 @@ __device__ __forceinline__ void verdict_tail(int N, float thr, CosFn c, int32_t*
 }
 
 // ------------------------------------------------------------------------------------------
-// K3 path A: N <= 8.  One warp per decision; every lane streams 16-byte column chunks of all
-// N rows, keeps the N(N+1)/2 partial dot products in registers, one butterfly reduction at the end.
+// K3 path A: N <= 8.  WPD warps per decision (1 for large batches, 4 when the batch alone cannot fill
+// the GPU); every lane streams 16-byte column chunks of all N rows and keeps the N(N+1)/2 partial dot
+// products in registers.  The cross-lane reduction and the verdict tail are DISTRIBUTED through shared
+// memory (lane p sums pair p in a fixed order, lane e forms cosine element e, lane i the row mean i):
+// doing the tail redundantly on every lane cost as many instructions as the streaming loop itself.
 // ------------------------------------------------------------------------------------------
-template <int N, bool VEC>
+template <int N, bool VEC, int WPD>
 __global__ void __launch_bounds__(256) qc_sim_small_kernel(const float* __restrict__ emb, int B, int D,
                                                            const float* __restrict__ thr,
                                                            int32_t* __restrict__ ref_ok,
                                                            int32_t* __restrict__ medoid, float* __restrict__ cos) {
   constexpr int P = N * (N + 1) / 2;
+  constexpr int DPB = 8 / WPD;             // decisions per 8-warp block
+  constexpr int GT = 32 * WPD;             // threads cooperating on one decision
+  __shared__ float red[DPB][P][GT + 1];
+  __shared__ float tot[DPB][P];
+  __shared__ float cs[DPB][N * N];
+  __shared__ float rmean[DPB][N];
+
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= B) return;
-  const float* x = emb + static_cast<size_t>(b) * N * D;
+  const int warp = threadIdx.x >> 5;
+  const int ds = warp / WPD;               // decision slot in this block
+  const int slice = warp % WPD;            // which part of the columns this warp streams
+  const int tg = slice * 32 + lane;        // thread index within the decision group
+  const int b = blockIdx.x * DPB + ds;
+  const bool live = b < B;
+
   float acc[P];
 #pragma unroll
   for (int p = 0; p < P; ++p) acc[p] = 0.f;
-
-  if constexpr (VEC) {
-    for (int col = lane * 4; col < D; col += 128) {
-      float4 v[N];
+  if (live) {
+    const float* x = emb + static_cast<size_t>(b) * N * D;
+    if constexpr (VEC) {
+      for (int col = tg * 4; col < D; col += GT * 4) {
+        float4 v[N];
 #pragma unroll
-      for (int i = 0; i < N; ++i) v[i] = ldg_stream4(x + static_cast<size_t>(i) * D + col);
-      int p = 0;
+        for (int i = 0; i < N; ++i) v[i] = ldg_stream4(x + static_cast<size_t>(i) * D + col);
+        int p = 0;
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
+        for (int i = 0; i < N; ++i) {
 #pragma unroll
-        for (int j = i; j < N; ++j, ++p) {
-          acc[p] = fmaf(v[i].x, v[j].x, acc[p]);
-          acc[p] = fmaf(v[i].y, v[j].y, acc[p]);
-          acc[p] = fmaf(v[i].z, v[j].z, acc[p]);
-          acc[p] = fmaf(v[i].w, v[j].w, acc[p]);
+          for (int j = i; j < N; ++j, ++p) {
+            acc[p] = fmaf(v[i].x, v[j].x, acc[p]);
+            acc[p] = fmaf(v[i].y, v[j].y, acc[p]);
+            acc[p] = fmaf(v[i].z, v[j].z, acc[p]);
+            acc[p] = fmaf(v[i].w, v[j].w, acc[p]);
+          }
+        }
+      }
+    } else {
+      for (int col = tg; col < D; col += GT) {
+        float v[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = __ldg(x + static_cast<size_t>(i) * D + col);
+        int p = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+#pragma unroll
+          for (int j = i; j < N; ++j, ++p) acc[p] = fmaf(v[i], v[j], acc[p]);
         }
       }
     }
-  } else {
-    for (int col = lane; col < D; col += 32) {
-      float v[N];
-#pragma unroll
-      for (int i = 0; i < N; ++i) v[i] = __ldg(x + static_cast<size_t>(i) * D + col);
-      int p = 0;
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-#pragma unroll
-        for (int j = i; j < N; ++j, ++p) acc[p] = fmaf(v[i], v[j], acc[p]);
-      }
-    }
   }
 #pragma unroll
-  for (int p = 0; p < P; ++p) acc[p] = warp_sum(acc[p]);
-
-  // Full cosine matrix in registers (every lane holds the same values).
-  float nrm[N];
-  float cm[N][N];
-  {
-    int p = 0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      nrm[i] = sqrtf(acc[p]);
-      p += N - i;
-    }
-    p = 0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-#pragma unroll
-      for (int j = i; j < N; ++j, ++p) {
-        const float c = cosine_from(acc[p], nrm[i], nrm[j]);
-        cm[i][j] = c;
-        cm[j][i] = c;
-      }
-    }
+  for (int p = 0; p < P; ++p) red[ds][p][tg] = acc[p];
+  __syncthreads();
+  // pair p: fixed-order sum of the GT per-thread partials
+  for (int p = tg; p < P; p += GT) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int t = 0; t < GT; ++t) s += red[ds][p][t];
+    tot[ds][p] = s;
   }
-  if (cos != nullptr) {
-    float* o = cos + static_cast<size_t>(b) * N * N;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        if (lane == ((i * N + j) & 31)) o[i * N + j] = cm[i][j];
-      }
-    }
+  __syncthreads();
+  // cosine element e = (i, j); pair index of (i <= j) is i*N - i(i-1)/2 + (j - i)
+  for (int e = tg; e < N * N; e += GT) {
+    const int i = e / N, j = e - i * N;
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    const float dot = tot[ds][lo * N - lo * (lo - 1) / 2 + (hi - lo)];
+    const float ni = sqrtf(tot[ds][i * N - i * (i - 1) / 2]);
+    const float nj = sqrtf(tot[ds][j * N - j * (j - 1) / 2]);
+    const float c = cosine_from(dot, ni, nj);
+    cs[ds][e] = c;
+    if (live && cos != nullptr) cos[static_cast<size_t>(b) * N * N + e] = c;
   }
-  if (lane == 0) {
+  __syncthreads();
+  if (tg < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) s += cs[ds][tg * N + j];   // j ascending, diagonal included
+    rmean[ds][tg] = s / static_cast<float>(N);
+  }
+  __syncthreads();
+  if (tg == 0 && live) {
+    const float th = thr[b];
     int ok = 1;
 #pragma unroll
-    for (int i = 1; i < N; ++i) ok &= (cm[0][i] >= thr[b]) ? 1 : 0;
+    for (int i = 1; i < N; ++i) ok &= (cs[ds][i] >= th) ? 1 : 0;
     int best = 0;
-    float best_mean = 0.f;
+    float best_mean = rmean[ds][0];
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < N; ++j) s += cm[i][j];
-      const float m = s / static_cast<float>(N);
-      if (i == 0 || m > best_mean) {
-        best_mean = m;
+    for (int i = 1; i < N; ++i) {
+      if (rmean[ds][i] > best_mean) {
+        best_mean = rmean[ds][i];
         best = i;
       }
     }
@@ -353,11 +362,19 @@ constexpr int kSimLargeSmem = (2 * 64 * kSimRS + 64 * 65) * static_cast<int>(siz
 
 template <int N>
 static cudaError_t launch_small(const float* emb, int B, int D, const float* thr, int32_t* ref_ok, int32_t* medoid,
-                                float* cos, bool vec, cudaStream_t stream) {
-  const int wpb = 8;
-  const int grid = (B + wpb - 1) / wpb;
-  if (vec) qc_sim_small_kernel<N, true><<<grid, wpb * 32, 0, stream>>>(emb, B, D, thr, ref_ok, medoid, cos);
-  else qc_sim_small_kernel<N, false><<<grid, wpb * 32, 0, stream>>>(emb, B, D, thr, ref_ok, medoid, cos);
+                                float* cos, bool vec, int num_sms, cudaStream_t stream) {
+  // one warp per decision needs >= ~16 warps per SM in flight to cover HBM latency; below that, split the
+  // columns of each decision over four warps
+  const bool wide = B < num_sms * 16;
+  if (wide) {
+    const int grid = (B + 1) / 2;
+    if (vec) qc_sim_small_kernel<N, true, 4><<<grid, 256, 0, stream>>>(emb, B, D, thr, ref_ok, medoid, cos);
+    else qc_sim_small_kernel<N, false, 4><<<grid, 256, 0, stream>>>(emb, B, D, thr, ref_ok, medoid, cos);
+  } else {
+    const int grid = (B + 7) / 8;
+    if (vec) qc_sim_small_kernel<N, true, 1><<<grid, 256, 0, stream>>>(emb, B, D, thr, ref_ok, medoid, cos);
+    else qc_sim_small_kernel<N, false, 1><<<grid, 256, 0, stream>>>(emb, B, D, thr, ref_ok, medoid, cos);
+  }
   return cudaGetLastError();
 }
 
@@ -367,14 +384,14 @@ cudaError_t launch_similarity(const float* emb, int B, int N, int D, const float
   if (N < 1 || N > 64 || D < 1) return cudaErrorInvalidValue;
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(emb) & 15) == 0);
   switch (N) {
-    case 1: return launch_small<1>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
-    case 2: return launch_small<2>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
-    case 3: return launch_small<3>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
-    case 4: return launch_small<4>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
-    case 5: return launch_small<5>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
-    case 6: return launch_small<6>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
-    case 7: return launch_small<7>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
-    case 8: return launch_small<8>(emb, B, D, thr, ref_ok, medoid, cos, vec, stream);
+    case 1: return launch_small<1>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
+    case 2: return launch_small<2>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
+    case 3: return launch_small<3>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
+    case 4: return launch_small<4>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
+    case 5: return launch_small<5>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
+    case 6: return launch_small<6>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
+    case 7: return launch_small<7>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
+    case 8: return launch_small<8>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
     default: break;
   }
   static bool attr_set = false;
