@@ -259,16 +259,27 @@ def run_ours(args):
     pin_len.array[...] = batches[0].lens
     pin_thr = native.PinnedArray((b,), np.float32)
     pin_thr.array[...] = batches[0].thr
-    pin_ok = native.PinnedArray((b,), np.int32)
-    pin_med = native.PinnedArray((b,), np.int32)
-    out = native.DecideResult(pin_ok.array, pin_med.array, None, None)
+    # Two-deep pipeline of the host API (qc_decide_batch_submit / _wait): the H2D copy of step k+1 overlaps the
+    # GPU work of step k; every step still copies its own inputs from pinned host memory and reads its own
+    # verdicts back, all inside the timed region.
+    pin_ok = [native.PinnedArray((b,), np.int32) for _ in range(2)]
+    pin_med = [native.PinnedArray((b,), np.int32) for _ in range(2)]
+    outs = [native.DecideResult(pin_ok[k].array, pin_med[k].array, None, None) for k in range(2)]
     e2e_steps = args.steps
-    for i in range(min(3, args.warmup)):
-        ctx.decide_batch(pinned_tok[i % E2E_ROTATE].array, pin_len.array, pin_thr.array, want_cos=False, out=out)
+
+    def e2e_run(nsteps):
+        for i in range(nsteps):
+            k = i & 1
+            if i >= 2:
+                ctx.decide_batch_wait(k)
+            ctx.decide_batch_submit(k, pinned_tok[i % E2E_ROTATE].array, pin_len.array, pin_thr.array, outs[k])
+        for i in range(max(0, nsteps - 2), nsteps):
+            ctx.decide_batch_wait(i & 1)
+
+    e2e_run(max(3, min(6, args.warmup)))
     barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        ctx.decide_batch(pinned_tok[i % E2E_ROTATE].array, pin_len.array, pin_thr.array, want_cos=False, out=out)
+    e2e_run(e2e_steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -310,7 +321,7 @@ def run_ours(args):
                        "encoder": ctx.encoder_info(), "seed": synth.BASE_SEED + 2},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": b * n * t * 4 + b * n * 4 + b * 4,
                     "d2h_bytes_per_step": 2 * b * 4, "steps": e2e_steps,
-                    "api": "qc_decide_batch (host C ABI), pinned host buffers, wall clock"},
+                    "api": "qc_decide_batch_submit/_wait (host C ABI, two batches in flight), pinned host buffers, wall clock"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "qc_encode_kernel (K1)", "achieved": achieved, "peak": peak,

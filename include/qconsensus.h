@@ -116,6 +116,16 @@ int qc_decide_batch(qc_ctx* ctx, const int32_t* token_ids, const int32_t* lens, 
                     const float* thr, int32_t* out_ref_ok, int32_t* out_medoid, float* out_cos,
                     float* out_emb);
 
+/*
+ * Two-deep pipelined form of qc_decide_batch: `submit` enqueues the copies and kernels of one batch on
+ * slot 0 or 1 and returns; `wait` blocks until that slot's outputs are in the caller's buffers.  A caller
+ * (the NIF collector) that submits batch k+1 before waiting for batch k overlaps its host->device copy with
+ * the GPU work of batch k.  Input and output buffers must stay valid and untouched until `wait` returns.
+ */
+int qc_decide_batch_submit(qc_ctx* ctx, int slot, const int32_t* token_ids, const int32_t* lens, int B, int N,
+                           int T, const float* thr, int32_t* out_ref_ok, int32_t* out_medoid, float* out_cos);
+int qc_decide_batch_wait(qc_ctx* ctx, int slot);
+
 /* Embedding only: R candidate rows -> out_emb [R*dim] f32 (what an `:embedding_fn` returns). */
 int qc_embed_batch(qc_ctx* ctx, const int32_t* token_ids, const int32_t* lens, int R, int T,
                    float* out_emb);

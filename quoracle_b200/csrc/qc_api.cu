@@ -61,6 +61,22 @@ struct ProfRec {
   cudaEvent_t start, stop;
 };
 
+struct PendingOut {
+  void* user;
+  const void* staged;
+  size_t bytes;
+};
+
+// One in-flight batch of the pipelined host API (qc_decide_batch_submit / _wait): its own stream,
+// device workspaces, pinned staging and status words, so two batches can overlap copy and compute.
+struct Slot {
+  cudaStream_t stream = nullptr;
+  DevBuf tok, lens, thr, emb, refok, medoid, cosm, part;
+  HostBuf h_in, h_out, h_flags;
+  std::vector<PendingOut> pend;
+  bool busy = false;
+};
+
 }  // namespace
 
 struct qc_ctx {
@@ -78,6 +94,7 @@ struct qc_ctx {
   int32_t hang[4] = {};
   // workspaces
   DevBuf part, emb, tok, lens, thr, cosm, refok, medoid, q, rows, idx, stall;
+  Slot slots[2];
   bool stall_on = false;
   HostBuf h_in, h_out;
   // counters / profiling
@@ -223,12 +240,6 @@ int h2d(qc_ctx* c, void* dst, const void* src, size_t bytes, size_t* stage_off) 
   return QC_OK;
 }
 
-struct PendingOut {
-  void* user;
-  const void* staged;
-  size_t bytes;
-};
-
 int d2h(qc_ctx* c, void* user, const void* dsrc, size_t bytes, size_t* stage_off, std::vector<PendingOut>* pend) {
   if (bytes == 0 || user == nullptr) return QC_OK;
   if (is_pinned(user)) {
@@ -244,10 +255,12 @@ int d2h(qc_ctx* c, void* user, const void* dsrc, size_t bytes, size_t* stage_off
 
 size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
 
-int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, int T, float* d_emb, cudaStream_t s) {
+int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, int T, float* d_emb, cudaStream_t s,
+               DevBuf* part_buf = nullptr) {
+  DevBuf& part = part_buf ? *part_buf : c->part;
   const int TB = c->variant.token_block;
   const int bpc = (T + TB - 1) / TB;
-  QC_CUDA(c->part.ensure(static_cast<size_t>(R) * bpc * c->dim * sizeof(float)));
+  QC_CUDA(part.ensure(static_cast<size_t>(R) * bpc * c->dim * sizeof(float)));
   {
     KernelScope ks(c, QC_K_ENCODE, s);
     qc::EncoderLaunch a;
@@ -257,7 +270,7 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
     a.table = c->d_table;
     a.token_ids = d_tok;
     a.lens = d_lens;
-    a.part = static_cast<float*>(c->part.p);
+    a.part = static_cast<float*>(part.p);
     a.err_flag = c->d_err;
     a.stall = c->stall_on ? static_cast<unsigned long long*>(c->stall.p) : nullptr;
     a.R = R;
@@ -271,7 +284,7 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
   }
   {
     KernelScope ks(c, QC_K_FINALIZE, s);
-    QC_CUDA(qc::launch_finalize(static_cast<const float*>(c->part.p), d_lens, d_emb, R, bpc, TB, c->dim, s));
+    QC_CUDA(qc::launch_finalize(static_cast<const float*>(part.p), d_lens, d_emb, R, bpc, TB, c->dim, s));
   }
   return QC_OK;
 }
@@ -415,6 +428,12 @@ void qc_ctx_destroy(qc_ctx* c) {
   c->rows.release();
   c->idx.release();
   c->stall.release();
+  for (Slot& sl : c->slots) {
+    if (sl.stream) cudaStreamSynchronize(sl.stream);
+    sl.tok.release(); sl.lens.release(); sl.thr.release(); sl.emb.release(); sl.refok.release(); sl.medoid.release();
+    sl.cosm.release(); sl.part.release(); sl.h_in.release(); sl.h_out.release(); sl.h_flags.release();
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+  }
   c->h_in.release();
   c->h_out.release();
   if (c->d_table) cudaFree(c->d_table);
@@ -697,6 +716,99 @@ int qc_decide_batch(qc_ctx* c, const int32_t* token_ids, const int32_t* lens, in
   if ((st = d2h(c, out_emb, c->emb.p, embb, &ooff, &pend)) != QC_OK) return st;
   if ((st = check_token_flag(c)) != QC_OK) return st;
   for (const PendingOut& p : pend) memcpy(p.user, p.staged, p.bytes);
+  return QC_OK;
+}
+
+int qc_decide_batch_submit(qc_ctx* c, int slot, const int32_t* token_ids, const int32_t* lens, int B, int N, int T,
+                           const float* thr, int32_t* out_ref_ok, int32_t* out_medoid, float* out_cos) {
+  if (c == nullptr || slot < 0 || slot > 1 || token_ids == nullptr || lens == nullptr || thr == nullptr || B < 1 || T < 1)
+    return QC_ERR_INVALID_INPUT;
+  if (N < 1 || N > QC_MAX_POOL) return QC_ERR_UNSUPPORTED;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  if (T > QC_MAX_TOKENS) return QC_ERR_CONTEXT_LENGTH;
+  Slot& sl = c->slots[slot];
+  if (sl.busy) return QC_ERR_INVALID_INPUT;   // the previous batch in this slot has not been waited for
+  const int R = B * N;
+  for (int r = 0; r < R; ++r)
+    if (lens[r] < 0 || lens[r] > T) return QC_ERR_INVALID_INPUT;
+  DeviceGuard g(c->device);
+  if (sl.stream == nullptr) QC_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+  const size_t tokb = static_cast<size_t>(R) * T * 4, lenb = static_cast<size_t>(R) * 4;
+  const size_t thrb = static_cast<size_t>(B) * 4, ib = static_cast<size_t>(B) * 4;
+  const size_t embb = static_cast<size_t>(R) * c->dim * 4, cosb = static_cast<size_t>(B) * N * N * 4;
+  QC_CUDA(sl.tok.ensure(tokb));
+  QC_CUDA(sl.lens.ensure(lenb));
+  QC_CUDA(sl.thr.ensure(thrb));
+  QC_CUDA(sl.emb.ensure(embb));
+  QC_CUDA(sl.refok.ensure(ib));
+  QC_CUDA(sl.medoid.ensure(ib));
+  if (out_cos) QC_CUDA(sl.cosm.ensure(cosb));
+  QC_CUDA(sl.h_in.ensure(pad256(tokb) + pad256(lenb) + pad256(thrb)));
+  QC_CUDA(sl.h_out.ensure(2 * pad256(ib) + pad256(cosb)));
+  QC_CUDA(sl.h_flags.ensure(8 * sizeof(int32_t)));
+  // stage / copy inputs on the slot's stream
+  size_t off = 0;
+  auto in = [&](void* dst, const void* src, size_t bytes) -> int {
+    if (is_pinned(src)) {
+      QC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, sl.stream));
+    } else {
+      char* st = static_cast<char*>(sl.h_in.p) + off;
+      memcpy(st, src, bytes);
+      off += pad256(bytes);
+      QC_CUDA(cudaMemcpyAsync(dst, st, bytes, cudaMemcpyHostToDevice, sl.stream));
+    }
+    return QC_OK;
+  };
+  int st;
+  if ((st = in(sl.tok.p, token_ids, tokb)) != QC_OK) return st;
+  if ((st = in(sl.lens.p, lens, lenb)) != QC_OK) return st;
+  if ((st = in(sl.thr.p, thr, thrb)) != QC_OK) return st;
+  st = encode_dev(c, static_cast<int32_t*>(sl.tok.p), static_cast<int32_t*>(sl.lens.p), R, T,
+                  static_cast<float*>(sl.emb.p), sl.stream, &sl.part);
+  if (st != QC_OK) return st;
+  st = qc_similarity_batch_dev(c, static_cast<float*>(sl.emb.p), B, N, c->dim, static_cast<float*>(sl.thr.p),
+                               static_cast<int32_t*>(sl.refok.p), static_cast<int32_t*>(sl.medoid.p),
+                               out_cos ? static_cast<float*>(sl.cosm.p) : nullptr, sl.stream);
+  if (st != QC_OK) return st;
+  sl.pend.clear();
+  size_t ooff = 0;
+  auto outc = [&](void* user, const void* dsrc, size_t bytes) -> int {
+    if (user == nullptr || bytes == 0) return QC_OK;
+    if (is_pinned(user)) {
+      QC_CUDA(cudaMemcpyAsync(user, dsrc, bytes, cudaMemcpyDeviceToHost, sl.stream));
+    } else {
+      char* stg = static_cast<char*>(sl.h_out.p) + ooff;
+      ooff += pad256(bytes);
+      QC_CUDA(cudaMemcpyAsync(stg, dsrc, bytes, cudaMemcpyDeviceToHost, sl.stream));
+      sl.pend.push_back({user, stg, bytes});
+    }
+    return QC_OK;
+  };
+  if ((st = outc(out_ref_ok, sl.refok.p, ib)) != QC_OK) return st;
+  if ((st = outc(out_medoid, sl.medoid.p, ib)) != QC_OK) return st;
+  if ((st = outc(out_cos, sl.cosm.p, cosb)) != QC_OK) return st;
+  QC_CUDA(cudaMemcpyAsync(sl.h_flags.p, c->d_err, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+  sl.busy = true;
+  return QC_OK;
+}
+
+int qc_decide_batch_wait(qc_ctx* c, int slot) {
+  if (c == nullptr || slot < 0 || slot > 1) return QC_ERR_INVALID_INPUT;
+  Slot& sl = c->slots[slot];
+  if (!sl.busy) return QC_ERR_INVALID_INPUT;
+  DeviceGuard g(c->device);
+  sl.busy = false;
+  QC_CUDA(cudaStreamSynchronize(sl.stream));
+  const int32_t* flags = static_cast<const int32_t*>(sl.h_flags.p);
+  if (flags[0] != 0 || flags[4] != 0) {
+    const bool hang = flags[0] != 0;
+    if (hang) for (int i = 0; i < 4; ++i) c->hang[i] = flags[i];
+    QC_CUDA(cudaMemsetAsync(c->d_err, 0, 8 * sizeof(int32_t), sl.stream));
+    QC_CUDA(cudaStreamSynchronize(sl.stream));
+    return hang ? QC_ERR_KERNEL_TIMEOUT : QC_ERR_TOKEN_RANGE;
+  }
+  for (const PendingOut& p : sl.pend) memcpy(p.user, p.staged, p.bytes);
+  sl.pend.clear();
   return QC_OK;
 }
 

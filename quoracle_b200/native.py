@@ -25,7 +25,7 @@ QC_PAD_TOKEN = -1
 ABI_SYMBOLS = (
     "qc_ctx_create", "qc_ctx_destroy", "qc_ctx_device", "qc_ctx_dim", "qc_ctx_synchronize",
     "qc_host_alloc", "qc_host_free",
-    "qc_decide_batch", "qc_embed_batch", "qc_similarity_batch", "qc_first_match_batch", "qc_chunk_mean",
+    "qc_decide_batch", "qc_decide_batch_submit", "qc_decide_batch_wait", "qc_embed_batch", "qc_similarity_batch", "qc_first_match_batch", "qc_chunk_mean",
     "qc_decide_batch_dev", "qc_embed_batch_dev", "qc_similarity_batch_dev",
     "qc_strerror", "qc_status_atom", "qc_abi_version",
     "qc_check_status", "qc_last_hang",
@@ -75,6 +75,10 @@ def load_library() -> ctypes.CDLL:
     lib.qc_host_free.argtypes = [vp]
     lib.qc_decide_batch.restype = i32
     lib.qc_decide_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.qc_decide_batch_submit.restype = i32
+    lib.qc_decide_batch_submit.argtypes = [vp, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.qc_decide_batch_wait.restype = i32
+    lib.qc_decide_batch_wait.argtypes = [vp, i32]
     lib.qc_embed_batch.restype = i32
     lib.qc_embed_batch.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.qc_similarity_batch.restype = i32
@@ -226,6 +230,20 @@ class Context:
         _check(self._lib.qc_decide_batch(self._h, _ptr(token_ids), _ptr(lens), b, n, t, _ptr(thr),
                                          _ptr(out.ref_ok), _ptr(out.medoid), _ptr(out.cos), _ptr(out.emb)))
         return out
+
+    def decide_batch_submit(self, slot: int, token_ids: np.ndarray, lens: np.ndarray, thr: np.ndarray,
+                            out: DecideResult) -> None:
+        """Pipelined form: enqueue one batch on slot 0/1; arrays must be C-contiguous int32/float32 and stay
+        alive and untouched until ``decide_batch_wait(slot)`` returns (no copies are made here)."""
+        b, n, t = token_ids.shape
+        for a, dt in ((token_ids, np.int32), (lens, np.int32), (thr, np.float32)):
+            if a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("submit needs C-contiguous arrays of the exact dtype (they are read asynchronously)")
+        _check(self._lib.qc_decide_batch_submit(self._h, int(slot), _ptr(token_ids), _ptr(lens), b, n, t, _ptr(thr),
+                                                _ptr(out.ref_ok), _ptr(out.medoid), _ptr(out.cos)))
+
+    def decide_batch_wait(self, slot: int) -> None:
+        _check(self._lib.qc_decide_batch_wait(self._h, int(slot)))
 
     def embed_batch(self, token_ids: np.ndarray, lens: np.ndarray) -> np.ndarray:
         token_ids = _as(token_ids, np.int32)
