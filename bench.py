@@ -136,13 +136,21 @@ def cpu_threads() -> int:
 
 
 def calibrate_cpu_sample(weights, batch, threads, target_s):
-    """Pick how many decisions of the workload make ~target_s seconds of CPU work."""
-    t0 = time.perf_counter()
-    cpu_path(weights, batch.token_ids[:1], batch.lens[:1], batch.thr[:1], threads)   # also warms the library
-    t0 = time.perf_counter()
-    cpu_path(weights, batch.token_ids[:2], batch.lens[:2], batch.thr[:2], threads)
-    per = (time.perf_counter() - t0) / 2
-    return max(1, min(AGENTS_PER_GPU, int(target_s / max(per, 1e-6))))
+    """Pick the thread count (all logical CPUs, or half of them when SMT oversubscription is slower) and how many
+    decisions of the workload make ~target_s seconds of CPU work.  -> (sample, threads)"""
+    cpu_path(weights, batch.token_ids[:1], batch.lens[:1], batch.thr[:1], threads)   # warms the library
+    probe = min(AGENTS_PER_GPU, max(4, (4 * threads + POOL - 1) // POOL))            # four candidates per thread
+    best = None
+    for th in sorted({threads, max(1, threads // 2)}, reverse=True):
+        per = float("inf")
+        for _ in range(2):
+            t0 = time.perf_counter()
+            cpu_path(weights, batch.token_ids[:probe], batch.lens[:probe], batch.thr[:probe], th)
+            per = min(per, (time.perf_counter() - t0) / probe)
+        if best is None or per < best[0]:
+            best = (per, th)
+    per, th = best
+    return max(1, min(AGENTS_PER_GPU, int(target_s / max(per, 1e-6)))), th
 
 
 def run_reference(args):
@@ -153,8 +161,7 @@ def run_reference(args):
     from quoracle_b200 import synth
     weights = synth.make_encoder(DIM, VOCAB, seed=synth.BASE_SEED + 2)
     batch = synth.make_decisions(AGENTS_PER_GPU, POOL, TOKENS, VOCAB, seed=synth.BASE_SEED + 2)
-    threads = cpu_threads()
-    sample = calibrate_cpu_sample(weights, batch, threads, target_s=1.0)
+    sample, threads = calibrate_cpu_sample(weights, batch, cpu_threads(), target_s=1.0)
     steps, warmup = args.steps, args.warmup
     budget_s = 150.0                                   # keep the whole run within a few minutes
     est = (steps + warmup) * 1.0                       # each step was sized to ~1 s
@@ -332,8 +339,7 @@ def run_ours(args):
             "kernels_ms_per_launch": {k: (v["ms"] / v["launches"] if v["launches"] else None) for k, v in stats.items()},
         }
         if world == 1 and not args.no_cpu_baseline:
-            threads = cpu_threads()
-            sample = calibrate_cpu_sample(weights, batches[0], threads, target_s=args.cpu_seconds)
+            sample, threads = calibrate_cpu_sample(weights, batches[0], cpu_threads(), target_s=args.cpu_seconds)
             t0 = time.perf_counter()
             ok, med, emb = cpu_path(weights, batches[0].token_ids[:sample], batches[0].lens[:sample],
                                     batches[0].thr[:sample], threads)
