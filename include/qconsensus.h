@@ -201,7 +201,8 @@ int qc_encoder_stall_profile(qc_ctx* ctx, int enable, double out[16]);
 /* Test hook: force the encoder variant (cta_group 1 or 2) for subsequent launches. */
 int qc_encoder_set_cta_group(qc_ctx* ctx, int cta_group);
 /* Test/tuning hook: select the K1 tiling (tokens per resident block, CTAs per MMA group, W stage k-width,
- * gather mode 0 = cp.async / 1 = TMA gather4). */
+ * gather mode 0 = cp.async / 1 = TMA gather4).  token_block 0 returns to the default: the tiling is
+ * chosen per call from T (fastest measured tiling weighted by the fraction of non-padding token slots). */
 int qc_encoder_set_variant(qc_ctx* ctx, int token_block, int cta_group, int w_bk, int gather_mode);
 
 #ifdef __cplusplus

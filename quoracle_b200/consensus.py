@@ -1,0 +1,295 @@
+"""Batched per-agent decide step: cluster the N proposals of every pending decision, pick the winner,
+merge its parameters -- with ALL semantic-similarity merges of the whole agent tree evaluated in one GPU
+flush -- and score confidence.
+
+This is the host-side mirror of ``Result.format_result/4`` after ``Aggregator.cluster_responses/1``
+(reference lib/quoracle/consensus/result.ex:30-42, aggregator.ex:23-35), i.e. what
+``Consensus.execute_consensus_process/3`` (lib/quoracle/agent/consensus.ex:295-330) does once the LLM
+responses are in, restructured so the only heavy arithmetic (embedding + cosine of the semantic parameters)
+is gathered across agents.  String/integer rules (fingerprints, mode, percentile, wait, tie-break,
+confidence) run on the host exactly as in the reference; the rule/priority tables are data
+(``data/action_schemas.json``, transcribed from the reference's schemas).
+"""
+from __future__ import annotations
+
+import json
+import math
+import re
+from collections import OrderedDict
+from pathlib import Path
+from typing import Any, Optional, Sequence
+
+from .collector import DecisionCollector
+
+_DATA = json.loads((Path(__file__).parent / "data" / "action_schemas.json").read_text())
+SCHEMAS = _DATA["schemas"]
+PRIORITIES = _DATA["priorities"]
+DEFAULT_THRESHOLD = _DATA["default_semantic_threshold"]
+
+
+# ---- term helpers (strict equality / BEAM map order for small maps) -------------------------------------
+def _key(v):
+    if isinstance(v, bool):
+        return ("a", "true" if v else "false")
+    if v is None:
+        return ("a", "nil")
+    if isinstance(v, int):
+        return ("n", float(v), 0)
+    if isinstance(v, float):
+        return ("n", v, 1)
+    if isinstance(v, str):
+        return ("s", v.encode())
+    if isinstance(v, (list, tuple)):
+        return ("l", tuple(_key(x) for x in v))
+    if isinstance(v, dict):
+        return ("m", tuple(sorted((_key(k), _key(x)) for k, x in v.items())))
+    raise TypeError(type(v))
+
+
+_RANK = {"n": 0, "a": 1, "m": 3, "l": 4, "s": 5}
+
+
+def _order(v):
+    k = _key(v)
+    return (_RANK[k[0]],) + k[1:]
+
+
+def mode_value(values: Sequence[Any]):
+    """Most frequent value; ties -> first in term order (Enum.frequencies + Enum.max_by, result.ex:367-372)."""
+    counts: "OrderedDict" = OrderedDict()
+    for v in values:
+        k = _key(v)
+        c = counts.setdefault(k, [0, v])
+        c[0] += 1
+    best = None
+    for k in sorted(counts, key=lambda kk: _order(counts[kk][1])):
+        if best is None or counts[k][0] > counts[best][0]:
+            best = k
+    return counts[best][1]
+
+
+def _uniq(values):
+    seen, out = set(), []
+    for v in values:
+        k = _key(v)
+        if k not in seen:
+            seen.add(k)
+            out.append(v)
+    return out
+
+
+# ---- non-semantic rules (consensus_rules.ex:49-163) --------------------------------------------------------
+def _median(sorted_ints):
+    n = len(sorted_ints)
+    if n % 2:
+        return sorted_ints[n // 2]
+    s = sorted_ints[n // 2 - 1] + sorted_ints[n // 2]
+    return int(math.trunc(s / 2)) if abs(s) < 2**52 else (abs(s) // 2) * (1 if s >= 0 else -1)
+
+
+def wait_rule(values):
+    bools = [v for v in values if isinstance(v, bool)]
+    ints = [v for v in values if not isinstance(v, bool)]
+    if not ints and bools:
+        if not any(bools):
+            return False
+        if all(bools) or len(bools) >= 3:
+            return True
+    if not bools and ints:
+        return _median(sorted(ints))
+    top = max(ints) if ints else 30
+    return _median(sorted(0 if v is False else top if v is True else v for v in values))
+
+
+def host_rule(rule, values):
+    """-> ("ok", v) | ("error", reason) for every rule that needs no embeddings."""
+    name = rule[0]
+    if name == "exact_match":
+        u = _uniq(values)
+        return ("ok", u[0]) if len(u) == 1 else ("error", "no_consensus")
+    if name == "mode_selection":
+        return ("ok", mode_value(values))
+    if name == "union_merge":
+        flat = []
+        stack = list(values)[::-1]
+        while stack:
+            v = stack.pop()
+            if isinstance(v, list):
+                stack.extend(v[::-1])
+            else:
+                flat.append(v)
+        return ("ok", _uniq(flat))
+    if name == "structural_merge":
+        def merge(a, b):
+            if isinstance(a, dict) and isinstance(b, dict):
+                out = dict(a)
+                for k, v in b.items():
+                    out[k] = merge(out[k], v) if isinstance(out.get(k), dict) and isinstance(v, dict) else v
+                return out
+            return b if isinstance(b, dict) else a
+        acc: Any = {}
+        for v in values:
+            acc = merge(acc, v)
+        return ("ok", acc)
+    if name == "percentile":
+        nums = sorted(v for v in values if isinstance(v, (int, float)) and not isinstance(v, bool))
+        if not nums:
+            return ("ok", mode_value(values))
+        idx = rule[1] / 100.0 * (len(nums) - 1)
+        lo = int(idx)
+        hi = min(lo + 1, len(nums) - 1)
+        x = nums[lo] + (nums[hi] - nums[lo]) * (idx - lo)
+        return ("ok", int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5)))
+    return ("error", "unknown_rule")            # :first_non_nil / :merge_maps have no clause -> mode fallback
+
+
+# ---- fingerprints and clustering (aggregator.ex:23-103,366-454) ----------------------------------------------
+_PUNCT = re.compile(r"[^\w\s]", re.ASCII)
+
+
+def _key_terms(s: str, threshold: float) -> str:
+    s = s.lower()
+    if threshold < 0.95:
+        s = _PUNCT.sub("", s)
+    words = sorted((w for w in s.split() if len(w) > 3), key=lambda w: w.encode())
+    return "_".join(words[:5])
+
+
+def fingerprint(response: dict):
+    action = response["action"]
+    params = response.get("params") or {}
+    if action in ("batch_sync", "batch_async"):
+        seq = [a.get("action", "unknown") if isinstance(a, dict) else "unknown" for a in (params.get("actions") or [])]
+        return (action, tuple(sorted(seq)) if action == "batch_async" else tuple(seq))
+    schema = SCHEMAS.get(action)
+    if schema is None:
+        return (action, "invalid")
+    sig = []
+    for p in schema["required"] + schema["optional"]:
+        v = params.get(p)
+        if v is None:
+            continue
+        rule = schema["rules"].get(p)
+        name = rule[0] if rule else None
+        if name == "semantic_similarity":
+            v = _key_terms(v, rule[1] or 0.9) if isinstance(v, str) else v
+        elif name == "mode_selection":
+            v = "_mode_mergeable"
+        elif name == "percentile":
+            v = "_percentile_mergeable"
+        elif name == "union_merge" and isinstance(v, list):
+            v = sorted(v, key=_order)
+        sig.append((p, _key(v)))
+    return (action, tuple(sig))
+
+
+def cluster(responses: Sequence[dict]) -> list:
+    groups: "OrderedDict" = OrderedDict()
+    for r in responses:
+        groups.setdefault(fingerprint(r), []).append(r)
+    ordered = sorted(groups.items(), key=lambda kv: (str(kv[0][0]), repr(kv[0][1])))
+    clusters = [{"count": len(a), "actions": a, "representative": a[0], "fingerprint": fp} for fp, a in ordered]
+    return sorted(clusters, key=lambda c: -c["count"])
+
+
+def find_majority(clusters, total, round_num):
+    for c in clusters:
+        if (round_num == 1 and c["count"] == total) or (round_num != 1 and c["count"] > total / 2):
+            return c
+    return None
+
+
+# ---- winner, tie-break, confidence (result.ex:261-308, scoring.ex:15-102) --------------------------------------
+def _wait_score(v):
+    if v is True:
+        return (0, 0)
+    if v is None:
+        return (0, 1)
+    if v is False or v == 0:
+        return (1, 0)
+    return (0, 1 + v)
+
+
+def _priority(cluster):
+    rep = cluster["representative"]
+    if rep["action"] in ("batch_sync", "batch_async"):
+        acts = (rep.get("params") or {}).get("actions") or []
+        return max((PRIORITIES.get(a.get("action"), 999) for a in acts), default=999)
+    return PRIORITIES.get(rep["action"], 999)
+
+
+def pick_winner(clusters, total):
+    for c in clusters:
+        if c["count"] > total / 2:
+            return "consensus", c
+    top = max(c["count"] for c in clusters)
+    tied = [c for c in clusters if c["count"] == top]
+    def score(c):
+        ws = [_wait_score(a.get("wait")) for a in c.get("actions", [])]
+        return (_priority(c), (sum(w[0] for w in ws), sum(w[1] for w in ws)))
+    return "forced_decision", sorted(tied, key=score)[0]
+
+
+def confidence(count, total, round_num, max_rounds=4):
+    frac = count / total
+    bonus = 0.15 if frac > 0.8 else 0.10 if frac > 0.6 else 0.05 if frac > 0.5 else 0.0
+    penalty = (round_num - max_rounds) * 0.1 if round_num > max_rounds else 0.0
+    return min(max(frac + bonus - penalty, 0.1), 1.0)
+
+
+# ---- the batched decide step -----------------------------------------------------------------------------------
+def decide_tree(collector: DecisionCollector, pending: Sequence[dict], round_num: int = 2,
+                max_refinement_rounds: int = 4) -> list:
+    """pending: [{"agent_id", "responses": [ {action, params, reasoning, wait?} x N ]}] ->
+    [{"agent_id", "kind": "consensus" | "forced_decision" | "no_majority", "action", "confidence"}].
+
+    Pass 1 (host): cluster, find the winner, merge every non-semantic parameter, enqueue every semantic one.
+    One collector flush (GPU).  Pass 2 (host): fill the semantic parameters, mode fallback on error."""
+    plans = []
+    for d in pending:
+        responses = d["responses"]
+        clusters = cluster(responses)
+        total = len(responses)
+        if find_majority(clusters, total, round_num) is None and round_num <= max_refinement_rounds:
+            plans.append({"agent_id": d["agent_id"], "kind": "no_majority", "clusters": clusters})
+            continue
+        kind, win = pick_winner(clusters, total)
+        rep = win["representative"]
+        schema = SCHEMAS.get(rep["action"])
+        merged, waiting = {}, {}
+        if schema is not None and rep["action"] != "batch_sync":
+            for p in schema["required"] + schema["optional"]:
+                vals = [v for v in ((a.get("params") or {}).get(p) for a in win["actions"]) if v is not None]
+                if not vals:
+                    continue
+                rule = schema["rules"].get(p, ["mode_selection"])
+                if rule[0] == "semantic_similarity":
+                    waiting[p] = vals
+                    collector.submit(d["agent_id"], p, vals, rule[1] if len(rule) > 1 else DEFAULT_THRESHOLD)
+                else:
+                    r = host_rule(rule, vals)
+                    merged[p] = r[1] if r[0] == "ok" else mode_value(vals)
+        plans.append({"agent_id": d["agent_id"], "kind": kind, "win": win, "schema": schema, "merged": merged,
+                      "waiting": waiting, "total": total})
+    results = collector.flush()
+    out = []
+    for pl in plans:
+        if pl["kind"] == "no_majority":
+            out.append({"agent_id": pl["agent_id"], "kind": "no_majority", "action": None, "confidence": None})
+            continue
+        win, merged = pl["win"], pl["merged"]
+        for p, vals in pl["waiting"].items():
+            r = results[pl["agent_id"]][p]["result"]
+            merged[p] = r[1] if r[0] == "ok" else mode_value(vals)
+        rep = win["representative"]
+        if pl["schema"] is None or rep["action"] == "batch_sync":
+            action = dict(rep)
+        else:
+            ordered = {p: merged[p] for p in pl["schema"]["required"] + pl["schema"]["optional"] if p in merged}
+            waits = [a.get("wait") for a in win["actions"] if a.get("wait") is not None]
+            action = {"action": rep["action"], "params": ordered,
+                      "reasoning": next((a.get("reasoning") for a in win["actions"] if a.get("reasoning") != ""), ""),
+                      "wait": wait_rule(waits) if waits else False}
+        out.append({"agent_id": pl["agent_id"], "kind": pl["kind"], "action": action,
+                    "confidence": confidence(win["count"], pl["total"], round_num, max_refinement_rounds)})
+    return out

@@ -87,6 +87,7 @@ struct qc_ctx {
   bool has_encoder = false;
   int dim = 0, vocab = 0;
   qc::EncoderVariant variant{0, 0, 0, 0};
+  bool variant_forced = false;   // set by qc_encoder_set_variant / _set_cta_group; else chosen per call from T
   uint16_t* d_table = nullptr;
   uint16_t* d_wt = nullptr;  // W^T [dim(out) x dim(in)] bf16
   CUtensorMap w_tmap64, w_tmap32, e_tmap;
@@ -258,6 +259,7 @@ size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
 int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, int T, float* d_emb, cudaStream_t s,
                DevBuf* part_buf = nullptr) {
   DevBuf& part = part_buf ? *part_buf : c->part;
+  if (!c->variant_forced) c->variant = qc::encoder_auto_variant(c->dim, T);
   const int TB = c->variant.token_block;
   const int bpc = (T + TB - 1) / TB;
   QC_CUDA(part.ensure(static_cast<size_t>(R) * bpc * c->dim * sizeof(float)));
@@ -548,15 +550,22 @@ int qc_encoder_set_cta_group(qc_ctx* c, int cta_group) {
     if (!qc::encoder_variant_supported(c->dim, v)) return QC_ERR_UNSUPPORTED;
   }
   c->variant = v;
+  c->variant_forced = true;
   return QC_OK;
 }
 
 int qc_encoder_set_variant(qc_ctx* c, int token_block, int cta_group, int w_bk, int gather_mode) {
   if (c == nullptr) return QC_ERR_INVALID_INPUT;
   if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  if (token_block == 0) {             // back to automatic selection
+    c->variant_forced = false;
+    c->variant = qc::encoder_default_variant(c->dim);
+    return QC_OK;
+  }
   const qc::EncoderVariant v{token_block, cta_group, w_bk, gather_mode};
   if (!qc::encoder_variant_supported(c->dim, v)) return QC_ERR_UNSUPPORTED;
   c->variant = v;
+  c->variant_forced = true;
   return QC_OK;
 }
 

@@ -34,6 +34,7 @@ cudaError_t launch_encode(const EncoderLaunch& a);
 bool encoder_variant_supported(int dim, const EncoderVariant& v);
 int encoder_variant_w_stages(int dim, const EncoderVariant& v);
 EncoderVariant encoder_default_variant(int dim);
+EncoderVariant encoder_auto_variant(int dim, int T);
 
 // K2: emb[r, :] = L2normalise( (sum_j part[r, j, :]) / len[r] ), j < ceil(len/TB); len == 0 -> zeros.
 cudaError_t launch_finalize(const float* part, const int32_t* lens, float* emb, int R, int bpc, int TB, int dim,

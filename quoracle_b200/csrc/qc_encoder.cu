@@ -565,6 +565,30 @@ EncoderVariant encoder_default_variant(int dim) {
   }
 }
 
+// Token-block choice for a given slot count T: the measured throughput of each tiling (profiles/
+// k1_variants_*_r1.log, normalised to the fastest) times the fraction of gathered token slots that are
+// real (ceil(T/TB)*TB >= T).  T = 512 keeps TB = 128; T = 300 prefers TB = 104 (3 blocks, 4 % padding)
+// over TB = 128 (3 blocks, 22 % padding).
+EncoderVariant encoder_auto_variant(int dim, int T) {
+  struct Cand { EncoderVariant v; float tput; };
+  static const Cand c768[] = {{{128, 2, 64, 1}, 1.00f}, {{112, 2, 64, 1}, 0.955f}, {{104, 2, 64, 1}, 0.965f}, {{96, 2, 64, 1}, 0.80f}};
+  static const Cand c1536[] = {{{56, 2, 64, 1}, 1.00f}, {{64, 2, 64, 1}, 0.91f}, {{48, 2, 64, 1}, 0.84f}};
+  const Cand* cs = nullptr;
+  int n = 0;
+  if (dim == 768) { cs = c768; n = 4; }
+  else if (dim == 1536) { cs = c1536; n = 3; }
+  else return encoder_default_variant(dim);
+  EncoderVariant best = cs[0].v;
+  float best_score = -1.f;
+  for (int i = 0; i < n; ++i) {
+    const int tb = cs[i].v.token_block;
+    const int padded = ((T + tb - 1) / tb) * tb;
+    const float score = cs[i].tput * static_cast<float>(T) / static_cast<float>(padded);
+    if (score > best_score) { best_score = score; best = cs[i].v; }
+  }
+  return best;
+}
+
 cudaError_t launch_encode(const EncoderLaunch& a) {
   const int dim = a.dim;
   const EncoderVariant& v = a.variant;

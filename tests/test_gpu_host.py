@@ -82,3 +82,22 @@ def test_lesson_dedup_matches_oracle(emb):
         want = olm.deduplicate_lesson(lesson, existing, {"embedding_fn": fn1, "similarity_threshold": thr})
         got = lesson_manager.deduplicate_lesson(emb, lesson, existing, thr)
         assert got == want
+
+
+def test_decide_tree_on_gpu_matches_oracle(emb):
+    """The batched decide step over a small tree on the real GPU path vs oracle format_result."""
+    from oracle import aggregator as oagg
+    from oracle import result as ores
+    from quoracle_b200 import consensus
+    from tests.test_host_logic import _random_proposals
+    fn = oracle_fn(emb)
+    rng = np.random.default_rng(5)
+    pending = [{"agent_id": f"a{i}", "responses": _random_proposals(rng, int(rng.integers(3, 9)))} for i in range(40)]
+    before = emb.ctx.launch_count()
+    got = consensus.decide_tree(DecisionCollector(emb), pending, round_num=5)
+    assert emb.ctx.launch_count() - before <= 3 + 7                      # K1 + K2 + one K3 per pool size
+    for d, g in zip(pending, got):
+        clusters = oagg.cluster_responses(d["responses"])
+        kind, action, opts = ores.format_result(clusters, len(d["responses"]), 5, {"embedding_fn": fn})
+        assert g["kind"] == kind and g["action"]["action"] == action["action"]
+        assert g["action"]["params"] == action["params"]

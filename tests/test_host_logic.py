@@ -110,3 +110,75 @@ def test_sharding_maths():
     parts = [sharding.shard_tree(4, 8, r, 8) for r in range(8)]
     assert sum(len(p) for p in parts) == len(order)
     assert all(p[0][0] == r for r, p in enumerate(parts))                     # a top-level subtree per GPU
+
+
+def test_schema_data_is_in_sync_with_the_oracle_tables():
+    import json
+    from pathlib import Path
+    from oracle import schema_tables as st
+    data = json.loads((Path(__file__).parent.parent / "quoracle_b200" / "data" / "action_schemas.json").read_text())
+    assert data["priorities"] == st.ACTION_PRIORITIES
+    assert set(data["schemas"]) == set(st.SCHEMAS)
+    for a, s in st.SCHEMAS.items():
+        assert data["schemas"][a]["required"] == s["required"] and data["schemas"][a]["optional"] == s["optional"]
+        assert {p: tuple(r) for p, r in data["schemas"][a]["rules"].items()} == s["rules"]
+
+
+def _random_proposals(rng, n):
+    """N proposals over a few actions with overlapping / conflicting params, like the reference's mock scenarios."""
+    texts = ["analyze the customer data for patterns", "Analyze customer data patterns!", "deploy release to production",
+             "summarise quarterly revenue figures please", "analyze the customer data for patterns"]
+    out = []
+    for _ in range(n):
+        kind = int(rng.integers(0, 4))
+        wait = [True, False, None, 5, 0][int(rng.integers(0, 5))]
+        if kind == 0:
+            r = {"action": "send_message", "params": {"to": ["parent", "child"][int(rng.integers(0, 2))],
+                                                      "content": texts[int(rng.integers(0, len(texts)))]}}
+        elif kind == 1:
+            r = {"action": "fetch_web", "params": {"url": "https://example.com", "timeout": int(rng.integers(1, 60)),
+                                                   "follow_redirects": bool(rng.integers(0, 2))}}
+        elif kind == 2:
+            r = {"action": "orient", "params": {"current_situation": texts[int(rng.integers(0, len(texts)))],
+                                                "goal_clarity": texts[int(rng.integers(0, 2))],
+                                                "available_resources": "cpu gpu disk", "key_challenges": "latency",
+                                                "delegation_consideration": "none needed"}}
+        else:
+            r = {"action": "spawn_child", "params": {"task_description": texts[int(rng.integers(0, len(texts)))],
+                                                     "success_criteria": "tests pass", "immediate_context": "ctx",
+                                                     "approach_guidance": "carefully", "profile": "default",
+                                                     "skills": [["a", "b"], ["b", "c"], ["c"]][int(rng.integers(0, 3))]}}
+        r["reasoning"] = ["", "because", "since"][int(rng.integers(0, 3))]
+        if wait is not None:
+            r["wait"] = wait
+        out.append(r)
+    return out
+
+
+def test_batched_decide_step_matches_the_oracle_format_result():
+    """quoracle_b200.consensus.decide_tree == oracle Aggregator.cluster_responses + Result.format_result, decision
+    by decision, when both see the same embedding function -- and the whole tree costs one embed call."""
+    from oracle import aggregator as oagg
+    from oracle import result as ores
+    from quoracle_b200 import consensus
+    emb, ctx = make_emb()
+    fn = emb.embedding_fn()
+    ofn = lambda v, o: (lambda r: ("ok", {"embedding": r[1]["embedding"].astype(np.float64).tolist()}) if r[0] == "ok" else r)(fn(v, {}))  # noqa: E731
+    rng = np.random.default_rng(11)
+    pending = [{"agent_id": f"a{i}", "responses": _random_proposals(rng, int(rng.integers(3, 9)))} for i in range(60)]
+    for round_num in (1, 2, 6):
+        emb2, ctx2 = make_emb()
+        got = consensus.decide_tree(DecisionCollector(emb2), pending, round_num=round_num)
+        assert ctx2.calls["embed"] <= 1
+        for d, g in zip(pending, got):
+            clusters = oagg.cluster_responses(d["responses"])
+            maj = oagg.find_majority_cluster(clusters, len(d["responses"]), round_num)
+            if maj[0] == "no_majority" and round_num <= 4:
+                assert g["kind"] == "no_majority"
+                continue
+            kind, action, opts = ores.format_result(clusters, len(d["responses"]), round_num, {"embedding_fn": ofn})
+            assert g["kind"] == kind, (d, g)
+            assert g["action"]["action"] == action["action"]
+            assert g["action"]["params"] == action["params"], (g["action"], action)
+            assert g["action"]["wait"] == action["wait"] and g["action"]["reasoning"] == action["reasoning"]
+            assert abs(g["confidence"] - opts["confidence"]) < 1e-12
