@@ -217,12 +217,16 @@ __global__ void __launch_bounds__(256) qc_sim_small_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------
-// K3 path B: 8 < N <= 64.  One CTA per decision.  Column chunks of all rows are staged in shared
-// memory with cp.async (double buffered); each thread owns a 4x4 tile of the upper-triangular Gram
-// matrix (rows interleaved by N/4 so the 16-byte shared loads are conflict free) and a k-slice.
+// K3 path B: 8 < N <= 64.  The Gram matrix X X^T is GEMM-shaped and, at 2 N^2 D flop per 4 N D bytes,
+// far past what the fp32 FMA pipe sustains against HBM (N = 64: 32 flop/B), so it runs on the tensor
+// cores: warp-level m16n8k8 TF32 MMAs with the 3xTF32 split (x = hi + lo; hi.hi + hi.lo + lo.hi), which
+// keeps the dot products at fp32 accuracy (error ~1e-7, the verdict tolerance is 1e-3).  One CTA per
+// decision; 64-column chunks of all rows are staged in shared memory with cp.async (double buffered,
+// padded rows: fragment loads are bank-conflict free); a warp owns one 16-row block x up to four
+// 8-column tiles, small pools split the k range over warps instead.
 // ------------------------------------------------------------------------------------------
-constexpr int kSimDC = 128;             // columns per chunk
-constexpr int kSimRS = kSimDC + 4;      // padded row stride (floats): odd in 16-byte units
+constexpr int kSimDC = 64;              // columns per chunk
+constexpr int kSimRS = kSimDC + 4;      // padded row stride (floats)
 constexpr int kSimThreads = 256;
 
 template <bool VEC>
@@ -247,6 +251,20 @@ __device__ __forceinline__ void sim_load_chunk(float* buf, const float* x, int N
   if constexpr (VEC) ptx::cp_async_commit();
 }
 
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float rest = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+}
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(kSimThreads) qc_sim_large_kernel(const float* __restrict__ emb, int B, int N, int D,
                                                                    const float* __restrict__ thr,
@@ -254,25 +272,20 @@ __global__ void __launch_bounds__(kSimThreads) qc_sim_large_kernel(const float* 
                                                                    int32_t* __restrict__ medoid,
                                                                    float* __restrict__ cos) {
   extern __shared__ __align__(16) float sm[];
-  const int N4 = (N + 3) / 4;
-  const int Np = N4 * 4;
-  const int ntiles = N4 * (N4 + 1) / 2;
-  const int nks = kSimThreads / ntiles;
+  const int Np = (N + 15) & ~15;                 // 16, 32, 48, 64
   float* buf0 = sm;
   float* buf1 = sm + 64 * kSimRS;
-  float* gram = sm + 2 * 64 * kSimRS;  // [64][65]
+  float* gram = sm + 2 * 64 * kSimRS;            // [64][65]; also k-slice partials for Np == 16
 
   const int t = threadIdx.x;
-  const int tile = t % ntiles;
-  const int ks = t / ntiles;
-  const bool active = ks < nks;
-  // tile -> (ti <= tj)
-  int ti = 0, rem = tile;
-  while (rem >= N4 - ti) {
-    rem -= N4 - ti;
-    ++ti;
-  }
-  const int tj = ti + rem;
+  const int warp = t >> 5, lane = t & 31;
+  const int g = lane >> 2, tq = lane & 3;        // mma fragment coordinates
+  // warp -> (row block rb, first column tile cb0, tiles ncb, k-slice ks of nks)
+  int rb, cb0, ncb, ks = 0, nks = 1;
+  if (Np == 16) { rb = 0; cb0 = warp & 1; ncb = 1; ks = warp >> 1; nks = 4; }
+  else if (Np == 32) { rb = warp >> 2; cb0 = warp & 3; ncb = 1; }
+  else if (Np == 48) { rb = warp >> 1; cb0 = (warp & 1) * 3; ncb = warp < 6 ? 3 : 0; }
+  else { rb = warp >> 1; cb0 = (warp & 1) * 4; ncb = 4; }
 
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const float* x = emb + static_cast<size_t>(b) * N * D;
@@ -285,7 +298,7 @@ __global__ void __launch_bounds__(kSimThreads) qc_sim_large_kernel(const float* 
     const int nchunks = (D + kSimDC - 1) / kSimDC;
     sim_load_chunk<VEC>(buf0, x, N, Np, D, 0);
     for (int ch = 0; ch < nchunks; ++ch) {
-      float* cur = (ch & 1) ? buf1 : buf0;
+      const float* cur = (ch & 1) ? buf1 : buf0;
       float* nxt = (ch & 1) ? buf0 : buf1;
       if (ch + 1 < nchunks) {
         sim_load_chunk<VEC>(nxt, x, N, Np, D, (ch + 1) * kSimDC);
@@ -294,49 +307,57 @@ __global__ void __launch_bounds__(kSimThreads) qc_sim_large_kernel(const float* 
         if constexpr (VEC) ptx::cp_async_wait<0>();
       }
       __syncthreads();
-      if (active) {
-        for (int g = ks; g < kSimDC / 4; g += nks) {
-          float4 av[4], bv[4];
+      if (ncb > 0) {
+        const float* arow0 = cur + (rb * 16 + g) * kSimRS;
+        const float* arow1 = arow0 + 8 * kSimRS;
+        for (int k0 = ks * 8; k0 < kSimDC; k0 += 8 * nks) {
+          uint32_t ah[4], al[4];
+          split_tf32(arow0[k0 + tq], ah[0], al[0]);
+          split_tf32(arow1[k0 + tq], ah[1], al[1]);
+          split_tf32(arow0[k0 + tq + 4], ah[2], al[2]);
+          split_tf32(arow1[k0 + tq + 4], ah[3], al[3]);
 #pragma unroll
-          for (int a = 0; a < 4; ++a) av[a] = *reinterpret_cast<const float4*>(cur + (ti + a * N4) * kSimRS + 4 * g);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) bv[c] = *reinterpret_cast<const float4*>(cur + (tj + c * N4) * kSimRS + 4 * g);
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              acc[a][c] = fmaf(av[a].x, bv[c].x, acc[a][c]);
-              acc[a][c] = fmaf(av[a].y, bv[c].y, acc[a][c]);
-              acc[a][c] = fmaf(av[a].z, bv[c].z, acc[a][c]);
-              acc[a][c] = fmaf(av[a].w, bv[c].w, acc[a][c]);
+          for (int c = 0; c < 4; ++c) {
+            if (c < ncb) {
+              const float* brow = cur + ((cb0 + c) * 8 + g) * kSimRS;
+              uint32_t bh[2], bl[2];
+              split_tf32(brow[k0 + tq], bh[0], bl[0]);
+              split_tf32(brow[k0 + tq + 4], bh[1], bl[1]);
+              mma_tf32(acc[c], al, bh);      // small terms first
+              mma_tf32(acc[c], ah, bl);
+              mma_tf32(acc[c], ah, bh);
             }
+          }
         }
       }
       __syncthreads();
     }
-    // reduce k-slices through shared memory (fixed order), build the symmetric Gram matrix
-    float* red = buf0;  // [nks][ntiles][16] <= 256*16 floats = 16 KB, fits in buf0 (64*132 floats)
-    if (active) {
+    // accumulators -> Gram matrix in shared memory.  c0:(g, 2tq) c1:(g, 2tq+1) c2:(g+8, 2tq) c3:(g+8, 2tq+1)
+    if (nks > 1) {
+      float* red = buf0;                       // [nks][16][17]
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) red[(ks * ntiles + tile) * 16 + a * 4 + c] = acc[a][c];
-    }
-    __syncthreads();
-    for (int idx = t; idx < ntiles * 16; idx += kSimThreads) {
-      const int tl = idx >> 4, e = idx & 15;
-      float s = 0.f;
-      for (int k = 0; k < nks; ++k) s += red[(k * ntiles + tl) * 16 + e];
-      int ri = 0, rr = tl;
-      while (rr >= N4 - ri) {
-        rr -= N4 - ri;
-        ++ri;
+      for (int e = 0; e < 4; ++e) {
+        const int r = g + (e >> 1) * 8, cc = cb0 * 8 + 2 * tq + (e & 1);
+        red[(ks * 16 + r) * 17 + cc] = acc[0][e];
       }
-      const int rj = ri + rr;
-      const int i = ri + (e >> 2) * N4;
-      const int j = rj + (e & 3) * N4;
-      gram[i * 65 + j] = s;
-      gram[j * 65 + i] = s;
+      __syncthreads();
+      if (t < 256) {
+        const int r = t >> 4, cc = t & 15;
+        float s = 0.f;
+        for (int k = 0; k < nks; ++k) s += red[(k * 16 + r) * 17 + cc];   // fixed order
+        gram[r * 65 + cc] = s;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < ncb) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = rb * 16 + g + (e >> 1) * 8, cc = (cb0 + c) * 8 + 2 * tq + (e & 1);
+            gram[r * 65 + cc] = acc[c][e];
+          }
+        }
+      }
     }
     __syncthreads();
     // cosine in place (needs the diagonal first): stash norms, then overwrite
@@ -345,14 +366,32 @@ __global__ void __launch_bounds__(kSimThreads) qc_sim_large_kernel(const float* 
     __syncthreads();
     for (int idx = t; idx < N * N; idx += kSimThreads) {
       const int i = idx / N, j = idx - i * N;
-      const float c = cosine_from(gram[i * 65 + j], nrm[i], nrm[j]);
-      gram[i * 65 + j] = c;
+      // G is symmetric up to rounding: use the upper-triangular entry for both (i, j) and (j, i)
+      const int lo = i < j ? i : j, hi = i < j ? j : i;
+      const float c = cosine_from(gram[lo * 65 + hi], nrm[i], nrm[j]);
       if (cos != nullptr) cos[static_cast<size_t>(b) * N * N + idx] = c;
+      buf0[idx] = c;                            // N*N <= 4096 floats fit in buf0 (64 * 68)
+    }
+    __syncthreads();
+    if (t < N) {
+      float s = 0.f;
+      for (int j = 0; j < N; ++j) s += buf0[t * N + j];   // j ascending, diagonal included
+      nrm[64 + t] = s / static_cast<float>(N);
     }
     __syncthreads();
     if (t == 0) {
-      verdict_tail(N, thr[b], [&](int i, int j) { return gram[i * 65 + j]; }, ref_ok ? ref_ok + b : nullptr,
-                   medoid ? medoid + b : nullptr);
+      const float th = thr[b];
+      int ok = 1;
+      for (int i = 1; i < N; ++i) ok &= (buf0[i] >= th) ? 1 : 0;
+      int best = 0;
+      float best_mean = nrm[64];
+      for (int i = 1; i < N; ++i)
+        if (nrm[64 + i] > best_mean) {
+          best_mean = nrm[64 + i];
+          best = i;
+        }
+      if (ref_ok) ref_ok[b] = ok;
+      if (medoid) medoid[b] = best;
     }
     __syncthreads();
   }
@@ -404,7 +443,7 @@ cudaError_t launch_similarity(const float* emb, int B, int N, int D, const float
     if (e2 != cudaSuccess) return e2;
     attr_set = true;
   }
-  int grid = B < num_sms * 2 ? B : num_sms * 2;  // two resident CTAs per SM (84 KB each)
+  int grid = B < num_sms * 4 ? B : num_sms * 4;  // four resident CTAs per SM (51 KB each)
   if (vec) qc_sim_large_kernel<true><<<grid, kSimThreads, kSimLargeSmem, stream>>>(emb, B, N, D, thr, ref_ok, medoid, cos);
   else qc_sim_large_kernel<false><<<grid, kSimThreads, kSimLargeSmem, stream>>>(emb, B, N, D, thr, ref_ok, medoid, cos);
   return cudaGetLastError();

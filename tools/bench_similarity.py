@@ -22,6 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--cpu", action="store_true", help="also time the oracle C port (single thread) on a sample")
+    ap.add_argument("--pools", default="2,4,8,16,32,64")
     args = ap.parse_args()
     import torch
     dev = torch.device("cuda:0")
@@ -30,7 +31,7 @@ def main():
     ctx = native.Context(0)
     stream = torch.cuda.Stream(device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    pools = [2, 4, 8, 16, 32, 64]
+    pools = [int(x) for x in args.pools.split(",")]
     dims = [384, 768, 1536]
     batches = [256, 4096, 65536] if not args.quick else [4096, 65536]
     print(f"| N | D | B | bytes/decision | ms | decisions/s | GB/s | frac of {hbm:.0f} GB/s | cpu 1-thread decisions/s |")
