@@ -53,6 +53,8 @@ def select_config(name: str) -> None:
     per_batch = AGENTS_PER_GPU * POOL * TOKENS * 4
     ROTATE = max(4, -(-(168 * 2**20) // per_batch))          # enough distinct batches to exceed the 126 MB L2
     E2E_ROTATE = min(8, ROTATE)
+    global METRIC
+    METRIC = f"consensus decisions/sec ({POOL}-model, {TOKENS}-tok)"
     WORKLOAD = (f"{c['name']}: {POOL}-model pool, {AGENTS_PER_GPU} concurrent agents per GPU, {TOKENS}-token "
                 f"candidates, embedding dim {DIM}, vocab {VOCAB}, threshold 0.85")
 
@@ -333,7 +335,7 @@ def run_ours(args):
         peak = peaks["bf16_sustained"] if long_run else peaks["bf16_burst"]
         traffic = None
         tp = ROOT / "profiles" / "k1_traffic.json"
-        if tp.exists():
+        if tp.exists() and args.config == "c2":
             traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
         step_ms = ms / args.steps
         line = {
