@@ -220,9 +220,7 @@ __global__ void __launch_bounds__(256) qc_sim_small_kernel(const float* __restri
 // K3 path B: 8 < N <= 64.  The Gram matrix X X^T is GEMM-shaped and, at 2 N^2 D flop per 4 N D bytes,
 // far past what the fp32 FMA pipe sustains against HBM (N = 64: 32 flop/B), so it runs on the tensor
 // cores: warp-level m16n8k8 TF32 MMAs with the 3xTF32 split (x = hi + lo; hi.hi + hi.lo + lo.hi), which
-// keeps the dot products at fp32 accuracy (error ~1e-7, the verdict tolerance is 1e-3).  Because the Gram
-// matrix is symmetric, lo.hi is the transpose of hi.lo: only H H^T and H L^T are accumulated (two MMAs per
-// k-step instead of three) and G = HH + HL + HL^T is assembled in shared memory.  One CTA per
+// keeps the dot products at fp32 accuracy (error ~1e-7, the verdict tolerance is 1e-3).  One CTA per
 // decision; 64-column chunks of all rows are staged in shared memory with cp.async (double buffered,
 // padded rows: fragment loads are bank-conflict free); a warp owns one 16-row block x up to four
 // 8-column tiles, small pools split the k range over warps instead.
@@ -277,8 +275,7 @@ __global__ void __launch_bounds__(kSimThreads) qc_sim_large_kernel(const float* 
   const int Np = (N + 15) & ~15;                 // 16, 32, 48, 64
   float* buf0 = sm;
   float* buf1 = sm + 64 * kSimRS;
-  float* gram = sm + 2 * 64 * kSimRS;            // [64][65]  H H^T, then the assembled Gram matrix
-  float* ghl = gram + 64 * 65;                   // [64][65]  H L^T
+  float* gram = sm + 2 * 64 * kSimRS;            // [64][65]; also k-slice partials for Np == 16
 
   const int t = threadIdx.x;
   const int warp = t >> 5, lane = t & 31;
@@ -292,14 +289,11 @@ __global__ void __launch_bounds__(kSimThreads) qc_sim_large_kernel(const float* 
 
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const float* x = emb + static_cast<size_t>(b) * N * D;
-    float acc[4][4], acl[4][4];
+    float acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        acc[a][c] = 0.f;
-        acl[a][c] = 0.f;
-      }
+      for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
 
     const int nchunks = (D + kSimDC - 1) / kSimDC;
     sim_load_chunk<VEC>(buf0, x, N, Np, D, 0);
@@ -317,7 +311,7 @@ __global__ void __launch_bounds__(kSimThreads) qc_sim_large_kernel(const float* 
         const float* arow0 = cur + (rb * 16 + g) * kSimRS;
         const float* arow1 = arow0 + 8 * kSimRS;
         for (int k0 = ks * 8; k0 < kSimDC; k0 += 8 * nks) {
-          uint32_t ah[4], al[4];                       // al is unused: A enters only through its hi part
+          uint32_t ah[4], al[4];
           split_tf32(arow0[k0 + tq], ah[0], al[0]);
           split_tf32(arow1[k0 + tq], ah[1], al[1]);
           split_tf32(arow0[k0 + tq + 4], ah[2], al[2]);
@@ -329,8 +323,9 @@ __global__ void __launch_bounds__(kSimThreads) qc_sim_large_kernel(const float* 
               uint32_t bh[2], bl[2];
               split_tf32(brow[k0 + tq], bh[0], bl[0]);
               split_tf32(brow[k0 + tq + 4], bh[1], bl[1]);
-              mma_tf32(acl[c], ah, bl);      // H L^T
-              mma_tf32(acc[c], ah, bh);      // H H^T
+              mma_tf32(acc[c], al, bh);      // small terms first
+              mma_tf32(acc[c], ah, bl);
+              mma_tf32(acc[c], ah, bh);
             }
           }
         }
@@ -339,23 +334,18 @@ __global__ void __launch_bounds__(kSimThreads) qc_sim_large_kernel(const float* 
     }
     // accumulators -> Gram matrix in shared memory.  c0:(g, 2tq) c1:(g, 2tq+1) c2:(g+8, 2tq) c3:(g+8, 2tq+1)
     if (nks > 1) {
-      float* red = buf0;                       // [2][nks][16][17]
+      float* red = buf0;                       // [nks][16][17]
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int r = g + (e >> 1) * 8, cc = cb0 * 8 + 2 * tq + (e & 1);
         red[(ks * 16 + r) * 17 + cc] = acc[0][e];
-        red[((nks + ks) * 16 + r) * 17 + cc] = acl[0][e];
       }
       __syncthreads();
       if (t < 256) {
         const int r = t >> 4, cc = t & 15;
-        float s = 0.f, sl = 0.f;
-        for (int k = 0; k < nks; ++k) {         // fixed order
-          s += red[(k * 16 + r) * 17 + cc];
-          sl += red[((nks + k) * 16 + r) * 17 + cc];
-        }
+        float s = 0.f;
+        for (int k = 0; k < nks; ++k) s += red[(k * 16 + r) * 17 + cc];   // fixed order
         gram[r * 65 + cc] = s;
-        ghl[r * 65 + cc] = sl;
       }
     } else {
 #pragma unroll
@@ -365,24 +355,18 @@ __global__ void __launch_bounds__(kSimThreads) qc_sim_large_kernel(const float* 
           for (int e = 0; e < 4; ++e) {
             const int r = rb * 16 + g + (e >> 1) * 8, cc = (cb0 + c) * 8 + 2 * tq + (e & 1);
             gram[r * 65 + cc] = acc[c][e];
-            ghl[r * 65 + cc] = acl[c][e];
           }
         }
       }
     }
     __syncthreads();
-    // assemble G = HH + HL + HL^T on the upper triangle (small terms first), then the norms
-    for (int idx = t; idx < Np * Np; idx += kSimThreads) {
-      const int i = idx / Np, j = idx - i * Np;
-      if (i <= j) gram[i * 65 + j] = (ghl[i * 65 + j] + ghl[j * 65 + i]) + gram[i * 65 + j];
-    }
-    __syncthreads();
+    // cosine in place (needs the diagonal first): stash norms, then overwrite
     float* nrm = buf1;  // Np floats
     if (t < Np) nrm[t] = sqrtf(gram[t * 65 + t]);
     __syncthreads();
     for (int idx = t; idx < N * N; idx += kSimThreads) {
       const int i = idx / N, j = idx - i * N;
-      // symmetric by construction: the upper-triangular entry serves both (i, j) and (j, i)
+      // G is symmetric up to rounding: use the upper-triangular entry for both (i, j) and (j, i)
       const int lo = i < j ? i : j, hi = i < j ? j : i;
       const float c = cosine_from(gram[lo * 65 + hi], nrm[i], nrm[j]);
       if (cos != nullptr) cos[static_cast<size_t>(b) * N * N + idx] = c;
@@ -413,7 +397,7 @@ __global__ void __launch_bounds__(kSimThreads) qc_sim_large_kernel(const float* 
   }
 }
 
-constexpr int kSimLargeSmem = (2 * 64 * kSimRS + 2 * 64 * 65) * static_cast<int>(sizeof(float));
+constexpr int kSimLargeSmem = (2 * 64 * kSimRS + 64 * 65) * static_cast<int>(sizeof(float));
 
 template <int N>
 static cudaError_t launch_small(const float* emb, int B, int D, const float* thr, int32_t* ref_ok, int32_t* medoid,
@@ -459,7 +443,7 @@ cudaError_t launch_similarity(const float* emb, int B, int N, int D, const float
     if (e2 != cudaSuccess) return e2;
     attr_set = true;
   }
-  int grid = B < num_sms * 3 ? B : num_sms * 3;  // three resident CTAs per SM (68 KB each)
+  int grid = B < num_sms * 4 ? B : num_sms * 4;  // four resident CTAs per SM (51 KB each)
   if (vec) qc_sim_large_kernel<true><<<grid, kSimThreads, kSimLargeSmem, stream>>>(emb, B, N, D, thr, ref_ok, medoid, cos);
   else qc_sim_large_kernel<false><<<grid, kSimThreads, kSimLargeSmem, stream>>>(emb, B, N, D, thr, ref_ok, medoid, cos);
   return cudaGetLastError();
