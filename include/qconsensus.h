@@ -198,6 +198,10 @@ int qc_encoder_info(const qc_ctx* ctx, int32_t* cta_group, int32_t* token_block,
  * total, [7] waiting for free token buffers, [8] W producer total, [9] waiting for free W stages.
  */
 int qc_encoder_stall_profile(qc_ctx* ctx, int enable, double out[16]);
+/* Test/tuning hook: K3 kernel for pools of 9..64 candidates. 0 = auto (tcgen05 kind::tf32 kernel when the
+ * matrix is TMA-addressable: D % 4 == 0, 16-byte aligned base; the mma.sync kernel otherwise), 1 = always the
+ * mma.sync kernel, 2 = tcgen05 only (QC_ERR_UNSUPPORTED when the layout does not allow it). */
+int qc_similarity_set_path(qc_ctx* ctx, int path);
 /* Test hook: force the encoder variant (cta_group 1 or 2) for subsequent launches. */
 int qc_encoder_set_cta_group(qc_ctx* ctx, int cta_group);
 /* Test/tuning hook: select the K1 tiling (tokens per resident block, CTAs per MMA group, W stage k-width,

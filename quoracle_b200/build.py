@@ -10,7 +10,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "lib" / "libqconsensus.so"
-SOURCES = ["qc_api.cu", "qc_encoder.cu", "qc_similarity.cu"]
+SOURCES = ["qc_api.cu", "qc_encoder.cu", "qc_similarity.cu", "qc_similarity_tc.cu"]
 HEADERS = ["qc_common.cuh", "ptx.cuh", "../../include/qconsensus.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

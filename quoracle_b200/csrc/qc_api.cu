@@ -87,6 +87,8 @@ struct qc_ctx {
   bool has_encoder = false;
   int dim = 0, vocab = 0;
   qc::EncoderVariant variant{0, 0, 0, 0};
+  int sim_path = 0;              // K3 for pools 9..64: 0 auto (tcgen05 when the layout allows), 1 mma.sync, 2 tcgen05
+  void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved once at create
   bool variant_forced = false;   // set by qc_encoder_set_variant / _set_cta_group; else chosen per call from T
   uint16_t* d_table = nullptr;
   uint16_t* d_wt = nullptr;  // W^T [dim(out) x dim(in)] bf16
@@ -188,12 +190,17 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_w_tmap(qc_ctx* c) {
+int resolve_encode_tiled(qc_ctx* c) {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
   if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) return QC_ERR_CUDA;
-  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
+  c->encode_tiled = fn;
+  return QC_OK;
+}
+
+int make_w_tmap(qc_ctx* c) {
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(c->encode_tiled);
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(c->dim), static_cast<cuuint64_t>(c->dim)};  // {k, feature}
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(c->dim) * 2};
   const cuuint32_t box64[2] = {64, 128};
@@ -387,6 +394,7 @@ int qc_ctx_create(qc_ctx** out, int device_id, const qc_encoder_cfg* enc) {
     if ((st = cuda_status(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking))) != QC_OK) break;
     if ((st = cuda_status(cudaMalloc(&c->d_err, 8 * sizeof(int32_t)))) != QC_OK) break;
     if ((st = cuda_status(cudaMemset(c->d_err, 0, 8 * sizeof(int32_t)))) != QC_OK) break;
+    if ((st = resolve_encode_tiled(c)) != QC_OK) break;
     if (enc != nullptr) {
       c->dim = enc->dim;
       c->vocab = enc->vocab;
@@ -511,7 +519,6 @@ int qc_encoder_info(const qc_ctx* c, int32_t* cta_group, int32_t* token_block, i
 
 int qc_encoder_stall_profile(qc_ctx* c, int enable, double out[16]) {
   if (c == nullptr) return QC_ERR_INVALID_INPUT;
-  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
   DeviceGuard g(c->device);
   const size_t n = static_cast<size_t>(c->num_sms) * 16;
   QC_CUDA(cudaDeviceSynchronize());
@@ -591,7 +598,33 @@ int qc_similarity_batch_dev(qc_ctx* c, const float* d_emb, int B, int N, int D, 
   DeviceGuard g(c->device);
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
   KernelScope ks(c, QC_K_SIMILARITY, s);
+  // Pools of 9..64 run on the tensor cores (tcgen05 kind::tf32, 3xTF32 split) when TMA can address the
+  // matrix: 16-byte aligned base and row pitch, row count within a 32-bit coordinate.
+  const bool tc_ok = N > 8 && N <= 64 && (D % 4) == 0 && (reinterpret_cast<uintptr_t>(d_emb) & 15) == 0 &&
+                     static_cast<long long>(B) * N < (1ll << 31) && c->encode_tiled != nullptr;
+  if (c->sim_path == 2 && !tc_ok) return QC_ERR_UNSUPPORTED;
+  if (tc_ok && c->sim_path != 1) {
+    CUtensorMap xm;
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(B) * N};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(D) * 4};
+    const cuuint32_t box[2] = {32, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(c->encode_tiled)(
+        &xm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d_emb), gdim, gstride, box, estr,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return QC_ERR_CUDA;
+    QC_CUDA(qc::launch_similarity_tc(&xm, B, N, D, d_thr, d_ref_ok, d_medoid, d_cos, c->d_err,
+                                     c->stall_on ? static_cast<unsigned long long*>(c->stall.p) : nullptr, c->num_sms, s));
+    return QC_OK;
+  }
   QC_CUDA(qc::launch_similarity(d_emb, B, N, D, d_thr, d_ref_ok, d_medoid, d_cos, c->num_sms, s));
+  return QC_OK;
+}
+
+int qc_similarity_set_path(qc_ctx* c, int path) {
+  if (c == nullptr || path < 0 || path > 2) return QC_ERR_INVALID_INPUT;
+  c->sim_path = path;
   return QC_OK;
 }
 

@@ -44,6 +44,11 @@ cudaError_t launch_finalize(const float* part, const int32_t* lens, float* emb, 
 cudaError_t launch_similarity(const float* emb, int B, int N, int D, const float* thr, int32_t* ref_ok,
                               int32_t* medoid, float* cos, int num_sms, cudaStream_t stream);
 
+// K3 for pools of 9..64 on tcgen05 (kind::tf32, 3xTF32 split); x_tmap views emb as [B*N x D] fp32, box 32 x 128.
+cudaError_t launch_similarity_tc(const CUtensorMap* x_tmap, int B, int N, int D, const float* thr, int32_t* ref_ok,
+                                 int32_t* medoid, float* cos, int32_t* dbg, unsigned long long* stall, int num_sms,
+                                 cudaStream_t stream);
+
 // Lesson dedup: first m with cos(query_q, rows[q, m]) >= thr[q].
 cudaError_t launch_first_match(const float* query, const float* rows, int Q, int M, int D, const float* thr,
                                int32_t* out_index, float* out_cos, cudaStream_t stream);

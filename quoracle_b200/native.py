@@ -31,6 +31,7 @@ ABI_SYMBOLS = (
     "qc_check_status", "qc_last_hang",
     "qc_launch_count", "qc_profile_enable", "qc_profile_reset", "qc_kernel_stats",
     "qc_encoder_info", "qc_encoder_set_cta_group", "qc_encoder_set_variant", "qc_encoder_stall_profile",
+    "qc_similarity_set_path",
 )
 
 
@@ -116,6 +117,8 @@ def load_library() -> ctypes.CDLL:
                                     ctypes.POINTER(ctypes.c_int32)]
     lib.qc_encoder_set_variant.restype = i32
     lib.qc_encoder_set_variant.argtypes = [vp, i32, i32, i32, i32]
+    lib.qc_similarity_set_path.restype = i32
+    lib.qc_similarity_set_path.argtypes = [vp, i32]
     lib.qc_encoder_stall_profile.restype = i32
     lib.qc_encoder_stall_profile.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]
     lib.qc_encoder_set_cta_group.restype = i32
@@ -338,6 +341,10 @@ class Context:
         if out is None:
             return None
         return {name: float(out[i]) for i, name in enumerate(self.STALL_FIELDS)}
+
+    def set_similarity_path(self, path: int) -> None:
+        """K3 kernel for pools of 9..64: 0 auto, 1 mma.sync, 2 tcgen05 (test/tuning hook)."""
+        _check(self._lib.qc_similarity_set_path(self._h, int(path)))
 
     def set_variant(self, token_block: int, cta_group: int, w_bk: int = 64, gather: int = 0) -> None:
         _check(self._lib.qc_encoder_set_variant(self._h, int(token_block), int(cta_group), int(w_bk), int(gather)))

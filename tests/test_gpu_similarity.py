@@ -70,12 +70,70 @@ def test_small_pools(ctx, n, d):
     _check(ctx, emb, thr)
 
 
+@pytest.fixture(params=[0, 1], ids=["auto-tcgen05", "mma-sync"])
+def large_path(ctx, request):
+    """Pools of 9..64 have two kernels: tcgen05 kind::tf32 (auto, when D % 4 == 0) and mma.sync (fallback layout)."""
+    ctx.set_similarity_path(request.param)
+    yield request.param
+    ctx.set_similarity_path(0)
+
+
 @pytest.mark.parametrize("n", [9, 12, 16, 17, 31, 32, 33, 48, 63, 64])
 @pytest.mark.parametrize("d", [5, 128, 200, 384, 768, 1536])
-def test_large_pools(ctx, n, d):
+def test_large_pools(ctx, large_path, n, d):
     emb = synth.make_embeddings(9, n, d, seed=synth.BASE_SEED + 7 * n + d)
     thr = np.resize(np.array([0.1, 0.3, 0.5, 0.85], np.float32), 9)
     _check(ctx, emb, thr)
+
+
+@pytest.mark.parametrize("n,b", [(9, 2100), (16, 1500), (24, 777), (33, 450), (64, 301), (43, 149)])
+def test_large_pools_many_tiles(ctx, n, b):
+    """More 128-row tiles than SMs (persistent loop, both TMEM accumulator stages, ragged last tile),
+    pools that do not divide 128 (idle tile rows), dims that are not a multiple of the 32-column chunk."""
+    ctx.set_similarity_path(2)
+    try:
+        for d in (100, 384):
+            emb = synth.make_embeddings(b, n, d, seed=synth.BASE_SEED + n + b + d)
+            thr = np.resize(np.array([0.2, 0.4, 0.6], np.float32), b)
+            _check(ctx, emb, thr)
+    finally:
+        ctx.set_similarity_path(0)
+
+
+def test_large_pool_paths_agree_and_are_batch_independent(ctx):
+    rng = np.random.default_rng(9)
+    emb = (rng.standard_normal((500, 20, 256)) * rng.uniform(0.01, 30.0, (500, 20, 1))).astype(np.float32)
+    emb[:, 5] = -emb[:, 4]
+    emb[7, 3] = 0.0                                             # a zero row inside a live decision
+    thr = np.full(500, 0.05, np.float32)
+    ctx.set_similarity_path(2)
+    try:
+        tc = ctx.similarity_batch(emb, thr)
+        perm = rng.permutation(500)
+        tc_perm = ctx.similarity_batch(emb[perm], thr)
+        ctx.set_similarity_path(1)
+        legacy = ctx.similarity_batch(emb, thr)
+    finally:
+        ctx.set_similarity_path(0)
+    for a, b2 in zip(tc, tc_perm):
+        assert np.array_equal(a[perm], b2)                      # a decision does not see its tile neighbours
+    assert np.max(np.abs(tc[2] - legacy[2])) < TIGHT
+    assert np.max(np.abs(tc[2][:, 4, 5] + 1.0)) < 1e-5
+    assert np.all(tc[2][7, 3] == 0.0) and np.all(tc[2][7, :, 3] == 0.0)
+    assert np.array_equal(tc[2], np.swapaxes(tc[2], 1, 2))      # symmetric by construction
+    _check(ctx, emb, thr)
+
+
+def test_tcgen05_path_refuses_unaddressable_layout(ctx):
+    emb = synth.make_embeddings(4, 16, 6, seed=1)              # row pitch 24 bytes: not TMA-addressable
+    ctx.set_similarity_path(2)
+    try:
+        with pytest.raises(native.QcError) as e:
+            ctx.similarity_batch(emb, np.full(4, 0.5, np.float32))
+        assert e.value.atom == "bad_request"
+    finally:
+        ctx.set_similarity_path(0)
+    _check(ctx, emb, np.full(4, 0.5, np.float32))              # auto falls back to the mma.sync kernel
 
 
 def test_unnormalised_and_negative(ctx):
