@@ -97,6 +97,29 @@ __device__ __forceinline__ long long mbar_wait(uint64_t* bar, uint32_t parity, i
   }
   return clock64() - t0;
 }
+// Same wait with a suspend-time hint (nanoseconds): a waiting thread stays parked in hardware instead of
+// re-issuing try_wait, which leaves the issue slots of its scheduler to the warps that have work.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ long long mbar_wait_parked(uint64_t* bar, uint32_t parity, int32_t* dbg, int tag) {
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if ((++spins & 7u) == 0 && hang_check(dbg, t0, tag)) break;
+  }
+  return clock64() - t0;
+}
 // Acquire at cluster scope (needed when the arrivals come from the peer CTA).
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

@@ -607,7 +607,9 @@ int qc_similarity_batch_dev(qc_ctx* c, const float* d_emb, int B, int N, int D, 
     CUtensorMap xm;
     const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(B) * N};
     const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(D) * 4};
-    const cuuint32_t box[2] = {32, 128};
+    // a tile is floor(128 / N) whole decisions: only their rows are fetched (the rest of the 128-row MMA tile
+    // keeps stale shared memory, which only reaches accumulator entries that are discarded)
+    const cuuint32_t box[2] = {32, static_cast<cuuint32_t>((128 / N) * N)};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = reinterpret_cast<EncodeTiledFn>(c->encode_tiled)(
         &xm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d_emb), gdim, gstride, box, estr,

@@ -20,19 +20,25 @@
 #include "qc_common.cuh"
 #include "ptx.cuh"
 
+#ifndef QC_TC_SPLIT_GROUPS
+#define QC_TC_SPLIT_GROUPS 1
+#endif
+
 namespace qc {
 
 using namespace ptx;
 
 namespace {
 
-constexpr int kTcThreads = 448;             // 4 epilogue + 8 splitter + 1 TMA + 1 MMA warps
-constexpr int kSplitWarps = 8;
-constexpr int kRawStages = 4;
-constexpr int kHlStages = 2;
+constexpr int kSplitGroups = QC_TC_SPLIT_GROUPS;   // splitter groups of 4 warps; chunk c belongs to group c % kSplitGroups
+constexpr int kSplitWarps = 4 * kSplitGroups;
+constexpr int kTcThreads = (4 + kSplitWarps + 2) * 32;   // epilogue, splitters, TMA producer, MMA issuer
 constexpr int kChunkBytes = 128 * 128;       // 128 rows x 32 fp32
-constexpr int kWin = 65;                     // row stride of the per-decision windows (N <= 64)
-constexpr int kTcSmem = 1024 + kRawStages * kChunkBytes + kHlStages * 2 * kChunkBytes + 2 * 128 * kWin * 4 + 128 * 4 * 2 + 256 + 2560;   // tail: barriers + over-read padding
+// Shared memory: alignment slack, kStages x (raw 16 KB + lo 16 KB), two [128][kWin] fp32 windows, norms and row
+// means, barriers, over-read padding.  Pools <= 32 need narrower windows and get a fifth stage.
+constexpr int tc_smem_bytes(int stages, int win) {
+  return 1024 + stages * 2 * kChunkBytes + 2 * 128 * win * 4 + 128 * 4 * 2 + 256 + 2560;
+}
 
 // kind::tf32, fp32 accumulate, both operands K-major: c_format=1 (bit 4), a/b_format=2 (bits 7, 10), N>>3, M>>4
 __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N) {
@@ -55,32 +61,29 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Round-to-nearest (ties away) to the 10-bit TF32 mantissa; finite inputs only (the embeddings are).
-__device__ __forceinline__ float tf32_hi(float x) {
-  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
-}
+// What kind::tf32 sees of an fp32 operand: the 13 low mantissa bits are ignored.
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 }  // namespace
 
+template <int kStages, int kWin>
 __global__ void __launch_bounds__(kTcThreads, 1)
-qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N rows x D cols] fp32, box 32 x 128
+qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N rows x D cols] fp32, box 32 x (128/N)*N
                  int B, int N, int D, const float* __restrict__ thr, int32_t* __restrict__ ref_ok,
                  int32_t* __restrict__ medoid, float* __restrict__ cos, int32_t* __restrict__ dbg,
                  unsigned long long* __restrict__ stall) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
-  uint8_t* raw = smem;                                        // kRawStages x 16 KB
-  uint8_t* hl = raw + kRawStages * kChunkBytes;               // kHlStages x (hi 16 KB, lo 16 KB)
-  float* whh = reinterpret_cast<float*>(hl + kHlStages * 2 * kChunkBytes);   // [128][kWin] HH window
+  uint8_t* stages = smem;                                     // kStages x (raw 16 KB, lo 16 KB)
+  float* whh = reinterpret_cast<float*>(stages + kStages * 2 * kChunkBytes);   // [128][kWin] HH window
   float* whl = whh + 128 * kWin;                                             // [128][kWin] HL window
   float* diag = whl + 128 * kWin;                                            // [128] Gram diagonal
   float* rmean = diag + 128;                                                 // [128] row means
   uint64_t* bars = reinterpret_cast<uint64_t*>(rmean + 128);
-  uint64_t* raw_full = bars;
-  uint64_t* raw_empty = raw_full + kRawStages;
-  uint64_t* hl_full = raw_empty + kRawStages;
-  uint64_t* hl_empty = hl_full + kHlStages;
-  uint64_t* acc_full = hl_empty + kHlStages;
+  uint64_t* raw_full = bars;                                  // TMA landed the raw tile
+  uint64_t* lo_full = raw_full + kStages;                     // splitters wrote the lo tile
+  uint64_t* stage_empty = lo_full + kStages;                  // the MMAs that read the stage retired
+  uint64_t* acc_full = stage_empty + kStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -90,15 +93,12 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
   const int ntiles = (B + q - 1) / q;
   const int nchunks = (D + 31) / 32;
 
-  if (warp == 12 && lane == 0) {
+  if (warp == 4 + kSplitWarps && lane == 0) {
     tma_prefetch_desc(&x_tmap);
-    for (int s = 0; s < kRawStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], kSplitWarps);      // one arrival per splitter warp
-    }
-    for (int u = 0; u < kHlStages; ++u) {
-      mbar_init(&hl_full[u], kSplitWarps);
-      mbar_init(&hl_empty[u], 1);       // tcgen05.commit
+      mbar_init(&lo_full[s], 4);                  // one arrival per warp of the owning splitter group
+      mbar_init(&stage_empty[s], 1);              // tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
@@ -107,7 +107,7 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
     fence_barrier_init();
   }
   __syncwarp();
-  if (warp == 13) tmem_alloc<1>(tmem_slot, 512);
+  if (warp == 5 + kSplitWarps) tmem_alloc<1>(tmem_slot, 512);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -129,7 +129,7 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
       const int b = tile * q + d;
       const bool live = row_live && b < B;
       const float th = live ? thr[b] : 0.f;                   // in flight while the tile's MMAs finish
-      w_acc += mbar_wait(&acc_full[as], (acc_iter >> 1) & 1u, dbg, 700);
+      w_acc += mbar_wait_parked(&acc_full[as], (acc_iter >> 1) & 1u, dbg, 700);
       long long tp = clock64();
       tcgen05_fence_after();
       // accumulator rows -> shared windows (only the columns of the row's own decision; 32-column groups
@@ -159,8 +159,12 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
       if (lane == 0) mbar_arrive(&acc_empty[as]);
       named_bar_sync(1, 128);
       t_copy += clock64() - tp; tp = clock64();
-      // Gram diagonal G_ii = HH_ii + 2 HL_ii -> row norm
-      if (row_live) diag[i] = sqrtf((whl[i * kWin + r] + whl[i * kWin + r]) + whh[i * kWin + r]);
+      // Gram diagonal G_ii = HH_ii + 2 HL_ii -> reciprocal row norm (0 for a zero row: its cosines are 0,
+      // reference consensus_rules.ex:205-209)
+      if (row_live) {
+        const float nrm2 = (whl[i * kWin + r] + whl[i * kWin + r]) + whh[i * kWin + r];
+        diag[i] = nrm2 > 0.f ? rsqrtf(nrm2) : 0.f;
+      }
       named_bar_sync(1, 128);
       int ok = 1;
       if (live) {
@@ -172,8 +176,10 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
         const float* hh_row = whh + i * kWin;
         const float* hl_row = whl + i * kWin;
         const float* hl_col = whl + base * kWin + r;
-        const float* nrm = diag + base;
-        float* cos_row = cos != nullptr ? cos + (static_cast<size_t>(b) * N + r) * N : nullptr;
+        const float* nrm = diag + base;                       // reciprocal norms
+        // cos(r, j) == cos(j, r) bitwise (below), so row r's values are stored down column r of the output:
+        // consecutive lanes (consecutive r) then write consecutive addresses
+        float* cos_col = cos != nullptr ? cos + static_cast<size_t>(b) * N * N + r : nullptr;
         // Blocks of 8 columns, all loads of a block issued before use (shared memory is kept busy by the MMA
         // operand reads, so its latency is long here).  Loads past column N - 1 stay inside the padded
         // shared-memory carve-up and their results are discarded.
@@ -186,17 +192,16 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
             lc[k] = hl_col[(j0 + k) * kWin];
             nj[k] = nrm[j0 + k];
           }
+          // branch-free so the eight dependency chains interleave
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const int j = j0 + k;
-            if (j < N) {
-              const float g = (lr[k] + lc[k]) + up[k];
-              const float nn = ni * nj[k];
-              const float c = nn == 0.f ? 0.f : __fdividef(g, nn);
-              if (j > 0 && !(c >= th)) ok = 0;                // only row 0's verdict is used
-              s += c;                                         // j ascending, diagonal included
-              if (cos_row != nullptr) cos_row[j] = c;
-            }
+            const bool in = j < N;
+            const float g = (lr[k] + lc[k]) + up[k];
+            const float c = in ? g * (ni * nj[k]) : 0.f;        // ni * nj commutes: cos(r, j) == cos(j, r) bitwise
+            ok &= (!in || j == 0 || c >= th) ? 1 : 0;         // only row 0's verdict is used
+            s += c;                                           // j ascending, diagonal included
+            if (in && cos_col != nullptr) cos_col[j * N] = c;
           }
         }
         rmean[i] = s / static_cast<float>(N);
@@ -232,46 +237,41 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
     }
   } else if (warp < 4 + kSplitWarps) {
     // ===================== splitters: raw fp32 chunk -> TF32 hi / lo tiles ====================
-    const int p = threadIdx.x - 128;                          // 0..255
-    uint32_t ci = 0;
+    const int p = (threadIdx.x - 128) & 127;                  // position inside the group
+    const int grp = (warp - 4) >> 2;
     const long long t_role = clock64();
-    long long w_raw = 0, w_hl = 0;
+    long long w_raw = 0;
+    uint32_t ci = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int ch = 0; ch < nchunks; ++ch, ++ci) {
-        const uint32_t s = ci % kRawStages, u = ci % kHlStages;
-        w_raw += mbar_wait(&raw_full[s], (ci / kRawStages) & 1u, dbg, 710);
-        w_hl += mbar_wait(&hl_empty[u], ((ci / kHlStages) & 1u) ^ 1u, dbg, 711);
-        const float4* src = reinterpret_cast<const float4*>(raw + s * kChunkBytes);
-        float4* dh = reinterpret_cast<float4*>(hl + u * 2 * kChunkBytes);
-        float4* dl = reinterpret_cast<float4*>(hl + u * 2 * kChunkBytes + kChunkBytes);
+        if (static_cast<int>(ci % kSplitGroups) != grp) continue;
+        const uint32_t s = ci % kStages;
+        w_raw += mbar_wait_parked(&raw_full[s], (ci / kStages) & 1u, dbg, 710);
+        const float4* src = reinterpret_cast<const float4*>(stages + s * 2 * kChunkBytes);
+        float4* dl = reinterpret_cast<float4*>(stages + s * 2 * kChunkBytes + kChunkBytes);
         // 1024 16-byte pieces, consecutive per warp; all loads first so their latencies overlap
-        float4 x[4];
+        float4 x[8];
 #pragma unroll
-        for (int it = 0; it < 4; ++it) x[it] = src[it * (32 * kSplitWarps) + p];
+        for (int it = 0; it < 8; ++it) x[it] = src[it * 128 + p];
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int idx = it * (32 * kSplitWarps) + p;
-          float4 h, l;
-          h.x = tf32_hi(x[it].x); h.y = tf32_hi(x[it].y); h.z = tf32_hi(x[it].z); h.w = tf32_hi(x[it].w);
-          // the residual is exact in fp32; the tensor core drops its low bits itself (2^-21 relative overall)
-          l.x = x[it].x - h.x; l.y = x[it].y - h.y; l.z = x[it].z - h.z; l.w = x[it].w - h.w;
-          dh[idx] = h;
-          dl[idx] = l;
+        for (int it = 0; it < 8; ++it) {
+          // the tensor core reads the raw tile as TF32 by ignoring the 13 low mantissa bits; lo is the exact
+          // fp32 remainder of that truncation (its own low bits are dropped the same way: 2^-20 relative)
+          float4 l;
+          l.x = x[it].x - tf32_trunc(x[it].x); l.y = x[it].y - tf32_trunc(x[it].y);
+          l.z = x[it].z - tf32_trunc(x[it].z); l.w = x[it].w - tf32_trunc(x[it].w);
+          dl[it * 128 + p] = l;
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&hl_full[u]);
-          mbar_arrive(&raw_empty[s]);
-        }
+        if (lane == 0) mbar_arrive(&lo_full[s]);
       }
     }
-    if (stall != nullptr && p == 0) {
+    if (stall != nullptr && threadIdx.x == 128) {
       stall[blockIdx.x * 16 + 6] = clock64() - t_role;
       stall[blockIdx.x * 16 + 7] = w_raw;
-      stall[blockIdx.x * 16 + 10] = w_hl;
     }
-  } else if (warp == 12) {
+  } else if (warp == 4 + kSplitWarps) {
     // ===================== TMA producer (warp-convergent, elected issue) =====================
     uint32_t ci = 0;
     const long long t_role = clock64();
@@ -279,11 +279,11 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int row0 = tile * q * N;
       for (int ch = 0; ch < nchunks; ++ch, ++ci) {
-        const uint32_t s = ci % kRawStages;
-        w_free += mbar_wait(&raw_empty[s], ((ci / kRawStages) & 1u) ^ 1u, dbg, 720);
+        const uint32_t s = ci % kStages;
+        w_free += mbar_wait_parked(&stage_empty[s], ((ci / kStages) & 1u) ^ 1u, dbg, 720);
         if (elect_one()) {
-          mbar_expect_tx(&raw_full[s], kChunkBytes);
-          tma_load_2d(raw + s * kChunkBytes, &x_tmap, &raw_full[s], ch * 32, row0);
+          mbar_expect_tx(&raw_full[s], static_cast<uint32_t>(q * N) * 128u);
+          tma_load_2d(stages + s * 2 * kChunkBytes, &x_tmap, &raw_full[s], ch * 32, row0);
         }
         __syncwarp();
       }
@@ -295,27 +295,27 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
   } else {
     // ===================== MMA issuer ==========================================================
     constexpr uint32_t idesc = make_idesc_tf32(128, 256);   // B = [hi; lo] stacked: D = [HH | HL]
-    const uint32_t hl_base = smem_u32(hl);
+    const uint32_t st_base = smem_u32(stages);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     uint32_t ci = 0, acc_iter = 0;
     const long long t_role = clock64();
     long long w_hl = 0, w_acc = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++acc_iter) {
       const uint32_t as = acc_iter & 1u;
-      w_acc += mbar_wait(&acc_empty[as], ((acc_iter >> 1) & 1u) ^ 1u, dbg, 730);
+      w_acc += mbar_wait_parked(&acc_empty[as], ((acc_iter >> 1) & 1u) ^ 1u, dbg, 730);
       tcgen05_fence_after();
       const uint32_t d_acc = tmem_u + as * 256;               // columns 0..127 HH, 128..255 HL
       for (int ch = 0; ch < nchunks; ++ch, ++ci) {
-        const uint32_t u = ci % kHlStages;
-        w_hl += mbar_wait(&hl_full[u], (ci / kHlStages) & 1u, dbg, 731);
+        const uint32_t u = ci % kStages;
+        w_hl += mbar_wait_parked(&lo_full[u], (ci / kStages) & 1u, dbg, 731);
         tcgen05_fence_after();
-        // hi and lo tiles are adjacent: as a 256-row K-major operand they are [hi; lo]
-        const uint64_t hdesc = make_kmajor_sw128_desc(hl_base + u * 2 * kChunkBytes);
+        // raw and lo tiles are adjacent: as a 256-row K-major operand they are [hi; lo]
+        const uint64_t hdesc = make_kmajor_sw128_desc(st_base + u * 2 * kChunkBytes);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)                         // 8 fp32 (32 bytes) per K step
             umma_tf32(d_acc, hdesc + 2 * k, hdesc + 2 * k, idesc, (ch | k) != 0 ? 1u : 0u);
-          umma_commit<1>(&hl_empty[u]);
+          umma_commit<1>(&stage_empty[u]);
           if (ch == nchunks - 1) umma_commit<1>(&acc_full[as]);
         }
         __syncwarp();
@@ -331,28 +331,38 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
   __syncwarp();
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 13) {
+  if (warp == 5 + kSplitWarps) {
     tcgen05_fence_after();
     tmem_dealloc<1>(tmem_base, 512);
   }
 }
 
-cudaError_t launch_similarity_tc(const CUtensorMap* x_tmap, int B, int N, int D, const float* thr, int32_t* ref_ok,
-                                 int32_t* medoid, float* cos, int32_t* dbg, unsigned long long* stall, int num_sms,
-                                 cudaStream_t stream) {
+template <int kStages, int kWin>
+static cudaError_t launch_tc(const CUtensorMap* x_tmap, int B, int N, int D, const float* thr, int32_t* ref_ok,
+                             int32_t* medoid, float* cos, int32_t* dbg, unsigned long long* stall, int num_sms,
+                             cudaStream_t stream) {
+  constexpr int smem = tc_smem_bytes(kStages, kWin);
+  static_assert(smem <= 232448, "tcgen05 K3: shared-memory carve-up exceeds the 227 KB opt-in limit");
   static bool attr_set[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(qc_sim_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+    cudaError_t e = cudaFuncSetAttribute(qc_sim_tc_kernel<kStages, kWin>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
   const int q = 128 / N;
   const int ntiles = (B + q - 1) / q;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  qc_sim_tc_kernel<<<grid, kTcThreads, kTcSmem, stream>>>(*x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall);
+  qc_sim_tc_kernel<kStages, kWin><<<grid, kTcThreads, smem, stream>>>(*x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall);
   return cudaGetLastError();
+}
+
+cudaError_t launch_similarity_tc(const CUtensorMap* x_tmap, int B, int N, int D, const float* thr, int32_t* ref_ok,
+                                 int32_t* medoid, float* cos, int32_t* dbg, unsigned long long* stall, int num_sms,
+                                 cudaStream_t stream) {
+  if (N <= 32) return launch_tc<5, 33>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream);
+  return launch_tc<4, 65>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream);
 }
 
 }  // namespace qc

@@ -13,7 +13,10 @@ from typing import Optional
 
 import numpy as np
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libqconsensus.so"
+import os
+
+# QCONSENSUS_LIB: tuning hook -- load an alternative build of the same library (tools/ only)
+_LIB_PATH = Path(os.environ.get("QCONSENSUS_LIB") or Path(__file__).resolve().parent / "lib" / "libqconsensus.so")
 _lib: Optional[ctypes.CDLL] = None
 
 QC_K_NAMES = ("encode", "finalize", "similarity", "first_match", "chunk_mean")

@@ -124,6 +124,31 @@ def test_large_pool_paths_agree_and_are_batch_independent(ctx):
     _check(ctx, emb, thr)
 
 
+def test_tcgen05_split_keeps_the_low_mantissa_bits(ctx):
+    """The TF32 tensor core sees 10 mantissa bits; the kernel restores the rest with a hi/lo split.  Inputs whose
+    information sits exactly in the bits TF32 drops (and where truncation and rounding of the hi part differ)
+    must still come out at fp32 accuracy: a split that disagrees with what the hardware does to the hi operand
+    shows up here as an error of ~5e-4."""
+    n, d, b = 16, 64, 40
+    rng = np.random.default_rng(21)
+    x = np.float32(1.0 + 0.75 * 2.0 ** -10)                    # trunc -> 1.0, round-to-nearest -> 1 + 2^-10
+    emb = np.zeros((b, n, d), np.float32)
+    emb[:, :, 0::2] = x
+    emb[:, :, 1::2] = rng.choice(np.array([1.0, -1.0, 0.5, 2.0], np.float32), size=(b, n, d // 2))
+    # fine structure below the TF32 resolution that decides the verdict order
+    emb[:, :, 0] += (rng.integers(0, 64, size=(b, n)) * np.float32(2.0 ** -18)).astype(np.float32)
+    thr = np.full(b, 0.3, np.float32)
+    ctx.set_similarity_path(2)
+    try:
+        ref_ok, medoid, cos = ctx.similarity_batch(emb, thr)
+    finally:
+        ctx.set_similarity_path(0)
+    o_ok, o_med, o_cos, margins = numeric.decide_batch(emb, thr)
+    assert np.max(np.abs(cos - o_cos)) < 2e-6
+    safe = margins["vote"] > 1e-5
+    assert np.array_equal(medoid[safe], o_med[safe])
+
+
 def test_tcgen05_path_refuses_unaddressable_layout(ctx):
     emb = synth.make_embeddings(4, 16, 6, seed=1)              # row pitch 24 bytes: not TMA-addressable
     ctx.set_similarity_path(2)
