@@ -198,6 +198,50 @@ int qc_encoder_info(const qc_ctx* ctx, int32_t* cta_group, int32_t* token_block,
  * total, [7] waiting for free token buffers, [8] W producer total, [9] waiting for free W stages.
  */
 int qc_encoder_stall_profile(qc_ctx* ctx, int enable, double out[16]);
+/*
+ * Pool split across GPUs (north star: "a single all-gather of embedding rows over NVLink only
+ * when one agent's model pool spans devices").  The reference has no multi-device notion -- its pool is the
+ * model_ids list of Quoracle.Consensus.get_consensus (lib/quoracle/consensus.ex) -- so this is the seam a
+ * multi-GPU deployment adds: `world` processes (one per GPU of one node), each holding `pool_local` consecutive
+ * members of every decision's pool (pool order = rank-major).  Every rank creates a split object, exports its
+ * handle, and attaches every peer's handle (exchanged by the host runtime: Erlang distribution, or
+ * torch.distributed in this repo's tests).  qc_decide_split_dev then runs K1 on the local candidates, K2 stores
+ * each normalised row straight into every rank's gathered buffer through peer memory (no separate collective),
+ * a device-side flag handshake orders the ranks, and K3 decides on the full pool: every rank gets all verdicts.
+ * All ranks must make the same sequence of calls with the same B.  d_* pointers are device memory of the
+ * context's GPU; `stream` as in the other _dev entry points.  A peer that never arrives ends the wait after ~3 s
+ * and surfaces as QC_ERR_KERNEL_TIMEOUT from qc_check_status.
+ */
+typedef struct qc_split qc_split;
+#define QC_SPLIT_HANDLE_BYTES 64
+#define QC_MAX_SPLIT_WORLD 8
+int qc_split_create(qc_ctx* ctx, int world, int rank, int max_decisions, int pool_local, qc_split** out);
+int qc_split_export(qc_split* split, uint8_t handle[QC_SPLIT_HANDLE_BYTES]);
+int qc_split_attach(qc_split* split, int peer_rank, const uint8_t handle[QC_SPLIT_HANDLE_BYTES]);
+int qc_decide_split_dev(qc_ctx* ctx, qc_split* split, const int32_t* d_token_ids, const int32_t* d_lens, int B, int T,
+                        const float* d_thr, int32_t* d_ref_ok, int32_t* d_medoid, float* d_cos, void* stream);
+/* Device pointer to the gathered rows [decisions, world * pool_local, dim] of the last qc_decide_split_dev. */
+int qc_split_gathered(const qc_split* split, const float** d_emb, int32_t* decisions);
+int qc_split_destroy(qc_split* split);
+
+/*
+ * Long candidates sharded on T across GPUs (BASELINE config 4).  Rank p holds the p-th token
+ * slice of EVERY candidate: d_token_ids [R x T_local], d_lens[r] = valid tokens of row r inside this slice (0 when
+ * the candidate ends earlier).  K1 runs on the slice; one fp32 partial sum and the token count per row go into
+ * every rank's exchange buffer through peer memory; after the flag handshake each rank forms
+ * L2normalise(sum_p partial_p / sum_p len_p) -- the unsplit encoder's value up to fp32 summation order, identical
+ * on all ranks.  (The reference's own long-text path is the unweighted chunk mean of qc_chunk_mean,
+ * lib/quoracle/models/embeddings.ex:173-192,371-383; this is the encoder itself spread over devices.)
+ * Handles are exported / attached with qc_split_export / qc_split_attach and released with qc_split_destroy.
+ * qc_decide_tsplit_dev adds K3; d_emb may be NULL (context workspace) or receives the [B*N, dim] rows.
+ */
+int qc_tsplit_create(qc_ctx* ctx, int world, int rank, int max_rows, qc_split** out);
+int qc_embed_tsplit_dev(qc_ctx* ctx, qc_split* split, const int32_t* d_token_ids, const int32_t* d_lens, int R,
+                        int T_local, float* d_emb, void* stream);
+int qc_decide_tsplit_dev(qc_ctx* ctx, qc_split* split, const int32_t* d_token_ids, const int32_t* d_lens, int B, int N,
+                         int T_local, const float* d_thr, int32_t* d_ref_ok, int32_t* d_medoid, float* d_cos,
+                         float* d_emb, void* stream);
+
 /* Test/tuning hook: K3 kernel for pools of 9..64 candidates. 0 = auto (tcgen05 kind::tf32 kernel when the
  * matrix is TMA-addressable: D % 4 == 0, 16-byte aligned base; the mma.sync kernel otherwise), 1 = always the
  * mma.sync kernel, 2 = tcgen05 only (QC_ERR_UNSUPPORTED when the layout does not allow it). */

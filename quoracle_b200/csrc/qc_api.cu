@@ -264,7 +264,8 @@ int d2h(qc_ctx* c, void* user, const void* dsrc, size_t bytes, size_t* stage_off
 size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
 
 int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, int T, float* d_emb, cudaStream_t s,
-               DevBuf* part_buf = nullptr) {
+               DevBuf* part_buf = nullptr, const qc::FinalizeDst* scatter = nullptr,
+               const qc::TsplitDst* tsplit = nullptr) {
   DevBuf& part = part_buf ? *part_buf : c->part;
   if (!c->variant_forced) c->variant = qc::encoder_auto_variant(c->dim, T);
   const int TB = c->variant.token_block;
@@ -293,7 +294,12 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
   }
   {
     KernelScope ks(c, QC_K_FINALIZE, s);
-    QC_CUDA(qc::launch_finalize(static_cast<const float*>(part.p), d_lens, d_emb, R, bpc, TB, c->dim, s));
+    if (tsplit != nullptr) {
+      QC_CUDA(qc::launch_tsplit_partial(static_cast<const float*>(part.p), d_lens, *tsplit, R, bpc, TB, c->dim, s));
+      return QC_OK;
+    }
+    QC_CUDA(qc::launch_finalize(static_cast<const float*>(part.p), d_lens, scatter ? *scatter : qc::finalize_plain(d_emb),
+                                R, bpc, TB, c->dim, s));
   }
   return QC_OK;
 }
@@ -683,6 +689,224 @@ int qc_embed_batch(qc_ctx* c, const int32_t* token_ids, const int32_t* lens, int
   if ((st = check_token_flag(c)) != QC_OK) return st;
   for (const PendingOut& p : pend) memcpy(p.user, p.staged, p.bytes);
   return QC_OK;
+}
+
+// ---- pool split across GPUs -------------------------------------------
+// Each rank embeds its pool_local candidates of every decision; K2 stores each normalised row into the
+// gathered [B, world * pool_local, D] buffer of every rank (its own and, through CUDA IPC peer mappings over
+// NVLink, each peer's) -- the all-gather is those stores -- then a flag handshake and K3 on the local copy.
+// Two buffers alternate by call parity: a rank can only be two calls ahead of a peer that has not yet read.
+struct qc_split {
+  qc_ctx* ctx = nullptr;
+  int world = 0, rank = 0, max_decisions = 0, pool_local = 0;
+  size_t buf_bytes = 0;                       // one gathered buffer
+  char* local = nullptr;                      // [2 x buf_bytes][flags]
+  char* peer[qc::kMaxFinalizeDst] = {};       // peer-mapped bases (peer[rank] == local)
+  bool attached[qc::kMaxFinalizeDst] = {};
+  uint32_t epoch = 0;
+  int last_buf = 0, last_B = 0;
+  int mode = 0;                               // 0: pool split (rows gathered), 1: candidates sharded on T
+  int max_rows = 0;                           // mode 1
+  size_t psum_bytes = 0;                      // mode 1: [world][max_rows][D] fp32, followed by the token counts
+};
+
+int qc_split_create(qc_ctx* c, int world, int rank, int max_decisions, int pool_local, qc_split** out) {
+  if (c == nullptr || out == nullptr || world < 1 || world > qc::kMaxFinalizeDst || rank < 0 || rank >= world ||
+      max_decisions < 1 || pool_local < 1)
+    return QC_ERR_INVALID_INPUT;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  if (world * pool_local > QC_MAX_POOL) return QC_ERR_UNSUPPORTED;
+  DeviceGuard g(c->device);
+  qc_split* sp = new (std::nothrow) qc_split();
+  if (sp == nullptr) return QC_ERR_OUT_OF_MEMORY;
+  sp->ctx = c;
+  sp->world = world;
+  sp->rank = rank;
+  sp->max_decisions = max_decisions;
+  sp->pool_local = pool_local;
+  sp->buf_bytes = pad256(static_cast<size_t>(max_decisions) * world * pool_local * c->dim * sizeof(float));
+  const size_t total = 2 * sp->buf_bytes + 256;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, total);      // cudaMalloc: the allocation kind CUDA IPC can export
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    delete sp;
+    return cuda_status(e);
+  }
+  cudaMemset(p, 0, total);
+  cudaDeviceSynchronize();
+  sp->local = static_cast<char*>(p);
+  sp->peer[rank] = sp->local;
+  sp->attached[rank] = true;
+  *out = sp;
+  return QC_OK;
+}
+
+int qc_split_export(qc_split* sp, uint8_t handle[QC_SPLIT_HANDLE_BYTES]) {
+  if (sp == nullptr || handle == nullptr) return QC_ERR_INVALID_INPUT;
+  static_assert(sizeof(cudaIpcMemHandle_t) <= QC_SPLIT_HANDLE_BYTES, "IPC handle does not fit the ABI handle");
+  DeviceGuard g(sp->ctx->device);
+  cudaIpcMemHandle_t h;
+  QC_CUDA(cudaIpcGetMemHandle(&h, sp->local));
+  memset(handle, 0, QC_SPLIT_HANDLE_BYTES);
+  memcpy(handle, &h, sizeof(h));
+  return QC_OK;
+}
+
+int qc_split_attach(qc_split* sp, int peer_rank, const uint8_t handle[QC_SPLIT_HANDLE_BYTES]) {
+  if (sp == nullptr || handle == nullptr || peer_rank < 0 || peer_rank >= sp->world) return QC_ERR_INVALID_INPUT;
+  if (peer_rank == sp->rank || sp->attached[peer_rank]) return QC_OK;
+  DeviceGuard g(sp->ctx->device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  QC_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  sp->peer[peer_rank] = static_cast<char*>(p);
+  sp->attached[peer_rank] = true;
+  return QC_OK;
+}
+
+int qc_split_destroy(qc_split* sp) {
+  if (sp == nullptr) return QC_OK;
+  DeviceGuard g(sp->ctx->device);
+  cudaDeviceSynchronize();
+  for (int p = 0; p < sp->world; ++p)
+    if (p != sp->rank && sp->attached[p] && sp->peer[p]) cudaIpcCloseMemHandle(sp->peer[p]);
+  if (sp->local) cudaFree(sp->local);
+  delete sp;
+  return QC_OK;
+}
+
+int qc_split_gathered(const qc_split* sp, const float** d_emb, int32_t* decisions) {
+  if (sp == nullptr || d_emb == nullptr || sp->mode != 0) return QC_ERR_INVALID_INPUT;
+  *d_emb = reinterpret_cast<const float*>(sp->local + static_cast<size_t>(sp->last_buf) * sp->buf_bytes);
+  if (decisions) *decisions = sp->last_B;
+  return QC_OK;
+}
+
+int qc_decide_split_dev(qc_ctx* c, qc_split* sp, const int32_t* d_tok, const int32_t* d_lens, int B, int T,
+                        const float* d_thr, int32_t* d_ref_ok, int32_t* d_medoid, float* d_cos, void* stream) {
+  if (c == nullptr || sp == nullptr || sp->ctx != c || sp->mode != 0 || d_tok == nullptr || d_lens == nullptr ||
+      d_thr == nullptr || B < 0 || T < 1)
+    return QC_ERR_INVALID_INPUT;
+  if (B > sp->max_decisions) return QC_ERR_UNSUPPORTED;
+  if (T > QC_MAX_TOKENS) return QC_ERR_CONTEXT_LENGTH;
+  for (int p = 0; p < sp->world; ++p)
+    if (!sp->attached[p]) return QC_ERR_NOT_CONFIGURED;
+  if (B == 0) return QC_OK;
+  DeviceGuard g(c->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  const uint32_t epoch = ++sp->epoch;
+  const int buf = static_cast<int>(epoch & 1u);
+  const int n_total = sp->world * sp->pool_local;
+  qc::FinalizeDst dst{};
+  qc::PeerFlags pf{};
+  dst.count = sp->world;
+  dst.n_local = sp->pool_local;
+  dst.n_total = n_total;
+  dst.row_offset = sp->rank * sp->pool_local;
+  pf.world = sp->world;
+  pf.rank = sp->rank;
+  for (int p = 0; p < sp->world; ++p) {
+    dst.base[p] = reinterpret_cast<float*>(sp->peer[p] + static_cast<size_t>(buf) * sp->buf_bytes);
+    pf.flags[p] = reinterpret_cast<uint32_t*>(sp->peer[p] + 2 * sp->buf_bytes);
+  }
+  int st = encode_dev(c, d_tok, d_lens, B * sp->pool_local, T, nullptr, s, nullptr, &dst);
+  if (st != QC_OK) return st;
+  c->launches += 2;
+  QC_CUDA(qc::launch_peer_signal(pf, epoch, s));
+  QC_CUDA(qc::launch_peer_wait(pf, epoch, c->d_err, s));
+  sp->last_buf = buf;
+  sp->last_B = B;
+  return qc_similarity_batch_dev(c, reinterpret_cast<const float*>(sp->local + static_cast<size_t>(buf) * sp->buf_bytes), B,
+                                 n_total, c->dim, d_thr, d_ref_ok, d_medoid, d_cos, s);
+}
+
+// ---- candidates sharded on T across GPUs (long-context path) -------------
+int qc_tsplit_create(qc_ctx* c, int world, int rank, int max_rows, qc_split** out) {
+  if (c == nullptr || out == nullptr || world < 1 || world > qc::kMaxFinalizeDst || rank < 0 || rank >= world ||
+      max_rows < 1)
+    return QC_ERR_INVALID_INPUT;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  DeviceGuard g(c->device);
+  qc_split* sp = new (std::nothrow) qc_split();
+  if (sp == nullptr) return QC_ERR_OUT_OF_MEMORY;
+  sp->ctx = c;
+  sp->world = world;
+  sp->rank = rank;
+  sp->mode = 1;
+  sp->max_rows = max_rows;
+  sp->psum_bytes = pad256(static_cast<size_t>(world) * max_rows * c->dim * sizeof(float));
+  sp->buf_bytes = sp->psum_bytes + pad256(static_cast<size_t>(world) * max_rows * sizeof(int32_t));
+  const size_t total = 2 * sp->buf_bytes + 256;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, total);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    delete sp;
+    return cuda_status(e);
+  }
+  cudaMemset(p, 0, total);
+  cudaDeviceSynchronize();
+  sp->local = static_cast<char*>(p);
+  sp->peer[rank] = sp->local;
+  sp->attached[rank] = true;
+  *out = sp;
+  return QC_OK;
+}
+
+int qc_embed_tsplit_dev(qc_ctx* c, qc_split* sp, const int32_t* d_tok, const int32_t* d_lens, int R, int T_local,
+                        float* d_emb, void* stream) {
+  if (c == nullptr || sp == nullptr || sp->ctx != c || sp->mode != 1 || d_tok == nullptr || d_lens == nullptr ||
+      d_emb == nullptr || R < 0 || T_local < 1)
+    return QC_ERR_INVALID_INPUT;
+  if (R > sp->max_rows) return QC_ERR_UNSUPPORTED;
+  if (T_local > QC_MAX_TOKENS) return QC_ERR_CONTEXT_LENGTH;
+  for (int p = 0; p < sp->world; ++p)
+    if (!sp->attached[p]) return QC_ERR_NOT_CONFIGURED;
+  if (R == 0) return QC_OK;
+  DeviceGuard g(c->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  const uint32_t epoch = ++sp->epoch;
+  const size_t off = static_cast<size_t>(epoch & 1u) * sp->buf_bytes;
+  qc::TsplitDst dst{};
+  qc::PeerFlags pf{};
+  dst.count = sp->world;
+  dst.rank = sp->rank;
+  dst.max_rows = sp->max_rows;
+  pf.world = sp->world;
+  pf.rank = sp->rank;
+  for (int p = 0; p < sp->world; ++p) {
+    dst.psum[p] = reinterpret_cast<float*>(sp->peer[p] + off);
+    dst.lens[p] = reinterpret_cast<int32_t*>(sp->peer[p] + off + sp->psum_bytes);
+    pf.flags[p] = reinterpret_cast<uint32_t*>(sp->peer[p] + 2 * sp->buf_bytes);
+  }
+  int st = encode_dev(c, d_tok, d_lens, R, T_local, nullptr, s, nullptr, nullptr, &dst);
+  if (st != QC_OK) return st;
+  c->launches += 3;
+  QC_CUDA(qc::launch_peer_signal(pf, epoch, s));
+  QC_CUDA(qc::launch_peer_wait(pf, epoch, c->d_err, s));
+  QC_CUDA(qc::launch_tsplit_reduce(reinterpret_cast<const float*>(sp->local + off),
+                                   reinterpret_cast<const int32_t*>(sp->local + off + sp->psum_bytes), d_emb, R, sp->world,
+                                   sp->max_rows, c->dim, s));
+  return QC_OK;
+}
+
+int qc_decide_tsplit_dev(qc_ctx* c, qc_split* sp, const int32_t* d_tok, const int32_t* d_lens, int B, int N, int T_local,
+                         const float* d_thr, int32_t* d_ref_ok, int32_t* d_medoid, float* d_cos, float* d_emb,
+                         void* stream) {
+  if (c == nullptr || d_thr == nullptr || B < 0) return QC_ERR_INVALID_INPUT;
+  if (N < 1 || N > QC_MAX_POOL) return QC_ERR_UNSUPPORTED;
+  if (B == 0) return QC_OK;
+  float* emb = d_emb;
+  if (emb == nullptr) {
+    DeviceGuard g(c->device);
+    QC_CUDA(c->emb.ensure(static_cast<size_t>(B) * N * c->dim * sizeof(float)));
+    emb = static_cast<float*>(c->emb.p);
+  }
+  int st = qc_embed_tsplit_dev(c, sp, d_tok, d_lens, B * N, T_local, emb, stream);
+  if (st != QC_OK) return st;
+  return qc_similarity_batch_dev(c, emb, B, N, c->dim, d_thr, d_ref_ok, d_medoid, d_cos, stream);
 }
 
 int qc_similarity_batch(qc_ctx* c, const float* emb, int B, int N, int D, const float* thr, int32_t* out_ref_ok,

@@ -36,9 +36,51 @@ int encoder_variant_w_stages(int dim, const EncoderVariant& v);
 EncoderVariant encoder_default_variant(int dim);
 EncoderVariant encoder_auto_variant(int dim, int T);
 
-// K2: emb[r, :] = L2normalise( (sum_j part[r, j, :]) / len[r] ), j < ceil(len/TB); len == 0 -> zeros.
-cudaError_t launch_finalize(const float* part, const int32_t* lens, float* emb, int R, int bpc, int TB, int dim,
-                            cudaStream_t stream);
+// K2: row r -> L2normalise( (sum_j part[r, j, :]) / len[r] ), j < ceil(len/TB); len == 0 -> zeros.  The row is
+// stored to `count` destinations (one for the plain path; this rank's and every peer's gathered buffer when a
+// pool is split across GPUs) at row (r / n_local) * n_total + row_offset + r % n_local.
+constexpr int kMaxFinalizeDst = 8;
+struct FinalizeDst {
+  float* base[kMaxFinalizeDst];
+  int count;
+  int n_local;     // candidates per decision held by this rank
+  int n_total;     // candidates per decision in the destination layout
+  int row_offset;  // rank * n_local
+};
+inline FinalizeDst finalize_plain(float* emb) {
+  FinalizeDst d{};
+  d.base[0] = emb;
+  d.count = 1;
+  d.n_local = 1;
+  d.n_total = 1;
+  d.row_offset = 0;
+  return d;
+}
+cudaError_t launch_finalize(const float* part, const int32_t* lens, const FinalizeDst& dst, int R, int bpc, int TB,
+                            int dim, cudaStream_t stream);
+
+// Candidates sharded on T: per-rank partial sums [world][max_rows][D] + token counts [world][max_rows] in every
+// rank's exchange buffer; psum[q] / lens[q] = rank q's copy (peer-mapped).
+struct TsplitDst {
+  float* psum[kMaxFinalizeDst];
+  int32_t* lens[kMaxFinalizeDst];
+  int count;     // world
+  int rank;
+  int max_rows;
+};
+cudaError_t launch_tsplit_partial(const float* part, const int32_t* lens, const TsplitDst& dst, int R, int bpc, int TB,
+                                  int dim, cudaStream_t stream);
+cudaError_t launch_tsplit_reduce(const float* psum, const int32_t* lens, float* emb, int R, int world, int max_rows,
+                                 int dim, cudaStream_t stream);
+
+// Split-pool handshake: flags[p] = device pointer to rank p's flag array (uint32[kMaxFinalizeDst], peer-mapped).
+struct PeerFlags {
+  uint32_t* flags[kMaxFinalizeDst];
+  int world;
+  int rank;
+};
+cudaError_t launch_peer_signal(const PeerFlags& f, uint32_t epoch, cudaStream_t stream);
+cudaError_t launch_peer_wait(const PeerFlags& f, uint32_t epoch, int32_t* dbg, cudaStream_t stream);
 
 // K3: per decision: N x N cosine matrix, reference verdict, medoid vote.
 cudaError_t launch_similarity(const float* emb, int B, int N, int D, const float* thr, int32_t* ref_ok,

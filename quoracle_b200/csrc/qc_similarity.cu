@@ -35,8 +35,8 @@ __device__ __forceinline__ float cosine_from(float dot, float na, float nb) {
 // ------------------------------------------------------------------------------------------
 template <int PER>
 __global__ void __launch_bounds__(256) qc_finalize_kernel(const float* __restrict__ part,
-                                                          const int32_t* __restrict__ lens,
-                                                          float* __restrict__ emb, int R, int bpc, int TB, int D) {
+                                                          const int32_t* __restrict__ lens, FinalizeDst dst,
+                                                          int R, int bpc, int TB, int D) {
   const int r = blockIdx.x;
   if (r >= R) return;
   const int len = lens[r];
@@ -64,6 +64,92 @@ __global__ void __launch_bounds__(256) qc_finalize_kernel(const float* __restric
   for (int w = 0; w < 8; ++w) tot += red[w];
   const float nrm = sqrtf(tot);
   const float inv = nrm > 0.f ? 1.f / nrm : 0.f;
+  // Local row r = (decision b, local candidate n).  In the gathered layout of a pool split across ranks it is
+  // row (b, rank * n_local + n) of [B, n_total, D]; the same row goes to every destination (this rank's own
+  // buffer and, over NVLink, each peer's): the all-gather is these stores.  Unsplit: n_local == n_total.
+  const int b = r / dst.n_local;
+  const size_t row = static_cast<size_t>(b) * dst.n_total + dst.row_offset + (r - b * dst.n_local);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int d = threadIdx.x + i * 256;
+    if (d < D) {
+      const float o = v[i] * inv;
+      for (int q = 0; q < dst.count; ++q) dst.base[q][row * D + d] = o;
+    }
+  }
+}
+
+cudaError_t launch_finalize(const float* part, const int32_t* lens, const FinalizeDst& dst, int R, int bpc, int TB,
+                            int dim, cudaStream_t stream) {
+  if (R <= 0) return cudaSuccess;
+  if (dst.count < 1 || dst.count > kMaxFinalizeDst || dst.n_local < 1) return cudaErrorInvalidValue;
+  if (dim <= 512) qc_finalize_kernel<2><<<R, 256, 0, stream>>>(part, lens, dst, R, bpc, TB, dim);
+  else if (dim <= 1024) qc_finalize_kernel<4><<<R, 256, 0, stream>>>(part, lens, dst, R, bpc, TB, dim);
+  else if (dim <= 2048) qc_finalize_kernel<8><<<R, 256, 0, stream>>>(part, lens, dst, R, bpc, TB, dim);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Candidates sharded on T across ranks (long-context path).
+// partial: row r's block sums of THIS rank's token slice -> one fp32 partial sum, stored with the slice's token
+//          count into slot `rank` of every rank's exchange buffer (peer memory; the all-gather is these stores).
+// reduce:  emb[r] = L2normalise( (sum_p psum[p][r]) / (sum_p len[p][r]) ), p ascending -- the same value on
+//          every rank, and the same quantity the unsplit encoder computes (fp32 association differs).
+// ------------------------------------------------------------------------------------------
+template <int PER>
+__global__ void __launch_bounds__(256) qc_tsplit_partial_kernel(const float* __restrict__ part,
+                                                                const int32_t* __restrict__ lens, TsplitDst dst, int R,
+                                                                int bpc, int TB, int D) {
+  const int r = blockIdx.x;
+  if (r >= R) return;
+  const int len = lens[r];
+  const int nb = (len + TB - 1) / TB;
+  const float* p = part + static_cast<size_t>(r) * bpc * D;
+  const size_t row = (static_cast<size_t>(dst.rank) * dst.max_rows + r);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int d = threadIdx.x + i * 256;
+    if (d < D) {
+      float s = 0.f;
+      for (int j = 0; j < nb; ++j) s += p[static_cast<size_t>(j) * D + d];  // fixed block order
+      for (int q = 0; q < dst.count; ++q) dst.psum[q][row * D + d] = s;
+    }
+  }
+  if (threadIdx.x == 0)
+    for (int q = 0; q < dst.count; ++q) dst.lens[q][row] = len;
+}
+
+template <int PER>
+__global__ void __launch_bounds__(256) qc_tsplit_reduce_kernel(const float* __restrict__ psum,
+                                                               const int32_t* __restrict__ lens, float* __restrict__ emb,
+                                                               int R, int world, int max_rows, int D) {
+  const int r = blockIdx.x;
+  if (r >= R) return;
+  int total = 0;
+  for (int p = 0; p < world; ++p) total += lens[static_cast<size_t>(p) * max_rows + r];
+  float v[PER];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int d = threadIdx.x + i * 256;
+    float s = 0.f;
+    if (d < D) {
+      for (int p = 0; p < world; ++p) s += psum[(static_cast<size_t>(p) * max_rows + r) * D + d];  // rank order
+      s = total > 0 ? s / static_cast<float>(total) : 0.f;
+    }
+    v[i] = s;
+    ss += s * s;
+  }
+  __shared__ float red[8];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  const float nrm = sqrtf(tot);
+  const float inv = nrm > 0.f ? 1.f / nrm : 0.f;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const int d = threadIdx.x + i * 256;
@@ -71,13 +157,67 @@ __global__ void __launch_bounds__(256) qc_finalize_kernel(const float* __restric
   }
 }
 
-cudaError_t launch_finalize(const float* part, const int32_t* lens, float* emb, int R, int bpc, int TB, int dim,
-                            cudaStream_t stream) {
+cudaError_t launch_tsplit_partial(const float* part, const int32_t* lens, const TsplitDst& dst, int R, int bpc, int TB,
+                                  int dim, cudaStream_t stream) {
   if (R <= 0) return cudaSuccess;
-  if (dim <= 512) qc_finalize_kernel<2><<<R, 256, 0, stream>>>(part, lens, emb, R, bpc, TB, dim);
-  else if (dim <= 1024) qc_finalize_kernel<4><<<R, 256, 0, stream>>>(part, lens, emb, R, bpc, TB, dim);
-  else if (dim <= 2048) qc_finalize_kernel<8><<<R, 256, 0, stream>>>(part, lens, emb, R, bpc, TB, dim);
+  if (dst.count < 1 || dst.count > kMaxFinalizeDst) return cudaErrorInvalidValue;
+  if (dim <= 512) qc_tsplit_partial_kernel<2><<<R, 256, 0, stream>>>(part, lens, dst, R, bpc, TB, dim);
+  else if (dim <= 1024) qc_tsplit_partial_kernel<4><<<R, 256, 0, stream>>>(part, lens, dst, R, bpc, TB, dim);
+  else if (dim <= 2048) qc_tsplit_partial_kernel<8><<<R, 256, 0, stream>>>(part, lens, dst, R, bpc, TB, dim);
   else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tsplit_reduce(const float* psum, const int32_t* lens, float* emb, int R, int world, int max_rows,
+                                 int dim, cudaStream_t stream) {
+  if (R <= 0) return cudaSuccess;
+  if (dim <= 512) qc_tsplit_reduce_kernel<2><<<R, 256, 0, stream>>>(psum, lens, emb, R, world, max_rows, dim);
+  else if (dim <= 1024) qc_tsplit_reduce_kernel<4><<<R, 256, 0, stream>>>(psum, lens, emb, R, world, max_rows, dim);
+  else if (dim <= 2048) qc_tsplit_reduce_kernel<8><<<R, 256, 0, stream>>>(psum, lens, emb, R, world, max_rows, dim);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Cross-GPU handshake of the split-pool path (flags live in each rank's exported allocation).
+// signal: after this rank's rows are stored everywhere, publish `epoch` in slot `rank` of every peer's flag
+// array (system-scope release).  wait: spin until every peer's slot in the local array reached `epoch`
+// (system-scope acquire); a bounded spin turns a missing peer into a watchdog record instead of a hang.
+// ------------------------------------------------------------------------------------------
+__global__ void qc_peer_signal_kernel(PeerFlags f, uint32_t epoch) {
+  const int p = threadIdx.x;
+  if (p >= f.world) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.flags[p] + f.rank), "r"(epoch) : "memory");
+}
+
+__global__ void qc_peer_wait_kernel(PeerFlags f, uint32_t epoch, int32_t* dbg) {
+  const int p = threadIdx.x;
+  if (p >= f.world) return;
+  const uint32_t* slot = f.flags[f.rank] + p;
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
+    if (static_cast<int32_t>(v - epoch) >= 0) break;
+    if (clock64() - t0 > 6000000000LL) {          // ~3 s: a peer never arrived
+      if (atomicCAS(dbg, 0, 1) == 0) {
+        dbg[1] = 900 + p;
+        dbg[2] = f.rank;
+        dbg[3] = static_cast<int32_t>(epoch);
+      }
+      break;
+    }
+    __nanosleep(200);
+  }
+}
+
+cudaError_t launch_peer_signal(const PeerFlags& f, uint32_t epoch, cudaStream_t stream) {
+  qc_peer_signal_kernel<<<1, 32, 0, stream>>>(f, epoch);
+  return cudaGetLastError();
+}
+cudaError_t launch_peer_wait(const PeerFlags& f, uint32_t epoch, int32_t* dbg, cudaStream_t stream) {
+  qc_peer_wait_kernel<<<1, 32, 0, stream>>>(f, epoch, dbg);
   return cudaGetLastError();
 }
 

@@ -35,6 +35,8 @@ ABI_SYMBOLS = (
     "qc_launch_count", "qc_profile_enable", "qc_profile_reset", "qc_kernel_stats",
     "qc_encoder_info", "qc_encoder_set_cta_group", "qc_encoder_set_variant", "qc_encoder_stall_profile",
     "qc_similarity_set_path",
+    "qc_split_create", "qc_split_export", "qc_split_attach", "qc_decide_split_dev", "qc_split_gathered",
+    "qc_split_destroy", "qc_tsplit_create", "qc_embed_tsplit_dev", "qc_decide_tsplit_dev",
 )
 
 
@@ -97,6 +99,24 @@ def load_library() -> ctypes.CDLL:
     lib.qc_embed_batch_dev.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.qc_similarity_batch_dev.restype = i32
     lib.qc_similarity_batch_dev.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.qc_split_create.restype = i32
+    lib.qc_split_create.argtypes = [vp, i32, i32, i32, i32, ctypes.POINTER(vp)]
+    lib.qc_split_export.restype = i32
+    lib.qc_split_export.argtypes = [vp, ctypes.c_char_p]
+    lib.qc_split_attach.restype = i32
+    lib.qc_split_attach.argtypes = [vp, i32, ctypes.c_char_p]
+    lib.qc_decide_split_dev.restype = i32
+    lib.qc_decide_split_dev.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.qc_split_gathered.restype = i32
+    lib.qc_split_gathered.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i32)]
+    lib.qc_tsplit_create.restype = i32
+    lib.qc_tsplit_create.argtypes = [vp, i32, i32, i32, ctypes.POINTER(vp)]
+    lib.qc_embed_tsplit_dev.restype = i32
+    lib.qc_embed_tsplit_dev.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
+    lib.qc_decide_tsplit_dev.restype = i32
+    lib.qc_decide_tsplit_dev.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.qc_split_destroy.restype = i32
+    lib.qc_split_destroy.argtypes = [vp]
     lib.qc_strerror.restype = ctypes.c_char_p
     lib.qc_strerror.argtypes = [i32]
     lib.qc_status_atom.restype = ctypes.c_char_p
@@ -304,6 +324,14 @@ class Context:
         _check(self._lib.qc_similarity_batch_dev(self._h, _dev(d_emb), b, n, d, _dev(d_thr), _dev(d_ref_ok),
                                                  _dev(d_medoid), _dev(d_cos), _dev(stream)))
 
+    def token_split(self, world: int, rank: int, max_rows: int) -> "TokenSplit":
+        """Exchange object for candidates sharded on T over `world` GPUs; see TokenSplit."""
+        return TokenSplit(self, world, rank, max_rows)
+
+    def split_pool(self, world: int, rank: int, max_decisions: int, pool_local: int) -> "SplitPool":
+        """Gathered-buffer object for a pool split over `world` GPUs (one process each); see SplitPool."""
+        return SplitPool(self, world, rank, max_decisions, pool_local)
+
     # -- introspection ---------------------------------------------------------------------------
     def check_status(self) -> None:
         """Synchronise and raise if an earlier asynchronous ``*_dev`` call flagged a device-side error."""
@@ -358,3 +386,76 @@ class Context:
 
 def _as(a, dtype) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+QC_SPLIT_HANDLE_BYTES = 64
+
+
+class SplitPool:
+    """A decision pool split across the GPUs of one node (qc_split_*).
+
+    Each rank holds `pool_local` consecutive members of every pool.  ``handle()`` is this rank's 64-byte
+    export; ``attach(rank, handle)`` maps a peer's.  ``decide_dev`` embeds the local candidates, stores the
+    normalised rows into every rank's gathered buffer over peer memory, and decides on the full pool."""
+
+    def __init__(self, ctx: "Context", world: int, rank: int, max_decisions: int, pool_local: int):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        self.world, self.rank, self.pool_local = int(world), int(rank), int(pool_local)
+        h = ctypes.c_void_p()
+        _check(self._lib.qc_split_create(ctx._h, self.world, self.rank, int(max_decisions), self.pool_local,
+                                         ctypes.byref(h)))
+        self._h = h
+
+    def handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(QC_SPLIT_HANDLE_BYTES)
+        _check(self._lib.qc_split_export(self._h, buf))
+        return bytes(buf.raw)
+
+    def attach(self, peer_rank: int, handle: bytes) -> None:
+        if len(handle) != QC_SPLIT_HANDLE_BYTES:
+            raise ValueError("split-pool handle must be 64 bytes")
+        _check(self._lib.qc_split_attach(self._h, int(peer_rank), handle))
+
+    def decide_dev(self, d_token_ids, d_lens, b: int, t: int, d_thr, d_ref_ok=0, d_medoid=0, d_cos=0,
+                   stream=0) -> None:
+        _check(self._lib.qc_decide_split_dev(self._ctx._h, self._h, _dev(d_token_ids), _dev(d_lens), int(b), int(t),
+                                             _dev(d_thr), _dev(d_ref_ok), _dev(d_medoid), _dev(d_cos), _dev(stream)))
+
+    def gathered(self):
+        """(device address, decisions) of the gathered rows [decisions, world * pool_local, dim] of the last call."""
+        p, n = ctypes.c_void_p(), ctypes.c_int32()
+        _check(self._lib.qc_split_gathered(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.qc_split_destroy(self._h)
+            self._h = None
+
+
+class TokenSplit(SplitPool):
+    """Long candidates sharded on T across the GPUs of one node (qc_tsplit_*).
+
+    Rank p passes the p-th token slice of every candidate; every rank ends up with the full embeddings."""
+
+    def __init__(self, ctx: "Context", world: int, rank: int, max_rows: int):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        self.world, self.rank = int(world), int(rank)
+        h = ctypes.c_void_p()
+        _check(self._lib.qc_tsplit_create(ctx._h, self.world, self.rank, int(max_rows), ctypes.byref(h)))
+        self._h = h
+
+    def embed_dev(self, d_token_ids, d_lens, r: int, t_local: int, d_emb, stream=0) -> None:
+        _check(self._lib.qc_embed_tsplit_dev(self._ctx._h, self._h, _dev(d_token_ids), _dev(d_lens), int(r),
+                                             int(t_local), _dev(d_emb), _dev(stream)))
+
+    def decide_dev(self, d_token_ids, d_lens, b: int, n: int, t_local: int, d_thr, d_ref_ok=0, d_medoid=0, d_cos=0,
+                   d_emb=0, stream=0) -> None:
+        _check(self._lib.qc_decide_tsplit_dev(self._ctx._h, self._h, _dev(d_token_ids), _dev(d_lens), int(b), int(n),
+                                              int(t_local), _dev(d_thr), _dev(d_ref_ok), _dev(d_medoid), _dev(d_cos),
+                                              _dev(d_emb), _dev(stream)))
+
+    def gathered(self):
+        raise NotImplementedError("token-split objects hold partial sums, not gathered rows")

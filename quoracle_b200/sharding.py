@@ -72,3 +72,48 @@ def decide_split_pool(local_emb, thr, similarity_fn: Callable, group=None):
     dist.all_gather(parts, local_emb.contiguous(), group=group)
     full = torch.cat(parts, dim=1).contiguous()
     return similarity_fn(full, thr), full
+
+
+def connect_split_pool(ctx, max_decisions: int, pool_local: int, group=None):
+    """Builds the peer-memory split-pool object for the calling rank: every rank exports its 64-byte handle,
+    one all_gather_object exchanges them (control plane only), every rank maps its peers.  The data path
+    (`SplitPool.decide_dev`) then runs without any collective call: K2 stores the rows over NVLink."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sp = ctx.split_pool(world, rank, max_decisions, pool_local)
+    handles = [None] * world
+    dist.all_gather_object(handles, sp.handle(), group=group)
+    for p, h in enumerate(handles):
+        if p != rank:
+            sp.attach(p, h)
+    dist.barrier(group=group)
+    return sp
+
+
+def connect_token_split(ctx, max_rows: int, group=None):
+    """Same handshake as connect_split_pool for candidates sharded on T (`TokenSplit`)."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ts = ctx.token_split(world, rank, max_rows)
+    handles = [None] * world
+    dist.all_gather_object(handles, ts.handle(), group=group)
+    for p, h in enumerate(handles):
+        if p != rank:
+            ts.attach(p, h)
+    dist.barrier(group=group)
+    return ts
+
+
+def token_slices(token_ids, lens, world: int):
+    """Host helper: split [R, T] token ids (T divisible by world) and their lengths into per-rank slices:
+    rank p gets columns [p*T/world, (p+1)*T/world) and len_p = clip(len - p*T/world, 0, T/world)."""
+    import numpy as np
+    r, t = token_ids.shape
+    if t % world:
+        raise ValueError("T must divide over the ranks")
+    tl = t // world
+    out = []
+    for p in range(world):
+        out.append((np.ascontiguousarray(token_ids[:, p * tl:(p + 1) * tl]),
+                    np.clip(lens - p * tl, 0, tl).astype(np.int32)))
+    return out
