@@ -101,3 +101,41 @@ def test_decide_tree_on_gpu_matches_oracle(emb):
         kind, action, opts = ores.format_result(clusters, len(d["responses"]), 5, {"embedding_fn": fn})
         assert g["kind"] == kind and g["action"]["action"] == action["action"]
         assert g["action"]["params"] == action["params"]
+
+
+def test_http_facade_serves_the_library_embeddings(emb):
+    """The OpenAI-compatible endpoint the unmodified reference can point its local-model route at
+    (local_model_helper.ex:92-110): vectors are the library's, concurrent requests share GPU calls."""
+    import json
+    import threading
+    import urllib.request
+
+    from oracle import encoder as oenc
+    from quoracle_b200 import tokenizer
+    from quoracle_b200.http_facade import EmbeddingServer
+    srv = EmbeddingServer(emb, max_wait_ms=20.0).start()
+    try:
+        texts = [f"agent {i}: restart service {i % 5} after the config change" for i in range(16)]
+        out = [None] * len(texts)
+
+        def worker(i):
+            req = urllib.request.Request(srv.url + "/embeddings", data=json.dumps({"model": "vllm:x", "input": texts[i]}).encode(),
+                                         headers={"Content-Type": "application/json"})
+            with urllib.request.urlopen(req, timeout=60) as r:
+                out[i] = json.loads(r.read())
+
+        calls0 = emb.gpu_calls
+        ts = [threading.Thread(target=worker, args=(i,)) for i in range(len(texts))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert emb.gpu_calls - calls0 == srv.batches < len(texts)
+        ids, lens = tokenizer.pack(texts, emb.vocab)
+        w = synth.make_encoder(768, vocab=32768, seed=synth.BASE_SEED + 9)      # the fixture's weights
+        want = oenc.encode(w.table_bf16, w.w_bf16, ids, lens)
+        got = np.array([o["data"][0]["embedding"] for o in out], np.float64)
+        assert np.max(np.abs(got - want)) < 2e-4
+        assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+    finally:
+        srv.stop()
