@@ -221,3 +221,38 @@ def test_error_statuses(ctx):
     with pytest.raises(native.QcError) as e:
         ctx.embed_batch(np.zeros((1, 4), np.int32), np.array([4], np.int32))
     assert e.value.atom == "not_configured"
+
+
+@pytest.mark.parametrize("n,d,b", [(8, 768, 65536), (16, 768, 16384), (64, 384, 4096), (33, 200, 3000)])
+def test_full_size_properties(ctx, n, d, b):
+    """Size-independent properties at BASELINE config-5 sizes (where the f64 oracle is too slow to be the checker):
+    permuting a pool permutes the matrix and moves the vote with it; positive row scaling changes nothing;
+    the matrix is symmetric with a unit diagonal; row 0's rule is recomputable from the returned cosines."""
+    rng = np.random.default_rng(n * d)
+    emb = synth.make_embeddings(min(b, 2048), n, d, seed=synth.BASE_SEED + n + d)
+    emb = np.tile(emb, ((b + emb.shape[0] - 1) // emb.shape[0], 1, 1))[:b].copy()
+    emb += 1e-3 * rng.standard_normal(emb.shape, dtype=np.float32)          # make the tiled copies distinct
+    thr = np.resize(np.array([0.3, 0.5, 0.85], np.float32), b)
+    ok, med, cos = ctx.similarity_batch(emb, thr)
+    assert np.all(np.isfinite(cos))
+    assert np.array_equal(cos, np.swapaxes(cos, 1, 2))
+    assert np.max(np.abs(np.diagonal(cos, axis1=1, axis2=2) - 1.0)) < 1e-6
+    # row-0 rule from the returned cosines (reference consensus_rules.ex:277-286)
+    assert np.array_equal(ok, np.all(cos[:, 0, 1:] >= thr[:, None], axis=1).astype(np.int32))
+    # vote from the returned cosines wherever the top two means are separated beyond fp32 summation noise
+    means = cos.astype(np.float64).mean(axis=2)
+    top2 = np.sort(means, axis=1)[:, -2:]
+    safe = (top2[:, 1] - top2[:, 0]) > 1e-6
+    assert safe.mean() > 0.5
+    assert np.array_equal(med[safe], np.argmax(means, axis=1)[safe].astype(np.int32))
+    # permutation equivariance
+    perm = rng.permutation(n)
+    ok_p, med_p, cos_p = ctx.similarity_batch(np.ascontiguousarray(emb[:, perm]), thr)
+    assert np.max(np.abs(cos_p - cos[:, perm][:, :, perm])) < 2e-6
+    inv = np.argsort(perm)
+    assert np.array_equal(med_p[safe], inv[med[safe]].astype(np.int32))
+    # positive scaling invariance
+    scale = rng.uniform(0.25, 4.0, size=(b, n, 1)).astype(np.float32)
+    _, med_s, cos_s = ctx.similarity_batch(emb * scale, thr)
+    assert np.max(np.abs(cos_s - cos)) < 2e-6
+    assert np.array_equal(med_s[safe], med[safe])
