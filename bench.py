@@ -43,6 +43,7 @@ CONFIGS = {
 }
 ROTATE = 40                      # distinct input batches per rank: 40 x 4.2 MB = 168 MB > 126 MB L2
 E2E_ROTATE = 8
+E2E_DEPTH = 4                    # batches in flight through qc_decide_batch_submit/_wait (<= QC_PIPELINE_SLOTS)
 WORKLOAD = ""
 
 
@@ -287,22 +288,23 @@ def run_ours(args):
     pin_len.array[...] = batches[0].lens
     pin_thr = native.PinnedArray((b,), np.float32)
     pin_thr.array[...] = batches[0].thr
-    # Two-deep pipeline of the host API (qc_decide_batch_submit / _wait): the H2D copy of step k+1 overlaps the
-    # GPU work of step k; every step still copies its own inputs from pinned host memory and reads its own
-    # verdicts back, all inside the timed region.
-    pin_ok = [native.PinnedArray((b,), np.int32) for _ in range(2)]
-    pin_med = [native.PinnedArray((b,), np.int32) for _ in range(2)]
-    outs = [native.DecideResult(pin_ok[k].array, pin_med[k].array, None, None) for k in range(2)]
+    # Pipelined host API (qc_decide_batch_submit / _wait), E2E_DEPTH batches in flight: the H2D copy of one step
+    # overlaps the GPU work of another and an encoder launch is always queued while the host turns a finished
+    # slot around; every step still copies its own inputs from pinned host memory and reads its own verdicts
+    # back, all inside the timed region.
+    pin_ok = [native.PinnedArray((b,), np.int32) for _ in range(E2E_DEPTH)]
+    pin_med = [native.PinnedArray((b,), np.int32) for _ in range(E2E_DEPTH)]
+    outs = [native.DecideResult(pin_ok[k].array, pin_med[k].array, None, None) for k in range(E2E_DEPTH)]
     e2e_steps = args.steps
 
     def e2e_run(nsteps):
         for i in range(nsteps):
-            k = i & 1
-            if i >= 2:
+            k = i % E2E_DEPTH
+            if i >= E2E_DEPTH:
                 ctx.decide_batch_wait(k)
             ctx.decide_batch_submit(k, pinned_tok[i % E2E_ROTATE].array, pin_len.array, pin_thr.array, outs[k])
-        for i in range(max(0, nsteps - 2), nsteps):
-            ctx.decide_batch_wait(i & 1)
+        for i in range(max(0, nsteps - E2E_DEPTH), nsteps):
+            ctx.decide_batch_wait(i % E2E_DEPTH)
 
     e2e_run(max(3, min(6, args.warmup)))
     barrier()
@@ -350,7 +352,7 @@ def run_ours(args):
                        "encoder": ctx.encoder_info(), "seed": synth.BASE_SEED + 2},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": b * n * t * 4 + b * n * 4 + b * 4,
                     "d2h_bytes_per_step": 2 * b * 4, "steps": e2e_steps,
-                    "api": "qc_decide_batch_submit/_wait (host C ABI, two batches in flight), pinned host buffers, wall clock"},
+                    "api": f"qc_decide_batch_submit/_wait (host C ABI, {E2E_DEPTH} batches in flight), pinned host buffers, wall clock"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "qc_encode_kernel (K1)", "achieved": achieved, "peak": peak,
@@ -390,10 +392,13 @@ def main():
     ap.add_argument("--cta-group", type=int, default=0, help="force the K1 variant (1 or 2); 0 = library default")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="size of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-depth", type=int, default=E2E_DEPTH, choices=[1, 2, 3, 4],
+                    help="batches in flight in the e2e leg (host C ABI submit/wait slots)")
     ap.add_argument("--config", choices=sorted(CONFIGS), default="c2",
                     help="BASELINE config (c2 = the headline; c3/c4 are the 8-GPU configs, per-GPU share)")
     args = ap.parse_args()
     select_config(args.config)
+    globals()["E2E_DEPTH"] = args.e2e_depth
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":
         run_reference(args)

@@ -117,11 +117,15 @@ int qc_decide_batch(qc_ctx* ctx, const int32_t* token_ids, const int32_t* lens, 
                     float* out_emb);
 
 /*
- * Two-deep pipelined form of qc_decide_batch: `submit` enqueues the copies and kernels of one batch on
- * slot 0 or 1 and returns; `wait` blocks until that slot's outputs are in the caller's buffers.  A caller
- * (the NIF collector) that submits batch k+1 before waiting for batch k overlaps its host->device copy with
- * the GPU work of batch k.  Input and output buffers must stay valid and untouched until `wait` returns.
+ * Pipelined form of qc_decide_batch: `submit` enqueues the copies and kernels of one batch on one of
+ * QC_PIPELINE_SLOTS slots (each with its own stream and workspaces) and returns; `wait` blocks until that slot's
+ * outputs are in the caller's buffers.  A caller (the NIF collector) that keeps two batches in flight overlaps the
+ * host->device copy of one with the GPU work of the other; a third keeps an encoder launch queued while the
+ * host turns a finished slot around (the small K2/K3 kernels of a finished batch cannot always co-reside with
+ * the next batch's encoder, which holds 225 KB of shared memory per SM).  Input and output buffers must stay
+ * valid and untouched until `wait` returns.
  */
+#define QC_PIPELINE_SLOTS 4
 int qc_decide_batch_submit(qc_ctx* ctx, int slot, const int32_t* token_ids, const int32_t* lens, int B, int N,
                            int T, const float* thr, int32_t* out_ref_ok, int32_t* out_medoid, float* out_cos);
 int qc_decide_batch_wait(qc_ctx* ctx, int slot);

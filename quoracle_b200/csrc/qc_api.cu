@@ -97,7 +97,7 @@ struct qc_ctx {
   int32_t hang[4] = {};
   // workspaces
   DevBuf part, emb, tok, lens, thr, cosm, refok, medoid, q, rows, idx, stall;
-  Slot slots[2];
+  Slot slots[QC_PIPELINE_SLOTS];
   bool stall_on = false;
   HostBuf h_in, h_out;
   // counters / profiling
@@ -989,7 +989,7 @@ int qc_decide_batch(qc_ctx* c, const int32_t* token_ids, const int32_t* lens, in
 
 int qc_decide_batch_submit(qc_ctx* c, int slot, const int32_t* token_ids, const int32_t* lens, int B, int N, int T,
                            const float* thr, int32_t* out_ref_ok, int32_t* out_medoid, float* out_cos) {
-  if (c == nullptr || slot < 0 || slot > 1 || token_ids == nullptr || lens == nullptr || thr == nullptr || B < 1 || T < 1)
+  if (c == nullptr || slot < 0 || slot >= QC_PIPELINE_SLOTS || token_ids == nullptr || lens == nullptr || thr == nullptr || B < 1 || T < 1)
     return QC_ERR_INVALID_INPUT;
   if (N < 1 || N > QC_MAX_POOL) return QC_ERR_UNSUPPORTED;
   if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
@@ -1061,7 +1061,7 @@ int qc_decide_batch_submit(qc_ctx* c, int slot, const int32_t* token_ids, const 
 }
 
 int qc_decide_batch_wait(qc_ctx* c, int slot) {
-  if (c == nullptr || slot < 0 || slot > 1) return QC_ERR_INVALID_INPUT;
+  if (c == nullptr || slot < 0 || slot >= QC_PIPELINE_SLOTS) return QC_ERR_INVALID_INPUT;
   Slot& sl = c->slots[slot];
   if (!sl.busy) return QC_ERR_INVALID_INPUT;
   DeviceGuard g(c->device);
