@@ -214,23 +214,26 @@ def test_workspace_growth_and_context_reuse():
                     assert np.array_equal(ref.emb, res.emb) and np.array_equal(ref.medoid, res.medoid)
 
 
-def test_pipelined_submit_wait_matches_synchronous_call():
-    """qc_decide_batch_submit/_wait with two batches in flight gives the same verdicts as qc_decide_batch."""
+@pytest.mark.parametrize("depth", [2, 4])
+def test_pipelined_submit_wait_matches_synchronous_call(depth):
+    """qc_decide_batch_submit/_wait with `depth` batches in flight gives the same verdicts as qc_decide_batch."""
     w = weights(768, vocab=32768)
     batches = [synth.make_decisions(32, 8, 384, seed=synth.BASE_SEED + 300 + i, ragged=(i % 2 == 1),
-                                    thresholds=(0.9, 0.995)) for i in range(5)]
+                                    thresholds=(0.9, 0.995)) for i in range(9)]
     with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
         want = [ctx.decide_batch(x.token_ids, x.lens, x.thr, want_cos=True) for x in batches]
         outs = [native.DecideResult(np.empty(32, np.int32), np.empty(32, np.int32), np.empty((32, 8, 8), np.float32), None)
                 for _ in batches]
         for i, x in enumerate(batches):
-            if i >= 2:
-                ctx.decide_batch_wait(i & 1)
-            ctx.decide_batch_submit(i & 1, x.token_ids, x.lens, x.thr, outs[i])
-        ctx.decide_batch_wait(1)
-        ctx.decide_batch_wait(0)
+            if i >= depth:
+                ctx.decide_batch_wait(i % depth)
+            ctx.decide_batch_submit(i % depth, x.token_ids, x.lens, x.thr, outs[i])
+        for i in range(len(batches) - depth, len(batches)):
+            ctx.decide_batch_wait(i % depth)
         for o, wnt in zip(outs, want):
             assert np.array_equal(o.ref_ok, wnt.ref_ok) and np.array_equal(o.medoid, wnt.medoid)
             assert np.array_equal(o.cos, wnt.cos)
+        with pytest.raises(native.QcError):
+            ctx.decide_batch_submit(4, batches[0].token_ids, batches[0].lens, batches[0].thr, outs[0])   # QC_PIPELINE_SLOTS
         with pytest.raises(native.QcError):
             ctx.decide_batch_wait(0)                    # nothing in flight on that slot
