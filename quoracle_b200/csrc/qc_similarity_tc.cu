@@ -2,18 +2,23 @@
 //
 // The Gram matrix X X^T of a decision is GEMM-shaped and, at 2 N^2 D flop per 4 N D bytes, beyond what
 // the fp32 FMA pipe (or the legacy mma.sync path, profiles/sim_sweep_r1.md) sustains against HBM.  Here:
-//   * a tile is 128 consecutive rows of the [B*N x D] embedding matrix = floor(128/N) whole decisions;
-//     TMA streams it in 32-column fp32 chunks (128 rows x 128 B, 128-byte swizzle) through a 4-deep ring;
-//   * four splitter warps turn each raw chunk into a TF32 "hi" tile (low mantissa bits cleared) and a
-//     "lo" tile (x - hi), written with the same swizzled offsets, and publish them to the async proxy;
-//   * one elected lane issues tcgen05.mma kind::tf32, M = 128, N = 256 (B = [hi; lo]), K = 8:
-//     [HH | HL] += H [H; L]^T into one 256-column TMEM accumulator (3xTF32 with the symmetric term taken from the transpose:
-//     G = HH + HL + HL^T, fp32-accurate to ~1e-7 -- the verdict tolerance is 1e-3);
+//   * a tile is 128 consecutive rows of the [B*N x D] embedding matrix = floor(128/N) whole decisions (only
+//     those rows are fetched; the rest of the MMA tile is stale shared memory that reaches discarded
+//     accumulator entries only); TMA streams it in 32-column fp32 chunks (128 B rows, 128-byte swizzle)
+//     through a ring of 4 (pools > 32) or 5 stages, each stage = raw tile + lo tile, adjacent;
+//   * kind::tf32 reads an fp32 operand by ignoring its 13 low mantissa bits, so the landed tile IS the "hi"
+//     operand; four splitter warps write only the exact remainder lo = x - trunc_tf32(x) next to it (same
+//     swizzled offsets) and publish it to the async proxy;
+//   * one elected lane issues tcgen05.mma kind::tf32, M = 128, N = 256 (B = [raw; lo]), K = 8:
+//     [HH | HL] += H [H; L]^T into a 256-column TMEM accumulator, double-buffered (512 columns).
+//     G = HH + (HL + HL^T) is 3xTF32 with the symmetric term taken from the transpose: fp32-accurate
+//     (<= 2e-6 from the f64 oracle even for inputs living in the dropped bits; the tolerance is 1e-3);
 //   * four epilogue warps read the accumulator rows back with tcgen05.ld, keep only the columns of the
 //     row's own decision (the off-diagonal blocks of the 128 x 128 tile pair different decisions and are
-//     discarded), and finish cosine / row mean / reference verdict / medoid vote through shared memory.
-// Arithmetic per 16 KB chunk: 4 MMAs of 128x256x8; the kernel is co-limited by HBM and by shared-memory
-// bandwidth (each MMA reads 8 KB of operands).
+//     discarded), and finish reciprocal norms / cosine / row mean / reference verdict / medoid vote through
+//     shared memory; waiting roles park on mbarrier.try_wait with a suspend-time hint.
+// Per 16 KB chunk: 4 MMAs of 128x256x8 (512 tensor cycles) and 96 KB of shared-memory traffic (TMA 16, splitters
+// 32, MMA operands 48) -- shared-memory bandwidth is what bounds the kernel (profiles/k3_tc_full_r1_summary.md).
 //
 // Cosine and verdict definitions are those of qc_similarity.cu (reference
 // lib/quoracle/actions/consensus_rules.ex:189-210,277-286; medoid: SURVEY.md section 8(a) row A13).
@@ -236,7 +241,7 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
       stall[blockIdx.x * 16 + 13] = t_vote;
     }
   } else if (warp < 4 + kSplitWarps) {
-    // ===================== splitters: raw fp32 chunk -> TF32 hi / lo tiles ====================
+    // ===================== splitters: raw fp32 chunk -> lo tile (the raw tile is the hi operand) =====
     const int p = (threadIdx.x - 128) & 127;                  // position inside the group
     const int grp = (warp - 4) >> 2;
     const long long t_role = clock64();
