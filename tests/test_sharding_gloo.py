@@ -57,3 +57,29 @@ def test_two_rank_gloo(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_token_slices_partition_every_candidate():
+    """Host helper of the T-sharded path: slices tile the token matrix, slice lengths add up to the length."""
+    import numpy as np
+
+    from quoracle_b200 import sharding
+    rng = np.random.default_rng(3)
+    tok = rng.integers(0, 1000, size=(37, 96), dtype=np.int32)
+    lens = rng.integers(0, 97, size=37).astype(np.int32)
+    lens[:3] = (0, 96, 24)
+    for world in (1, 2, 4, 8):
+        parts = sharding.token_slices(tok, lens, world)
+        assert len(parts) == world
+        assert np.array_equal(np.concatenate([p[0] for p in parts], axis=1), tok)
+        assert np.array_equal(sum(p[1].astype(np.int64) for p in parts), lens)
+        tl = 96 // world
+        for p, (ids, ln) in enumerate(parts):
+            assert ids.flags["C_CONTIGUOUS"] and ids.shape == (37, tl) and ln.dtype == np.int32
+            assert np.all((ln >= 0) & (ln <= tl))
+            # a slice is non-empty only if every earlier slice is full
+            if p > 0:
+                assert np.all((ln == 0) | (parts[p - 1][1] == tl))
+    import pytest
+    with pytest.raises(ValueError):
+        sharding.token_slices(tok, lens, 5)
