@@ -246,6 +246,18 @@ int qc_decide_tsplit_dev(qc_ctx* ctx, qc_split* split, const int32_t* d_token_id
                          int T_local, const float* d_thr, int32_t* d_ref_ok, int32_t* d_medoid, float* d_cos,
                          float* d_emb, void* stream);
 
+/*
+ * Ragged batches on the device entry points.  K1 works on token blocks of qc_encoder_token_block(T) tokens; block
+ * (r, j) of candidate r has id r * ceil(T / token_block) + j and is non-empty when j * token_block < len[r].  The host
+ * entry points (which hold the lengths) list the non-empty blocks themselves; a caller of the *_dev entry points can
+ * do the same: upload the ascending ids of the non-empty blocks and pass them here -- the hint applies to the NEXT
+ * encoder launch of this context only (qc_embed_batch_dev / qc_decide_batch_dev / the split entry points) and the
+ * buffer must stay valid until that launch has run.  Without a hint every block is visited and empty ones are
+ * skipped (a CTA pair whose second block is empty then runs half empty).  Results are identical either way.
+ */
+int qc_encoder_token_block(qc_ctx* ctx, int T, int32_t* token_block);
+int qc_encoder_hint_block_map(qc_ctx* ctx, const int32_t* d_block_map, int nslots);
+
 /* Test/tuning hook: K3 kernel for pools of 9..64 candidates. 0 = auto (tcgen05 kind::tf32 kernel when the
  * matrix is TMA-addressable: D % 4 == 0, 16-byte aligned base; the mma.sync kernel otherwise), 1 = always the
  * mma.sync kernel, 2 = tcgen05 only (QC_ERR_UNSUPPORTED when the layout does not allow it). */

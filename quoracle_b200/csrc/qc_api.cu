@@ -71,8 +71,8 @@ struct PendingOut {
 // device workspaces, pinned staging and status words, so two batches can overlap copy and compute.
 struct Slot {
   cudaStream_t stream = nullptr;
-  DevBuf tok, lens, thr, emb, refok, medoid, cosm, part;
-  HostBuf h_in, h_out, h_flags;
+  DevBuf tok, lens, thr, emb, refok, medoid, cosm, part, map;
+  HostBuf h_in, h_out, h_flags, h_map;
   std::vector<PendingOut> pend;
   bool busy = false;
 };
@@ -87,6 +87,11 @@ struct qc_ctx {
   bool has_encoder = false;
   int dim = 0, vocab = 0;
   qc::EncoderVariant variant{0, 0, 0, 0};
+  // compacted block list of the NEXT encode_dev call (set by the host entry points, consumed once)
+  const int32_t* hint_map = nullptr;
+  int hint_nslots = 0;
+  DevBuf map;
+  HostBuf h_map;
   int sim_path = 0;              // K3 for pools 9..64: 0 auto (tcgen05 when the layout allows), 1 mma.sync, 2 tcgen05
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved once at create
   bool variant_forced = false;   // set by qc_encoder_set_variant / _set_cta_group; else chosen per call from T
@@ -263,6 +268,43 @@ int d2h(qc_ctx* c, void* user, const void* dsrc, size_t bytes, size_t* stage_off
 
 size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
 
+// Ragged batches: the host entry points hold the lengths, so they list the non-empty token blocks
+// (cand * bpc + j, in order) and K1 walks that list instead of skipping: no CTA pair runs half empty.  Batches
+// without an empty block need no list (dense enumeration is the same walk).  The list rides to the device on
+// the call's own stream through a pinned staging buffer that stays untouched until the call is waited for.
+int stage_block_map(qc_ctx* c, const int32_t* lens, int R, int T, DevBuf* dmap, HostBuf* hmap, cudaStream_t s) {
+  c->hint_map = nullptr;
+  c->hint_nslots = 0;
+  if (!c->variant_forced) c->variant = qc::encoder_auto_variant(c->dim, T);
+  const int TB = c->variant.token_block;
+  const int bpc = (T + TB - 1) / TB;
+  long long used = 0;
+  for (int r = 0; r < R; ++r) used += (lens[r] + TB - 1) / TB;
+  if (used == static_cast<long long>(R) * bpc || used > 0x7fffffffLL) return QC_OK;
+  QC_CUDA(hmap->ensure(static_cast<size_t>(used > 0 ? used : 1) * sizeof(int32_t)));
+  QC_CUDA(dmap->ensure(static_cast<size_t>(used > 0 ? used : 1) * sizeof(int32_t)));
+  int32_t* h = static_cast<int32_t*>(hmap->p);
+  size_t k = 0;
+  for (int r = 0; r < R; ++r) {
+    const int nb = (lens[r] + TB - 1) / TB;
+    for (int j = 0; j < nb; ++j) h[k++] = r * bpc + j;
+  }
+  if (used > 0) QC_CUDA(cudaMemcpyAsync(dmap->p, h, static_cast<size_t>(used) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  c->hint_map = static_cast<const int32_t*>(dmap->p);
+  c->hint_nslots = static_cast<int>(used);
+  return QC_OK;
+}
+
+// Drops an unconsumed hint when a host entry point leaves early, so it can never leak into a later call.
+struct HintGuard {
+  qc_ctx* c;
+  explicit HintGuard(qc_ctx* c_) : c(c_) {}
+  ~HintGuard() {
+    c->hint_map = nullptr;
+    c->hint_nslots = 0;
+  }
+};
+
 int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, int T, float* d_emb, cudaStream_t s,
                DevBuf* part_buf = nullptr, const qc::FinalizeDst* scatter = nullptr,
                const qc::TsplitDst* tsplit = nullptr) {
@@ -273,7 +315,11 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
   QC_CUDA(part.ensure(static_cast<size_t>(R) * bpc * c->dim * sizeof(float)));
   {
     KernelScope ks(c, QC_K_ENCODE, s);
-    qc::EncoderLaunch a;
+    qc::EncoderLaunch a{};
+    a.block_map = c->hint_map;
+    a.nslots = c->hint_nslots;
+    c->hint_map = nullptr;
+    c->hint_nslots = 0;
     a.w_tmap64 = &c->w_tmap64;
     a.w_tmap32 = &c->w_tmap32;
     a.e_tmap = &c->e_tmap;
@@ -444,10 +490,12 @@ void qc_ctx_destroy(qc_ctx* c) {
   c->rows.release();
   c->idx.release();
   c->stall.release();
+  c->map.release();
+  c->h_map.release();
   for (Slot& sl : c->slots) {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
     sl.tok.release(); sl.lens.release(); sl.thr.release(); sl.emb.release(); sl.refok.release(); sl.medoid.release();
-    sl.cosm.release(); sl.part.release(); sl.h_in.release(); sl.h_out.release(); sl.h_flags.release();
+    sl.cosm.release(); sl.part.release(); sl.h_in.release(); sl.h_out.release(); sl.h_flags.release(); sl.map.release(); sl.h_map.release();
     if (sl.stream) cudaStreamDestroy(sl.stream);
   }
   c->h_in.release();
@@ -630,6 +678,21 @@ int qc_similarity_batch_dev(qc_ctx* c, const float* d_emb, int B, int N, int D, 
   return QC_OK;
 }
 
+int qc_encoder_hint_block_map(qc_ctx* c, const int32_t* d_block_map, int nslots) {
+  if (c == nullptr || nslots < 0 || (d_block_map == nullptr && nslots != 0)) return QC_ERR_INVALID_INPUT;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  c->hint_map = d_block_map;
+  c->hint_nslots = d_block_map ? nslots : 0;
+  return QC_OK;
+}
+
+int qc_encoder_token_block(qc_ctx* c, int T, int32_t* token_block) {
+  if (c == nullptr || token_block == nullptr || T < 1) return QC_ERR_INVALID_INPUT;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  *token_block = (c->variant_forced ? c->variant : qc::encoder_auto_variant(c->dim, T)).token_block;
+  return QC_OK;
+}
+
 int qc_similarity_set_path(qc_ctx* c, int path) {
   if (c == nullptr || path < 0 || path > 2) return QC_ERR_INVALID_INPUT;
   c->sim_path = path;
@@ -680,6 +743,8 @@ int qc_embed_batch(qc_ctx* c, const int32_t* token_ids, const int32_t* lens, int
   int st;
   if ((st = h2d(c, c->tok.p, token_ids, tokb, &off)) != QC_OK) return st;
   if ((st = h2d(c, c->lens.p, lens, lenb, &off)) != QC_OK) return st;
+  HintGuard hg(c);
+  if ((st = stage_block_map(c, lens, R, T, &c->map, &c->h_map, c->stream)) != QC_OK) return st;
   st = encode_dev(c, static_cast<int32_t*>(c->tok.p), static_cast<int32_t*>(c->lens.p), R, T,
                   static_cast<float*>(c->emb.p), c->stream);
   if (st != QC_OK) return st;
@@ -971,6 +1036,8 @@ int qc_decide_batch(qc_ctx* c, const int32_t* token_ids, const int32_t* lens, in
   if ((st = h2d(c, c->tok.p, token_ids, tokb, &off)) != QC_OK) return st;
   if ((st = h2d(c, c->lens.p, lens, lenb, &off)) != QC_OK) return st;
   if ((st = h2d(c, c->thr.p, thr, thrb, &off)) != QC_OK) return st;
+  HintGuard hg(c);
+  if ((st = stage_block_map(c, lens, R, T, &c->map, &c->h_map, c->stream)) != QC_OK) return st;
   st = qc_decide_batch_dev(c, static_cast<int32_t*>(c->tok.p), static_cast<int32_t*>(c->lens.p), B, N, T,
                            static_cast<float*>(c->thr.p), static_cast<int32_t*>(c->refok.p),
                            static_cast<int32_t*>(c->medoid.p), out_cos ? static_cast<float*>(c->cosm.p) : nullptr,
@@ -1031,6 +1098,8 @@ int qc_decide_batch_submit(qc_ctx* c, int slot, const int32_t* token_ids, const 
   if ((st = in(sl.tok.p, token_ids, tokb)) != QC_OK) return st;
   if ((st = in(sl.lens.p, lens, lenb)) != QC_OK) return st;
   if ((st = in(sl.thr.p, thr, thrb)) != QC_OK) return st;
+  HintGuard hg(c);
+  if ((st = stage_block_map(c, lens, R, T, &sl.map, &sl.h_map, sl.stream)) != QC_OK) return st;
   st = encode_dev(c, static_cast<int32_t*>(sl.tok.p), static_cast<int32_t*>(sl.lens.p), R, T,
                   static_cast<float*>(sl.emb.p), sl.stream, &sl.part);
   if (st != QC_OK) return st;

@@ -24,6 +24,8 @@ struct EncoderLaunch {
   float* part;                 // device [R x ceil(T/TB) x dim]
   int32_t* err_flag;           // device int32[8]: [0..3] watchdog record, [4] token-range flag
   unsigned long long* stall;   // device [grid x 16] per-role stall cycles, or nullptr
+  const int32_t* block_map;    // device: ids of the non-empty token blocks (cand * bpc + j), or nullptr = dense
+  int nslots;                  // entries in block_map
   int R, T, dim, vocab, num_sms;
   EncoderVariant variant;
   cudaStream_t stream;

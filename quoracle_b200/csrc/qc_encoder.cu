@@ -90,6 +90,15 @@ __device__ __forceinline__ int block_valid(const int32_t* __restrict__ lens, int
   return v > TB ? TB : v;
 }
 
+// Work slot -> token block.  Dense mode (map == nullptr): slot == block, blocks past a candidate's length are
+// skipped by every role.  Compacted mode: `map` lists the non-empty blocks (built by the host entry points from
+// the lengths they already hold), so no CTA pair runs half empty and no item is skipped -- ragged batches then
+// cost what their non-empty blocks cost.  A slot past the end maps to block `nblocks`, which block_valid() rejects.
+__device__ __forceinline__ int slot_block(const int32_t* __restrict__ map, int slot, int nslots, int nblocks) {
+  if (slot >= nslots) return nblocks;
+  return map != nullptr ? map[slot] : slot;
+}
+
 // Sum of GELU over NCOL consecutive TMEM columns of this thread's lane, software-pipelined:
 // the next 32-column load is in flight while the current one is consumed.
 template <int NCOL>
@@ -136,7 +145,8 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
                  float* __restrict__ part,                             // [R x bpc x D]
                  int32_t* __restrict__ dbg,                            // [0..3] watchdog, [4] token-range flag
                  unsigned long long* __restrict__ stall,               // optional [grid x 16] per-role stall cycles
-                 int R, int T, int bpc, int vocab) {
+                 const int32_t* __restrict__ block_map,                // optional compacted block list [nslots]
+                 int nslots, int R, int T, int bpc, int vocab) {
   constexpr int D = Tr::D, TB = Tr::TB, CG = Tr::CG, KB = Tr::KB, NFT = Tr::NFT, WBK = Tr::WBK, NWS = Tr::NWS;
   constexpr int UMMA_N = Tr::UMMA_N, WS = Tr::W_STAGES, ACC_COLS = Tr::ACC_COLS;
 
@@ -160,7 +170,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
   const int group = blockIdx.x / CG;                           // CTA (pair) index
   const int ngroups = gridDim.x / CG;
   const int nblocks = R * bpc;
-  const int nitems = (nblocks + CG - 1) / CG;                  // work items: CG blocks each
+  const int nitems = (nslots + CG - 1) / CG;                   // work items: CG slots (blocks) each
 
   // ---- one-time setup -----------------------------------------------------------------
   if (warp == 8 && lane == 0) {
@@ -202,7 +212,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
       bool any = false;
 #pragma unroll
       for (int s = 0; s < CG; ++s) {
-        valid[s] = block_valid(lens, item * CG + s, nblocks, bpc, TB);
+        valid[s] = block_valid(lens, slot_block(block_map, item * CG + s, nslots, nblocks), nblocks, bpc, TB);
         any |= valid[s] > 0;
       }
       if (!any) continue;
@@ -222,7 +232,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
 #pragma unroll
         for (int s = 0; s < CG; ++s) {
           if (valid[s] > 0) {
-            const size_t blk = static_cast<size_t>(item) * CG + s;
+            const size_t blk = static_cast<size_t>(slot_block(block_map, item * CG + s, nslots, nblocks));
             part[blk * D + ft * Tr::MT + rank * 128 + row] = sums[s];
           }
         }
@@ -247,9 +257,9 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
       for (int item = group; item < nitems; item += ngroups) {
         bool any = false;
 #pragma unroll
-        for (int s = 0; s < CG; ++s) any |= block_valid(lens, item * CG + s, nblocks, bpc, TB) > 0;
+        for (int s = 0; s < CG; ++s) any |= block_valid(lens, slot_block(block_map, item * CG + s, nslots, nblocks), nblocks, bpc, TB) > 0;
         if (!any) continue;
-        const int blk = item * CG + static_cast<int>(rank);
+        const int blk = slot_block(block_map, item * CG + static_cast<int>(rank), nslots, nblocks);
         const int valid = block_valid(lens, blk, nblocks, bpc, TB);
         const int cand = blk < nblocks ? blk / bpc : 0;
         const int j = blk < nblocks ? blk - cand * bpc : 0;
@@ -299,9 +309,9 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
     for (int item = group; item < nitems; item += ngroups) {
       bool any = false;
 #pragma unroll
-      for (int s = 0; s < CG; ++s) any |= block_valid(lens, item * CG + s, nblocks, bpc, TB) > 0;
+      for (int s = 0; s < CG; ++s) any |= block_valid(lens, slot_block(block_map, item * CG + s, nslots, nblocks), nblocks, bpc, TB) > 0;
       if (!any) continue;
-      const int blk = item * CG + static_cast<int>(rank);
+      const int blk = slot_block(block_map, item * CG + static_cast<int>(rank), nslots, nblocks);
       const int valid = block_valid(lens, blk, nblocks, bpc, TB);
       const int cand = blk < nblocks ? blk / bpc : 0;
       const int j = blk < nblocks ? blk - cand * bpc : 0;
@@ -390,7 +400,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
       for (int item = group; item < nitems; item += ngroups) {
         bool any = false;
 #pragma unroll
-        for (int s = 0; s < CG; ++s) any |= block_valid(lens, item * CG + s, nblocks, bpc, TB) > 0;
+        for (int s = 0; s < CG; ++s) any |= block_valid(lens, slot_block(block_map, item * CG + s, nslots, nblocks), nblocks, bpc, TB) > 0;
         if (!__any_sync(0xffffffffu, any)) continue;
         for (int ft = 0; ft < NFT; ++ft) {
           for (int ws = 0; ws < NWS; ++ws, ++wi) {
@@ -434,7 +444,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
       for (int item = group; item < nitems; item += ngroups) {
         bool any = false;
 #pragma unroll
-        for (int s = 0; s < CG; ++s) any |= block_valid(lens, item * CG + s, nblocks, bpc, TB) > 0;
+        for (int s = 0; s < CG; ++s) any |= block_valid(lens, slot_block(block_map, item * CG + s, nslots, nblocks), nblocks, bpc, TB) > 0;
         if (!__any_sync(0xffffffffu, any)) continue;
         for (int ft = 0; ft < NFT; ++ft, ++acc_iter) {
           const uint32_t as = acc_iter & 1u;
@@ -508,7 +518,12 @@ static cudaError_t launch_encode_t(const EncoderLaunch& a) {
   const int bpc = (a.T + Tr::TB - 1) / Tr::TB;
   int grid = a.num_sms;
   if (Tr::CG == 2) grid &= ~1;
-  const long long nitems = (static_cast<long long>(a.R) * bpc + Tr::CG - 1) / Tr::CG;
+  const long long nblocks = static_cast<long long>(a.R) * bpc;
+  if (nblocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+  const int nslots = a.block_map != nullptr ? a.nslots : static_cast<int>(nblocks);
+  if (nslots < 0 || nslots > nblocks) return cudaErrorInvalidValue;
+  if (nslots == 0) return cudaSuccess;                         // every candidate is empty: K2 writes zero rows
+  const long long nitems = (static_cast<long long>(nslots) + Tr::CG - 1) / Tr::CG;
   if (nitems * Tr::CG < grid) grid = static_cast<int>(nitems * Tr::CG);
   if (grid < Tr::CG) grid = Tr::CG;
 
@@ -525,8 +540,8 @@ static cudaError_t launch_encode_t(const EncoderLaunch& a) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const CUtensorMap* tm = Tr::WBK == 64 ? a.w_tmap64 : a.w_tmap32;
-  return cudaLaunchKernelEx(&cfg, kern, *tm, *a.e_tmap, a.table, a.token_ids, a.lens, a.part, a.err_flag, a.stall, a.R, a.T, bpc,
-                            a.vocab);
+  return cudaLaunchKernelEx(&cfg, kern, *tm, *a.e_tmap, a.table, a.token_ids, a.lens, a.part, a.err_flag, a.stall,
+                            a.block_map, nslots, a.R, a.T, bpc, a.vocab);
 }
 
 // The instantiated variants.  {dim, token block, cta group, W stage width, gather mode}

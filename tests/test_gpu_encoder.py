@@ -237,3 +237,40 @@ def test_pipelined_submit_wait_matches_synchronous_call(depth):
             ctx.decide_batch_submit(4, batches[0].token_ids, batches[0].lens, batches[0].thr, outs[0])   # QC_PIPELINE_SLOTS
         with pytest.raises(native.QcError):
             ctx.decide_batch_wait(0)                    # nothing in flight on that slot
+
+
+@pytest.mark.parametrize("dim,t", [(768, 512), (384, 300), (1536, 200)])
+def test_compacted_block_list_equals_dense_walk(dim, t):
+    """Host entry points list the non-empty token blocks of a ragged batch (no half-empty CTA pair); the device
+    entry points walk every block and skip.  Same blocks, same K2 -> identical bits.  Includes empty candidates,
+    candidates of one token, and a batch in which every candidate is empty."""
+    import torch
+    w = weights(dim, vocab=8192)
+    rng = np.random.default_rng(dim + t)
+    b, n = 24, 8
+    batch = synth.make_decisions(b, n, t, vocab=8192, seed=synth.BASE_SEED + dim, ragged=True)
+    lens = batch.lens.copy()
+    lens.reshape(-1)[::5] = rng.integers(0, 3, size=lens.reshape(-1)[::5].shape)     # empty and tiny candidates
+    lens.reshape(-1)[1::11] = t
+    tok = batch.token_ids.copy()
+    tok[np.arange(t)[None, None, :] >= lens[:, :, None]] = -1
+    with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+        host = ctx.decide_batch(tok, lens, batch.thr, want_cos=True, want_emb=True)          # compacted walk
+        dev = torch.device("cuda:0")
+        d_tok, d_len = torch.from_numpy(tok).to(dev), torch.from_numpy(lens).to(dev)
+        d_emb = torch.empty((b * n, dim), dtype=torch.float32, device=dev)
+        ctx.embed_batch_dev(d_tok.data_ptr(), d_len.data_ptr(), b * n, t, d_emb.data_ptr())  # dense walk
+        ctx.synchronize()
+        ctx.check_status()
+        assert np.array_equal(host.emb.reshape(b * n, dim), d_emb.cpu().numpy())
+        want = oenc.encode(w.table_bf16, w.w_bf16, tok.reshape(b * n, t), lens.reshape(-1))
+        assert np.max(np.abs(host.emb.reshape(b * n, dim) - want)) < EMB_TOL
+        assert np.all(host.emb.reshape(b * n, dim)[lens.reshape(-1) == 0] == 0.0)
+        # pipelined host path takes the same route
+        out = native.DecideResult(np.empty(b, np.int32), np.empty(b, np.int32), np.empty((b, n, n), np.float32), None)
+        ctx.decide_batch_submit(2, tok, lens, batch.thr, out)
+        ctx.decide_batch_wait(2)
+        assert np.array_equal(out.cos, host.cos) and np.array_equal(out.medoid, host.medoid)
+        # nothing to encode at all
+        zero = ctx.decide_batch(tok, np.zeros_like(lens), batch.thr, want_cos=True, want_emb=True)
+        assert np.all(zero.emb == 0.0) and np.all(zero.cos == 0.0) and np.all(zero.ref_ok == 0)

@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--variants", default="")
+    ap.add_argument("--ragged", action="store_true", help="len ~ U[T/2, T] (flops counted on valid tokens only)")
     args = ap.parse_args()
     import torch
     dev = torch.device("cuda:0")
@@ -35,12 +36,12 @@ def main():
     w = synth.make_encoder(args.dim, seed=synth.BASE_SEED + 2)
     ctx = native.Context(0, w.table_bf16, w.w_bf16)
     nb = 8
-    batches = [synth.make_decisions(b, n, t, seed=synth.BASE_SEED + 50 + i) for i in range(nb)]
+    batches = [synth.make_decisions(b, n, t, seed=synth.BASE_SEED + 50 + i, ragged=args.ragged) for i in range(nb)]
     d_tok = [torch.from_numpy(x.token_ids).to(dev) for x in batches]
     d_len = [torch.from_numpy(x.lens).to(dev) for x in batches]
     d_emb = torch.empty((b * n, args.dim), dtype=torch.float32, device=dev)
     stream = torch.cuda.Stream(device=dev)
-    flops = 2.0 * b * n * t * args.dim * args.dim
+    flops = 2.0 * float(np.mean([x.lens.sum() for x in batches])) * args.dim * args.dim   # valid tokens only
     ref = None
     print(f"dim={args.dim} B={b} N={n} T={t}  flops/launch={flops:.3e}")
     for (tb, cg, wbk, gm) in variants:
