@@ -23,12 +23,14 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--cpu", action="store_true", help="also time the oracle C port (single thread) on a sample")
     ap.add_argument("--pools", default="2,4,8,16,32,64")
+    ap.add_argument("--sim-path", type=int, default=0, help="qc_similarity_set_path (0 auto, 1 mma.sync, 2 tcgen05, 3 tcgen05 A-from-TMEM)")
     args = ap.parse_args()
     import torch
     dev = torch.device("cuda:0")
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     hbm = peaks.get("hbm_gbs", 6650.0)
     ctx = native.Context(0)
+    ctx.set_similarity_path(args.sim_path)
     stream = torch.cuda.Stream(device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     pools = [int(x) for x in args.pools.split(",")]
