@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--cpu", action="store_true", help="also time the oracle C port (single thread) on a sample")
     ap.add_argument("--pools", default="2,4,8,16,32,64")
-    ap.add_argument("--sim-path", type=int, default=0, help="qc_similarity_set_path (0 auto, 1 mma.sync, 2 tcgen05, 3 tcgen05 A-from-TMEM)")
+    ap.add_argument("--sim-path", type=int, default=0, help="qc_similarity_set_path (0 auto, 1 mma.sync, 2 tcgen05)")
     args = ap.parse_args()
     import torch
     dev = torch.device("cuda:0")
