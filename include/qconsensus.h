@@ -256,6 +256,14 @@ int qc_decide_tsplit_dev(qc_ctx* ctx, qc_split* split, const int32_t* d_token_id
  * skipped (a CTA pair whose second block is empty then runs half empty).  Results are identical either way.
  */
 int qc_encoder_token_block(qc_ctx* ctx, int T, int32_t* token_block);
+/*
+ * Ragged batches on the host entry points (qc_decide_batch, qc_decide_batch_submit, qc_embed_batch): when it saves
+ * at least 5 % of the token blocks the valid tokens are packed into a stream of 32-slot chunks (four per 128-token
+ * block, each chunk owned by one candidate), K1 runs on the packed stream and K2 adds a candidate's chunk sums.
+ * Same arithmetic as the unpacked walk up to fp32 summation order (|delta| ~ 1e-8 on unit rows).
+ * mode 0 = auto (default), 1 = never pack, 2 = pack whenever the tiling allows (token block a multiple of 32).
+ */
+int qc_encoder_set_packing(qc_ctx* ctx, int mode);
 int qc_encoder_hint_block_map(qc_ctx* ctx, const int32_t* d_block_map, int nslots);
 
 /* Test/tuning hook: K3 kernel for pools of 9..64 candidates. 0 = auto (tcgen05 kind::tf32 kernel when the

@@ -71,7 +71,7 @@ struct PendingOut {
 // device workspaces, pinned staging and status words, so two batches can overlap copy and compute.
 struct Slot {
   cudaStream_t stream = nullptr;
-  DevBuf tok, lens, thr, emb, refok, medoid, cosm, part, map;
+  DevBuf tok, lens, thr, emb, refok, medoid, cosm, part, map, packed;
   HostBuf h_in, h_out, h_flags, h_map;
   std::vector<PendingOut> pend;
   bool busy = false;
@@ -90,8 +90,15 @@ struct qc_ctx {
   // compacted block list of the NEXT encode_dev call (set by the host entry points, consumed once)
   const int32_t* hint_map = nullptr;
   int hint_nslots = 0;
-  DevBuf map;
+  DevBuf map, packed;
   HostBuf h_map;
+  // packed token stream of the NEXT encode_dev call (ragged batches; same life cycle as hint_map)
+  const int32_t* hint_chunk_src = nullptr;
+  const int32_t* hint_chunk_n = nullptr;
+  const int32_t* hint_row_start = nullptr;
+  int hint_nchunks = 0;
+  DevBuf* hint_packed_buf = nullptr;
+  int packing = 0;               // 0 auto, 1 never, 2 whenever the tiling allows (test hook)
   int sim_path = 0;              // K3 for pools 9..64: 0 auto (tcgen05 when the layout allows), 1 mma.sync, 2 tcgen05
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved once at create
   bool variant_forced = false;   // set by qc_encoder_set_variant / _set_cta_group; else chosen per call from T
@@ -272,14 +279,59 @@ size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
 // (cand * bpc + j, in order) and K1 walks that list instead of skipping: no CTA pair runs half empty.  Batches
 // without an empty block need no list (dense enumeration is the same walk).  The list rides to the device on
 // the call's own stream through a pinned staging buffer that stays untouched until the call is waited for.
-int stage_block_map(qc_ctx* c, const int32_t* lens, int R, int T, DevBuf* dmap, HostBuf* hmap, cudaStream_t s) {
+int stage_block_map(qc_ctx* c, const int32_t* lens, int R, int T, DevBuf* dmap, HostBuf* hmap, DevBuf* dpacked,
+                    cudaStream_t s) {
   c->hint_map = nullptr;
   c->hint_nslots = 0;
+  c->hint_chunk_src = nullptr;
+  c->hint_nchunks = 0;
   if (!c->variant_forced) c->variant = qc::encoder_auto_variant(c->dim, T);
   const int TB = c->variant.token_block;
   const int bpc = (T + TB - 1) / TB;
-  long long used = 0;
-  for (int r = 0; r < R; ++r) used += (lens[r] + TB - 1) / TB;
+  long long used = 0, chunks = 0;
+  for (int r = 0; r < R; ++r) {
+    used += (lens[r] + TB - 1) / TB;
+    chunks += (lens[r] + 31) / 32;
+  }
+  // Packed token stream: every candidate is cut into 32-token chunks and the chunks of all candidates are laid
+  // end to end, four (TB / 32) to a block, so the only padding left is inside each candidate's last chunk.
+  // Worth its two extra small kernels when it saves at least 5 % of the blocks.
+  const bool can_pack = (TB % 32) == 0 && static_cast<long long>(R) * T < 0x7fffffffLL && c->packing != 1;
+  if (can_pack && chunks > 0) {
+    const int nch = TB / 32;
+    const long long pblocks = (chunks + nch - 1) / nch;
+    if (c->packing == 2 || pblocks * 100 <= used * 95) {
+      const long long nchunks = pblocks * nch;
+      const size_t ints = static_cast<size_t>(2 * nchunks + R + 1);
+      QC_CUDA(hmap->ensure(ints * sizeof(int32_t)));
+      QC_CUDA(dmap->ensure(ints * sizeof(int32_t)));
+      int32_t* src = static_cast<int32_t*>(hmap->p);
+      int32_t* cnt = src + nchunks;
+      int32_t* row = cnt + nchunks;
+      long long k = 0;
+      for (int r = 0; r < R; ++r) {
+        row[r] = static_cast<int32_t>(k);
+        for (int o = 0; o < lens[r]; o += 32) {
+          src[k] = static_cast<int32_t>(static_cast<long long>(r) * T + o);
+          cnt[k] = lens[r] - o < 32 ? lens[r] - o : 32;
+          ++k;
+        }
+      }
+      row[R] = static_cast<int32_t>(k);
+      for (; k < nchunks; ++k) {
+        src[k] = 0;
+        cnt[k] = 0;
+      }
+      QC_CUDA(cudaMemcpyAsync(dmap->p, src, ints * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+      const int32_t* d = static_cast<const int32_t*>(dmap->p);
+      c->hint_chunk_src = d;
+      c->hint_chunk_n = d + nchunks;
+      c->hint_row_start = d + 2 * nchunks;
+      c->hint_nchunks = static_cast<int>(nchunks);
+      c->hint_packed_buf = dpacked;
+      return QC_OK;
+    }
+  }
   if (used == static_cast<long long>(R) * bpc || used > 0x7fffffffLL) return QC_OK;
   QC_CUDA(hmap->ensure(static_cast<size_t>(used > 0 ? used : 1) * sizeof(int32_t)));
   QC_CUDA(dmap->ensure(static_cast<size_t>(used > 0 ? used : 1) * sizeof(int32_t)));
@@ -302,6 +354,8 @@ struct HintGuard {
   ~HintGuard() {
     c->hint_map = nullptr;
     c->hint_nslots = 0;
+    c->hint_chunk_src = nullptr;
+    c->hint_nchunks = 0;
   }
 };
 
@@ -312,25 +366,52 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
   if (!c->variant_forced) c->variant = qc::encoder_auto_variant(c->dim, T);
   const int TB = c->variant.token_block;
   const int bpc = (T + TB - 1) / TB;
-  QC_CUDA(part.ensure(static_cast<size_t>(R) * bpc * c->dim * sizeof(float)));
+  // one-shot hints of the host entry points (ragged batches)
+  const int32_t* map = c->hint_map;
+  const int nslots = c->hint_nslots;
+  const int32_t* chunk_src = c->hint_chunk_src;
+  const int32_t* chunk_n = c->hint_chunk_n;
+  const int32_t* row_start = c->hint_row_start;
+  const int nchunks = c->hint_nchunks;
+  DevBuf* packed = c->hint_packed_buf;
+  c->hint_map = nullptr;
+  c->hint_nslots = 0;
+  c->hint_chunk_src = nullptr;
+  c->hint_nchunks = 0;
+  const bool pack = chunk_src != nullptr && nchunks > 0 && tsplit == nullptr && (TB % 32) == 0 && packed != nullptr;
+  if (pack) {
+    // token ids -> stream of 32-slot chunks; K1 sees nchunks / (TB/32) full blocks and writes one partial row per chunk
+    QC_CUDA(packed->ensure(static_cast<size_t>(nchunks) * 32 * sizeof(int32_t)));
+    QC_CUDA(part.ensure(static_cast<size_t>(nchunks) * c->dim * sizeof(float)));
+    c->launches++;
+    QC_CUDA(qc::launch_pack_tokens(d_tok, chunk_src, chunk_n, static_cast<int32_t*>(packed->p), nchunks, s));
+  } else {
+    QC_CUDA(part.ensure(static_cast<size_t>(R) * bpc * c->dim * sizeof(float)));
+  }
   {
     KernelScope ks(c, QC_K_ENCODE, s);
     qc::EncoderLaunch a{};
-    a.block_map = c->hint_map;
-    a.nslots = c->hint_nslots;
-    c->hint_map = nullptr;
-    c->hint_nslots = 0;
     a.w_tmap64 = &c->w_tmap64;
     a.w_tmap32 = &c->w_tmap32;
     a.e_tmap = &c->e_tmap;
     a.table = c->d_table;
-    a.token_ids = d_tok;
-    a.lens = d_lens;
+    if (pack) {
+      a.token_ids = static_cast<const int32_t*>(packed->p);
+      a.lens = nullptr;                          // every block of the packed stream is full
+      a.R = nchunks / (TB / 32);
+      a.T = TB;
+      a.chunked = 1;
+    } else {
+      a.token_ids = d_tok;
+      a.lens = d_lens;
+      a.R = R;
+      a.T = T;
+      a.block_map = map;
+      a.nslots = nslots;
+    }
     a.part = static_cast<float*>(part.p);
     a.err_flag = c->d_err;
     a.stall = c->stall_on ? static_cast<unsigned long long*>(c->stall.p) : nullptr;
-    a.R = R;
-    a.T = T;
     a.dim = c->dim;
     a.vocab = c->vocab;
     a.variant = c->variant;
@@ -345,7 +426,7 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
       return QC_OK;
     }
     QC_CUDA(qc::launch_finalize(static_cast<const float*>(part.p), d_lens, scatter ? *scatter : qc::finalize_plain(d_emb),
-                                R, bpc, TB, c->dim, s));
+                                pack ? row_start : nullptr, R, bpc, TB, c->dim, s));
   }
   return QC_OK;
 }
@@ -491,11 +572,12 @@ void qc_ctx_destroy(qc_ctx* c) {
   c->idx.release();
   c->stall.release();
   c->map.release();
+  c->packed.release();
   c->h_map.release();
   for (Slot& sl : c->slots) {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
     sl.tok.release(); sl.lens.release(); sl.thr.release(); sl.emb.release(); sl.refok.release(); sl.medoid.release();
-    sl.cosm.release(); sl.part.release(); sl.h_in.release(); sl.h_out.release(); sl.h_flags.release(); sl.map.release(); sl.h_map.release();
+    sl.cosm.release(); sl.part.release(); sl.h_in.release(); sl.h_out.release(); sl.h_flags.release(); sl.map.release(); sl.h_map.release(); sl.packed.release();
     if (sl.stream) cudaStreamDestroy(sl.stream);
   }
   c->h_in.release();
@@ -678,6 +760,12 @@ int qc_similarity_batch_dev(qc_ctx* c, const float* d_emb, int B, int N, int D, 
   return QC_OK;
 }
 
+int qc_encoder_set_packing(qc_ctx* c, int mode) {
+  if (c == nullptr || mode < 0 || mode > 2) return QC_ERR_INVALID_INPUT;
+  c->packing = mode;
+  return QC_OK;
+}
+
 int qc_encoder_hint_block_map(qc_ctx* c, const int32_t* d_block_map, int nslots) {
   if (c == nullptr || nslots < 0 || (d_block_map == nullptr && nslots != 0)) return QC_ERR_INVALID_INPUT;
   if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
@@ -744,7 +832,7 @@ int qc_embed_batch(qc_ctx* c, const int32_t* token_ids, const int32_t* lens, int
   if ((st = h2d(c, c->tok.p, token_ids, tokb, &off)) != QC_OK) return st;
   if ((st = h2d(c, c->lens.p, lens, lenb, &off)) != QC_OK) return st;
   HintGuard hg(c);
-  if ((st = stage_block_map(c, lens, R, T, &c->map, &c->h_map, c->stream)) != QC_OK) return st;
+  if ((st = stage_block_map(c, lens, R, T, &c->map, &c->h_map, &c->packed, c->stream)) != QC_OK) return st;
   st = encode_dev(c, static_cast<int32_t*>(c->tok.p), static_cast<int32_t*>(c->lens.p), R, T,
                   static_cast<float*>(c->emb.p), c->stream);
   if (st != QC_OK) return st;
@@ -1037,7 +1125,7 @@ int qc_decide_batch(qc_ctx* c, const int32_t* token_ids, const int32_t* lens, in
   if ((st = h2d(c, c->lens.p, lens, lenb, &off)) != QC_OK) return st;
   if ((st = h2d(c, c->thr.p, thr, thrb, &off)) != QC_OK) return st;
   HintGuard hg(c);
-  if ((st = stage_block_map(c, lens, R, T, &c->map, &c->h_map, c->stream)) != QC_OK) return st;
+  if ((st = stage_block_map(c, lens, R, T, &c->map, &c->h_map, &c->packed, c->stream)) != QC_OK) return st;
   st = qc_decide_batch_dev(c, static_cast<int32_t*>(c->tok.p), static_cast<int32_t*>(c->lens.p), B, N, T,
                            static_cast<float*>(c->thr.p), static_cast<int32_t*>(c->refok.p),
                            static_cast<int32_t*>(c->medoid.p), out_cos ? static_cast<float*>(c->cosm.p) : nullptr,
@@ -1099,7 +1187,7 @@ int qc_decide_batch_submit(qc_ctx* c, int slot, const int32_t* token_ids, const 
   if ((st = in(sl.lens.p, lens, lenb)) != QC_OK) return st;
   if ((st = in(sl.thr.p, thr, thrb)) != QC_OK) return st;
   HintGuard hg(c);
-  if ((st = stage_block_map(c, lens, R, T, &sl.map, &sl.h_map, sl.stream)) != QC_OK) return st;
+  if ((st = stage_block_map(c, lens, R, T, &sl.map, &sl.h_map, &sl.packed, sl.stream)) != QC_OK) return st;
   st = encode_dev(c, static_cast<int32_t*>(sl.tok.p), static_cast<int32_t*>(sl.lens.p), R, T,
                   static_cast<float*>(sl.emb.p), sl.stream, &sl.part);
   if (st != QC_OK) return st;

@@ -20,12 +20,13 @@ struct EncoderLaunch {
   const CUtensorMap* e_tmap;   // E [vocab x dim], box 64 x 1, 128-byte swizzle (gather4)
   const uint16_t* table;       // device, bf16 [vocab x dim]
   const int32_t* token_ids;    // device [R x T]
-  const int32_t* lens;         // device [R]
+  const int32_t* lens;         // device [R]; nullptr = every block full (packed token stream)
   float* part;                 // device [R x ceil(T/TB) x dim]
   int32_t* err_flag;           // device int32[8]: [0..3] watchdog record, [4] token-range flag
   unsigned long long* stall;   // device [grid x 16] per-role stall cycles, or nullptr
   const int32_t* block_map;    // device: ids of the non-empty token blocks (cand * bpc + j), or nullptr = dense
   int nslots;                  // entries in block_map
+  int chunked;                 // 1: part is [R x bpc x (TB/32) x D], one row per 32-token chunk (packed token stream)
   int R, T, dim, vocab, num_sms;
   EncoderVariant variant;
   cudaStream_t stream;
@@ -58,8 +59,11 @@ inline FinalizeDst finalize_plain(float* emb) {
   d.row_offset = 0;
   return d;
 }
-cudaError_t launch_finalize(const float* part, const int32_t* lens, const FinalizeDst& dst, int R, int bpc, int TB,
-                            int dim, cudaStream_t stream);
+cudaError_t launch_finalize(const float* part, const int32_t* lens, const FinalizeDst& dst, const int32_t* row_start,
+                            int R, int bpc, int TB, int dim, cudaStream_t stream);
+// Ragged batches: token ids copied into a stream of 32-slot chunks (each chunk belongs to one candidate).
+cudaError_t launch_pack_tokens(const int32_t* token_ids, const int32_t* chunk_src, const int32_t* chunk_n,
+                               int32_t* packed, int nchunks, cudaStream_t stream);
 
 // Candidates sharded on T: per-rank partial sums [world][max_rows][D] + token counts [world][max_rows] in every
 // rank's exchange buffer; psum[q] / lens[q] = rank q's copy (peer-mapped).

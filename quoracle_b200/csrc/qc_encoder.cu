@@ -83,6 +83,7 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 
 __device__ __forceinline__ int block_valid(const int32_t* __restrict__ lens, int blk, int nblocks, int bpc, int TB) {
   if (blk >= nblocks) return 0;
+  if (lens == nullptr) return TB;                 // packed token stream: every block is full (padding ids are -1)
   const int cand = blk / bpc;
   const int j = blk - cand * bpc;
   int v = lens[cand] - j * TB;
@@ -135,6 +136,27 @@ __device__ __forceinline__ float gelu_sum_columns(uint32_t taddr) {
   return sum;
 }
 
+// Same traversal, one sum per 32-column chunk: the packed token stream gives every 32-token chunk of a block to
+// one candidate, so chunk sums are what K2 adds up (NCOL must be a multiple of 32).
+template <int NCOL>
+__device__ __forceinline__ void gelu_sum_chunks(uint32_t taddr, float (&out)[NCOL / 32]) {
+  static_assert(NCOL % 32 == 0, "chunked sums need 32-column chunks");
+  constexpr int FULL = NCOL / 32;
+  uint32_t va[32], vb[32];
+  tmem_ld_32x32b_x32(taddr, va);
+#pragma unroll
+  for (int c = 0; c < FULL; ++c) {
+    tmem_ld_wait();
+    if (c + 1 < FULL) {
+      if (c & 1) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, va); else tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sum += gelu_tanh(__uint_as_float((c & 1) ? vb[i] : va[i]));
+    out[c] = sum;
+  }
+}
+
 template <class Tr>
 __global__ void __launch_bounds__(kEncThreads, 1)
 qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D x D] bf16, box WBK x 128
@@ -146,7 +168,8 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
                  int32_t* __restrict__ dbg,                            // [0..3] watchdog, [4] token-range flag
                  unsigned long long* __restrict__ stall,               // optional [grid x 16] per-role stall cycles
                  const int32_t* __restrict__ block_map,                // optional compacted block list [nslots]
-                 int nslots, int R, int T, int bpc, int vocab) {
+                 int nslots, int chunked,                              // chunked: part holds one row per 32-token chunk
+                 int R, int T, int bpc, int vocab) {
   constexpr int D = Tr::D, TB = Tr::TB, CG = Tr::CG, KB = Tr::KB, NFT = Tr::NFT, WBK = Tr::WBK, NWS = Tr::NWS;
   constexpr int UMMA_N = Tr::UMMA_N, WS = Tr::W_STAGES, ACC_COLS = Tr::ACC_COLS;
 
@@ -220,6 +243,29 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
         const uint32_t as = acc_iter & 1u;
         st_wait += mbar_wait(&acc_full[as], (acc_iter >> 1) & 1u, dbg, 100 + ft);
         tcgen05_fence_after();
+        if constexpr (TB % 32 == 0) {
+          if (chunked) {
+            constexpr int NCH = TB / 32;
+            float csum[CG][NCH];
+#pragma unroll
+            for (int s = 0; s < CG; ++s) gelu_sum_chunks<TB>(tmem_base + lane_addr + as * ACC_COLS + s * TB, csum[s]);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_cluster(&acc_empty[as], 0); else mbar_arrive(&acc_empty[as]);
+            }
+#pragma unroll
+            for (int s = 0; s < CG; ++s) {
+              if (valid[s] > 0) {
+                const size_t blk = static_cast<size_t>(slot_block(block_map, item * CG + s, nslots, nblocks));
+#pragma unroll
+                for (int k = 0; k < NCH; ++k)
+                  part[(blk * NCH + k) * D + ft * Tr::MT + rank * 128 + row] = csum[s][k];
+              }
+            }
+            continue;
+          }
+        }
         float sums[CG];
 #pragma unroll
         for (int s = 0; s < CG; ++s) sums[s] = gelu_sum_columns<TB>(tmem_base + lane_addr + as * ACC_COLS + s * TB);
@@ -518,6 +564,7 @@ static cudaError_t launch_encode_t(const EncoderLaunch& a) {
   const int bpc = (a.T + Tr::TB - 1) / Tr::TB;
   int grid = a.num_sms;
   if (Tr::CG == 2) grid &= ~1;
+  if (a.chunked && (Tr::TB % 32 != 0)) return cudaErrorInvalidValue;
   const long long nblocks = static_cast<long long>(a.R) * bpc;
   if (nblocks > 0x7fffffffLL) return cudaErrorInvalidValue;
   const int nslots = a.block_map != nullptr ? a.nslots : static_cast<int>(nblocks);
@@ -541,7 +588,7 @@ static cudaError_t launch_encode_t(const EncoderLaunch& a) {
   cfg.numAttrs = 1;
   const CUtensorMap* tm = Tr::WBK == 64 ? a.w_tmap64 : a.w_tmap32;
   return cudaLaunchKernelEx(&cfg, kern, *tm, *a.e_tmap, a.table, a.token_ids, a.lens, a.part, a.err_flag, a.stall,
-                            a.block_map, nslots, a.R, a.T, bpc, a.vocab);
+                            a.block_map, nslots, a.chunked, a.R, a.T, bpc, a.vocab);
 }
 
 // The instantiated variants.  {dim, token block, cta group, W stage width, gather mode}

@@ -36,12 +36,15 @@ __device__ __forceinline__ float cosine_from(float dot, float na, float nb) {
 template <int PER>
 __global__ void __launch_bounds__(256) qc_finalize_kernel(const float* __restrict__ part,
                                                           const int32_t* __restrict__ lens, FinalizeDst dst,
-                                                          int R, int bpc, int TB, int D) {
+                                                          const int32_t* __restrict__ row_start, int R, int bpc, int TB,
+                                                          int D) {
   const int r = blockIdx.x;
   if (r >= R) return;
   const int len = lens[r];
-  const int nb = (len + TB - 1) / TB;
-  const float* p = part + static_cast<size_t>(r) * bpc * D;
+  // dense: candidate r owns partial rows r*bpc .. (one per token block).  packed (row_start != nullptr): it owns
+  // rows row_start[r] .. row_start[r+1]-1, one per 32-token chunk of the packed token stream.
+  const int nb = row_start != nullptr ? row_start[r + 1] - row_start[r] : (len + TB - 1) / TB;
+  const float* p = part + (row_start != nullptr ? static_cast<size_t>(row_start[r]) : static_cast<size_t>(r) * bpc) * D;
   float v[PER];
   float ss = 0.f;
 #pragma unroll
@@ -79,14 +82,36 @@ __global__ void __launch_bounds__(256) qc_finalize_kernel(const float* __restric
   }
 }
 
-cudaError_t launch_finalize(const float* part, const int32_t* lens, const FinalizeDst& dst, int R, int bpc, int TB,
-                            int dim, cudaStream_t stream) {
+cudaError_t launch_finalize(const float* part, const int32_t* lens, const FinalizeDst& dst, const int32_t* row_start,
+                            int R, int bpc, int TB, int dim, cudaStream_t stream) {
   if (R <= 0) return cudaSuccess;
   if (dst.count < 1 || dst.count > kMaxFinalizeDst || dst.n_local < 1) return cudaErrorInvalidValue;
-  if (dim <= 512) qc_finalize_kernel<2><<<R, 256, 0, stream>>>(part, lens, dst, R, bpc, TB, dim);
-  else if (dim <= 1024) qc_finalize_kernel<4><<<R, 256, 0, stream>>>(part, lens, dst, R, bpc, TB, dim);
-  else if (dim <= 2048) qc_finalize_kernel<8><<<R, 256, 0, stream>>>(part, lens, dst, R, bpc, TB, dim);
+  if (dim <= 512) qc_finalize_kernel<2><<<R, 256, 0, stream>>>(part, lens, dst, row_start, R, bpc, TB, dim);
+  else if (dim <= 1024) qc_finalize_kernel<4><<<R, 256, 0, stream>>>(part, lens, dst, row_start, R, bpc, TB, dim);
+  else if (dim <= 2048) qc_finalize_kernel<8><<<R, 256, 0, stream>>>(part, lens, dst, row_start, R, bpc, TB, dim);
   else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Packed token stream for ragged batches: chunk c (32 token slots) of the stream takes chunk_n[c] ids from
+// token_ids + chunk_src[c]; the rest of the chunk is padding (-1 -> zero embedding row -> GELU(0) = 0).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qc_pack_tokens_kernel(const int32_t* __restrict__ token_ids,
+                                                             const int32_t* __restrict__ chunk_src,
+                                                             const int32_t* __restrict__ chunk_n,
+                                                             int32_t* __restrict__ packed, int nchunks) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int c = idx >> 5, i = idx & 31;
+  if (c >= nchunks) return;
+  packed[idx] = i < chunk_n[c] ? token_ids[static_cast<size_t>(chunk_src[c]) + i] : -1;
+}
+
+cudaError_t launch_pack_tokens(const int32_t* token_ids, const int32_t* chunk_src, const int32_t* chunk_n,
+                               int32_t* packed, int nchunks, cudaStream_t stream) {
+  if (nchunks <= 0) return cudaSuccess;
+  const int blocks = (nchunks * 32 + 255) / 256;
+  qc_pack_tokens_kernel<<<blocks, 256, 0, stream>>>(token_ids, chunk_src, chunk_n, packed, nchunks);
   return cudaGetLastError();
 }
 

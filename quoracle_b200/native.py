@@ -34,7 +34,7 @@ ABI_SYMBOLS = (
     "qc_check_status", "qc_last_hang",
     "qc_launch_count", "qc_profile_enable", "qc_profile_reset", "qc_kernel_stats",
     "qc_encoder_info", "qc_encoder_set_cta_group", "qc_encoder_set_variant", "qc_encoder_stall_profile",
-    "qc_similarity_set_path", "qc_encoder_token_block", "qc_encoder_hint_block_map",
+    "qc_similarity_set_path", "qc_encoder_token_block", "qc_encoder_hint_block_map", "qc_encoder_set_packing",
     "qc_split_create", "qc_split_export", "qc_split_attach", "qc_decide_split_dev", "qc_split_gathered",
     "qc_split_destroy", "qc_tsplit_create", "qc_embed_tsplit_dev", "qc_decide_tsplit_dev",
 )
@@ -140,6 +140,8 @@ def load_library() -> ctypes.CDLL:
                                     ctypes.POINTER(ctypes.c_int32)]
     lib.qc_encoder_set_variant.restype = i32
     lib.qc_encoder_set_variant.argtypes = [vp, i32, i32, i32, i32]
+    lib.qc_encoder_set_packing.restype = i32
+    lib.qc_encoder_set_packing.argtypes = [vp, i32]
     lib.qc_encoder_token_block.restype = i32
     lib.qc_encoder_token_block.argtypes = [vp, i32, ctypes.POINTER(i32)]
     lib.qc_encoder_hint_block_map.restype = i32
@@ -376,6 +378,10 @@ class Context:
         if out is None:
             return None
         return {name: float(out[i]) for i, name in enumerate(self.STALL_FIELDS)}
+
+    def set_packing(self, mode: int) -> None:
+        """Ragged-batch token packing on the host entry points: 0 auto, 1 never, 2 whenever possible."""
+        _check(self._lib.qc_encoder_set_packing(self._h, int(mode)))
 
     def token_block(self, t: int) -> int:
         """Tokens per K1 block for sequences of `t` token slots (the tiling chosen for that T)."""

@@ -255,6 +255,7 @@ def test_compacted_block_list_equals_dense_walk(dim, t):
     tok = batch.token_ids.copy()
     tok[np.arange(t)[None, None, :] >= lens[:, :, None]] = -1
     with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+        ctx.set_packing(1)                                                                    # block list only
         host = ctx.decide_batch(tok, lens, batch.thr, want_cos=True, want_emb=True)          # compacted walk
         dev = torch.device("cuda:0")
         d_tok, d_len = torch.from_numpy(tok).to(dev), torch.from_numpy(lens).to(dev)
@@ -274,3 +275,52 @@ def test_compacted_block_list_equals_dense_walk(dim, t):
         # nothing to encode at all
         zero = ctx.decide_batch(tok, np.zeros_like(lens), batch.thr, want_cos=True, want_emb=True)
         assert np.all(zero.emb == 0.0) and np.all(zero.cos == 0.0) and np.all(zero.ref_ok == 0)
+
+
+@pytest.mark.parametrize("dim,t", [(768, 512), (384, 300), (768, 77)])
+def test_packed_token_stream_matches_unpacked(dim, t):
+    """Ragged batches on the host entry points are packed into 32-token chunks (four per block, each chunk owned by
+    one candidate).  Same tokens, same per-token arithmetic; only the fp32 summation order of the pooled sum
+    differs, so the embeddings agree to ~1e-8 and stay within the oracle tolerance."""
+    w = weights(dim, vocab=8192)
+    rng = np.random.default_rng(dim * 3 + t)
+    b, n = 40, 8
+    batch = synth.make_decisions(b, n, t, vocab=8192, seed=synth.BASE_SEED + dim + t, ragged=True)
+    lens = batch.lens.copy()
+    flat = lens.reshape(-1)
+    flat[::7] = rng.integers(0, 4, size=flat[::7].shape)         # empty and tiny candidates
+    flat[3::13] = t                                              # full ones
+    flat[5::17] = np.minimum(t, 33)                              # one chunk plus one token
+    tok = batch.token_ids.copy()
+    tok[np.arange(t)[None, None, :] >= lens[:, :, None]] = -1
+    with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+        ctx.set_packing(1)
+        plain = ctx.decide_batch(tok, lens, batch.thr, want_cos=True, want_emb=True)
+        ctx.set_packing(2)
+        packed = ctx.decide_batch(tok, lens, batch.thr, want_cos=True, want_emb=True)
+        again = ctx.decide_batch(tok, lens, batch.thr, want_cos=True, want_emb=True)
+        assert np.array_equal(packed.emb, again.emb)                                   # deterministic
+        assert np.max(np.abs(packed.emb - plain.emb)) < 1e-6
+        assert np.max(np.abs(packed.cos - plain.cos)) < 1e-5
+        want = oenc.encode(w.table_bf16, w.w_bf16, tok.reshape(b * n, t), flat)
+        assert np.max(np.abs(packed.emb.reshape(b * n, dim) - want)) < EMB_TOL
+        assert np.all(packed.emb.reshape(b * n, dim)[flat == 0] == 0.0)
+        o_ok, o_med, o_cos, margins = numeric.decide_batch(want.reshape(b, n, dim), batch.thr)
+        safe_t, safe_v = margins["thr"] > MARGIN, margins["vote"] > MARGIN
+        assert np.array_equal(packed.ref_ok[safe_t], o_ok[safe_t]) and np.array_equal(packed.medoid[safe_v], o_med[safe_v])
+        # the pipelined host path packs too; auto mode picks packing for this batch (much more than 5 % saved)
+        ctx.set_packing(0)
+        out = native.DecideResult(np.empty(b, np.int32), np.empty(b, np.int32), np.empty((b, n, n), np.float32), None)
+        ctx.decide_batch_submit(1, tok, lens, batch.thr, out)
+        ctx.decide_batch_wait(1)
+        assert np.array_equal(out.cos, packed.cos)
+        # full-length batches whose T fills whole token blocks are left alone (bit-identical to the unpacked path);
+        # a T that leaves the last block mostly empty (300 = 2 x 128 + 44) is packed like any ragged batch
+        full = synth.make_decisions(8, n, t, vocab=8192, seed=5)
+        a = ctx.decide_batch(full.token_ids, full.lens, full.thr, want_emb=True)
+        ctx.set_packing(1)
+        c2 = ctx.decide_batch(full.token_ids, full.lens, full.thr, want_emb=True)
+        if t % ctx.token_block(t) == 0:
+            assert np.array_equal(a.emb, c2.emb)
+        else:
+            assert np.max(np.abs(a.emb - c2.emb)) < 1e-6

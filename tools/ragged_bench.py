@@ -58,6 +58,29 @@ def main():
         ms = st["ms"] / st["launches"]
         print(f"{name:36s} K1 {ms:.4f} ms/launch  {flops / ms / 1e9:7.1f} TFLOP/s on valid tokens "
               f"({st['launches']} launches)")
+
+    # end to end through the pipelined host API (what a caller sees): wall clock, four batches in flight
+    import time
+
+    def host_pipeline(steps):
+        for i in range(steps):
+            k = i % 4
+            if i >= 4:
+                ctx.decide_batch_wait(k)
+            pt, pl, pth = pins[i % 8]
+            ctx.decide_batch_submit(k, pt.array, pl.array, pth.array, outs[k])
+        for i in range(max(0, steps - 4), steps):
+            ctx.decide_batch_wait(i % 4)
+
+    for mode, name in ((1, "host API, block list (packing off)"), (2, "host API, packed token stream")):
+        ctx.set_packing(mode)
+        host_pipeline(8)
+        t0 = time.perf_counter()
+        host_pipeline(200)
+        dt = time.perf_counter() - t0
+        print(f"{name:36s} {dt / 200 * 1e3:.4f} ms/step  {200 * b / dt:9.0f} decisions/s  "
+              f"{flops * 200 / dt / 1e12:7.1f} TFLOP/s on valid tokens")
+    ctx.set_packing(0)
     full = 2.0 * b * n * t * d * d
     print(f"valid tokens: {flops / full:.3f} of the padded shape; blocks of 128: "
           f"{np.mean([np.ceil(x.lens / 128).sum() for x in batches]) / (b * n * 4):.3f} non-empty")
