@@ -139,11 +139,16 @@ def cpu_path(weights, token_ids, lens, thr, threads):
     return ok, med, emb
 
 
-def cpu_sim_only(emb, thr, threads):
+def cpu_sim_only(emb, thr, threads, want_full=True, repeat=1):
+    """Similarity stage alone on the host cores, fed the GPU-sized embeddings (the reference has no encoder to time:
+    its embed step is a network call).  want_full=False is the reference rule only (N-1 cosines, consensus_rules.ex
+    :277-286); True adds the full N x N matrix and the medoid vote."""
     from oracle import cport
     t0 = time.perf_counter()
-    cport.similarity_batch(emb, thr.astype(np.float64), want_full=True, threads=threads, want_cos=False, native=True)
-    return time.perf_counter() - t0
+    for _ in range(repeat):
+        cport.similarity_batch(emb, thr.astype(np.float64), want_full=want_full, threads=threads, want_cos=False,
+                               native=True)
+    return (time.perf_counter() - t0) / repeat
 
 
 def cpu_threads() -> int:
@@ -368,12 +373,17 @@ def run_ours(args):
             ok, med, emb = cpu_path(weights, batches[0].token_ids[:sample], batches[0].lens[:sample],
                                     batches[0].thr[:sample], threads)
             dt = time.perf_counter() - t0
-            sim_dt = cpu_sim_only(emb.reshape(sample, n, -1), batches[0].thr[:sample], 1)
+            e3 = emb.reshape(sample, n, -1)
+            sim_dt = cpu_sim_only(e3, batches[0].thr[:sample], 1)
+            rule_dt = cpu_sim_only(e3, batches[0].thr[:sample], 1, want_full=False)
+            sim_all_dt = cpu_sim_only(e3, batches[0].thr[:sample], threads, repeat=20)
             line["cpu_baseline"] = {
                 "value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
                 "sample": f"first {sample} decisions of batch 0 ({sample * n} candidates x {t} tokens), C port of the "
                           f"whole path, {dt:.1f} s",
                 "similarity_only_1thread_decisions_per_s": sample / sim_dt if sim_dt > 0 else None,
+                "reference_rule_only_1thread_decisions_per_s": sample / rule_dt if rule_dt > 0 else None,
+                f"similarity_only_{threads}threads_decisions_per_s": sample / sim_all_dt if sim_all_dt > 0 else None,
                 "index_mismatch_vs_gpu": {"ref_ok": int((ok != gpu_ok0[:sample]).sum()),
                                           "medoid": int((med != gpu_med0[:sample]).sum()), "checked": int(sample)},
             }
