@@ -98,6 +98,7 @@ struct qc_ctx {
   const int32_t* hint_row_start = nullptr;
   int hint_nchunks = 0;
   DevBuf* hint_packed_buf = nullptr;
+  bool hint_variant_set = false;  // the staged plan was made for c->variant: encode_dev must not re-pick it
   int packing = 0;               // 0 auto, 1 never, 2 whenever the tiling allows (test hook)
   int sim_path = 0;              // K3 for pools 9..64: 0 auto (tcgen05 when the layout allows), 1 mma.sync, 2 tcgen05
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved once at create
@@ -285,8 +286,12 @@ int stage_block_map(qc_ctx* c, const int32_t* lens, int R, int T, DevBuf* dmap, 
   c->hint_nslots = 0;
   c->hint_chunk_src = nullptr;
   c->hint_nchunks = 0;
-  if (!c->variant_forced) c->variant = qc::encoder_auto_variant(c->dim, T);
-  const int TB = c->variant.token_block;
+  c->hint_variant_set = false;
+  // tiling for the unpacked walks: the one chosen for T (least padding of full-length candidates)
+  const qc::EncoderVariant va = c->variant_forced ? c->variant : qc::encoder_auto_variant(c->dim, T);
+  // tiling for the packed stream: padding no longer depends on T, so the fastest full-block tiling
+  const qc::EncoderVariant vp = c->variant_forced ? c->variant : qc::encoder_default_variant(c->dim);
+  const int TB = va.token_block;
   const int bpc = (T + TB - 1) / TB;
   long long used = 0, chunks = 0;
   for (int r = 0; r < R; ++r) {
@@ -294,13 +299,15 @@ int stage_block_map(qc_ctx* c, const int32_t* lens, int R, int T, DevBuf* dmap, 
     chunks += (lens[r] + 31) / 32;
   }
   // Packed token stream: every candidate is cut into 32-token chunks and the chunks of all candidates are laid
-  // end to end, four (TB / 32) to a block, so the only padding left is inside each candidate's last chunk.
-  // Worth its two extra small kernels when it saves at least 5 % of the blocks.
-  const bool can_pack = (TB % 32) == 0 && static_cast<long long>(R) * T < 0x7fffffffLL && c->packing != 1;
+  // end to end, TB / 32 to a block, so the only padding left is inside each candidate's last chunk.
+  // Worth its extra small kernel when it saves at least 5 % of the token slots K1 has to process.
+  const bool can_pack = (vp.token_block % 32) == 0 && static_cast<long long>(R) * T < 0x7fffffffLL && c->packing != 1;
   if (can_pack && chunks > 0) {
-    const int nch = TB / 32;
+    const int nch = vp.token_block / 32;
     const long long pblocks = (chunks + nch - 1) / nch;
-    if (c->packing == 2 || pblocks * 100 <= used * 95) {
+    if (c->packing == 2 || pblocks * vp.token_block * 100 <= used * TB * 95) {
+      c->variant = vp;
+      c->hint_variant_set = true;
       const long long nchunks = pblocks * nch;
       const size_t ints = static_cast<size_t>(2 * nchunks + R + 1);
       QC_CUDA(hmap->ensure(ints * sizeof(int32_t)));
@@ -332,6 +339,8 @@ int stage_block_map(qc_ctx* c, const int32_t* lens, int R, int T, DevBuf* dmap, 
       return QC_OK;
     }
   }
+  c->variant = va;
+  c->hint_variant_set = true;
   if (used == static_cast<long long>(R) * bpc || used > 0x7fffffffLL) return QC_OK;
   QC_CUDA(hmap->ensure(static_cast<size_t>(used > 0 ? used : 1) * sizeof(int32_t)));
   QC_CUDA(dmap->ensure(static_cast<size_t>(used > 0 ? used : 1) * sizeof(int32_t)));
@@ -356,6 +365,7 @@ struct HintGuard {
     c->hint_nslots = 0;
     c->hint_chunk_src = nullptr;
     c->hint_nchunks = 0;
+    c->hint_variant_set = false;
   }
 };
 
@@ -363,7 +373,8 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
                DevBuf* part_buf = nullptr, const qc::FinalizeDst* scatter = nullptr,
                const qc::TsplitDst* tsplit = nullptr) {
   DevBuf& part = part_buf ? *part_buf : c->part;
-  if (!c->variant_forced) c->variant = qc::encoder_auto_variant(c->dim, T);
+  if (!c->variant_forced && !c->hint_variant_set) c->variant = qc::encoder_auto_variant(c->dim, T);
+  c->hint_variant_set = false;
   const int TB = c->variant.token_block;
   const int bpc = (T + TB - 1) / TB;
   // one-shot hints of the host entry points (ragged batches)
