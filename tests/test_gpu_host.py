@@ -70,7 +70,7 @@ def test_collector_one_gpu_call_for_the_tree(emb):
         col.submit(f"a{a}", "content", [f"{SENTENCES[a % 3]} run {a}", f"{SENTENCES[a % 3]} run {a} now", SENTENCES[3]], 0.9)
     out = col.flush()
     assert emb.gpu_calls == calls + 1                                     # one embed call for 192 values
-    assert emb.ctx.launch_count() - before == 3                           # K1 + K2 + one K3
+    assert emb.ctx.launch_count() - before in (3, 4)                      # K1 + K2 + one K3 (+ the token pack kernel: texts are ragged)
     assert len(out) == 64 and all(v["content"]["medoid"] in (0, 1, 2) for v in out.values())
 
 
