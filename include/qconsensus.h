@@ -130,6 +130,18 @@ int qc_decide_batch_submit(qc_ctx* ctx, int slot, const int32_t* token_ids, cons
                            int T, const float* thr, int32_t* out_ref_ok, int32_t* out_medoid, float* out_cos);
 int qc_decide_batch_wait(qc_ctx* ctx, int slot);
 
+/*
+ * Ragged (CSR) forms of qc_embed_batch / qc_decide_batch for callers whose candidates differ in length (what a
+ * collector of real model responses holds): tokens of candidate r are tokens[offsets[r] .. offsets[r+1]), offsets has
+ * R + 1 (= B*N + 1) non-decreasing entries starting anywhere >= 0, no candidate longer than QC_MAX_TOKENS.  Nothing is
+ * padded on the host or on the wire; on the device the candidates are cut into chunks and laid end to end (packed
+ * token stream), so the encoder's work is proportional to the tokens that exist.  Same results as the padded entry
+ * points up to fp32 summation order of the pooled sum.
+ */
+int qc_embed_ragged(qc_ctx* ctx, const int32_t* tokens, const int32_t* offsets, int R, float* out_emb);
+int qc_decide_ragged(qc_ctx* ctx, const int32_t* tokens, const int32_t* offsets, int B, int N, const float* thr,
+                     int32_t* out_ref_ok, int32_t* out_medoid, float* out_cos, float* out_emb);
+
 /* Embedding only: R candidate rows -> out_emb [R*dim] f32 (what an `:embedding_fn` returns). */
 int qc_embed_batch(qc_ctx* ctx, const int32_t* token_ids, const int32_t* lens, int R, int T,
                    float* out_emb);
@@ -258,10 +270,11 @@ int qc_decide_tsplit_dev(qc_ctx* ctx, qc_split* split, const int32_t* d_token_id
 int qc_encoder_token_block(qc_ctx* ctx, int T, int32_t* token_block);
 /*
  * Ragged batches on the host entry points (qc_decide_batch, qc_decide_batch_submit, qc_embed_batch): when it saves
- * at least 5 % of the token blocks the valid tokens are packed into a stream of 32-slot chunks (four per 128-token
- * block, each chunk owned by one candidate), K1 runs on the packed stream and K2 adds a candidate's chunk sums.
+ * at least 5 % of the token slots the valid tokens are packed into a stream of chunks (32 tokens, or 16 / 8 when 32
+ * does not divide the token block; each chunk owned by one candidate), K1 runs on the packed stream and K2 adds a
+ * candidate's chunk sums.
  * Same arithmetic as the unpacked walk up to fp32 summation order (|delta| ~ 1e-8 on unit rows).
- * mode 0 = auto (default), 1 = never pack, 2 = pack whenever the tiling allows (token block a multiple of 32).
+ * mode 0 = auto (default), 1 = never pack, 2 = always pack.
  */
 int qc_encoder_set_packing(qc_ctx* ctx, int mode);
 int qc_encoder_hint_block_map(qc_ctx* ctx, const int32_t* d_block_map, int nslots);

@@ -293,17 +293,18 @@ int stage_block_map(qc_ctx* c, const int32_t* lens, int R, int T, DevBuf* dmap, 
   const qc::EncoderVariant vp = c->variant_forced ? c->variant : qc::encoder_default_variant(c->dim);
   const int TB = va.token_block;
   const int bpc = (T + TB - 1) / TB;
+  const int CH = qc::encoder_chunk_tokens(vp.token_block);
   long long used = 0, chunks = 0;
   for (int r = 0; r < R; ++r) {
     used += (lens[r] + TB - 1) / TB;
-    chunks += (lens[r] + 31) / 32;
+    chunks += (lens[r] + CH - 1) / CH;
   }
-  // Packed token stream: every candidate is cut into 32-token chunks and the chunks of all candidates are laid
-  // end to end, TB / 32 to a block, so the only padding left is inside each candidate's last chunk.
+  // Packed token stream: every candidate is cut into CH-token chunks (CH = 32, or 16 / 8 for token blocks that 32
+  // does not divide) and the chunks of all candidates are laid end to end, TB / CH to a block, so the only padding left is inside each candidate's last chunk.
   // Worth its extra small kernel when it saves at least 5 % of the token slots K1 has to process.
-  const bool can_pack = (vp.token_block % 32) == 0 && static_cast<long long>(R) * T < 0x7fffffffLL && c->packing != 1;
+  const bool can_pack = static_cast<long long>(R) * T < 0x7fffffffLL && c->packing != 1;
   if (can_pack && chunks > 0) {
-    const int nch = vp.token_block / 32;
+    const int nch = vp.token_block / CH;
     const long long pblocks = (chunks + nch - 1) / nch;
     if (c->packing == 2 || pblocks * vp.token_block * 100 <= used * TB * 95) {
       c->variant = vp;
@@ -318,9 +319,9 @@ int stage_block_map(qc_ctx* c, const int32_t* lens, int R, int T, DevBuf* dmap, 
       long long k = 0;
       for (int r = 0; r < R; ++r) {
         row[r] = static_cast<int32_t>(k);
-        for (int o = 0; o < lens[r]; o += 32) {
+        for (int o = 0; o < lens[r]; o += CH) {
           src[k] = static_cast<int32_t>(static_cast<long long>(r) * T + o);
-          cnt[k] = lens[r] - o < 32 ? lens[r] - o : 32;
+          cnt[k] = lens[r] - o < CH ? lens[r] - o : CH;
           ++k;
         }
       }
@@ -389,13 +390,14 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
   c->hint_nslots = 0;
   c->hint_chunk_src = nullptr;
   c->hint_nchunks = 0;
-  const bool pack = chunk_src != nullptr && nchunks > 0 && tsplit == nullptr && (TB % 32) == 0 && packed != nullptr;
+  const int CH = qc::encoder_chunk_tokens(TB);
+  const bool pack = chunk_src != nullptr && nchunks > 0 && tsplit == nullptr && packed != nullptr;
   if (pack) {
-    // token ids -> stream of 32-slot chunks; K1 sees nchunks / (TB/32) full blocks and writes one partial row per chunk
-    QC_CUDA(packed->ensure(static_cast<size_t>(nchunks) * 32 * sizeof(int32_t)));
+    // token ids -> stream of CH-slot chunks; K1 sees nchunks / (TB/CH) full blocks and writes one partial row per chunk
+    QC_CUDA(packed->ensure(static_cast<size_t>(nchunks) * CH * sizeof(int32_t)));
     QC_CUDA(part.ensure(static_cast<size_t>(nchunks) * c->dim * sizeof(float)));
     c->launches++;
-    QC_CUDA(qc::launch_pack_tokens(d_tok, chunk_src, chunk_n, static_cast<int32_t*>(packed->p), nchunks, s));
+    QC_CUDA(qc::launch_pack_tokens(d_tok, chunk_src, chunk_n, static_cast<int32_t*>(packed->p), nchunks, CH, s));
   } else {
     QC_CUDA(part.ensure(static_cast<size_t>(R) * bpc * c->dim * sizeof(float)));
   }
@@ -409,7 +411,7 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
     if (pack) {
       a.token_ids = static_cast<const int32_t*>(packed->p);
       a.lens = nullptr;                          // every block of the packed stream is full
-      a.R = nchunks / (TB / 32);
+      a.R = nchunks / (TB / CH);
       a.T = TB;
       a.chunked = 1;
     } else {
@@ -849,6 +851,128 @@ int qc_embed_batch(qc_ctx* c, const int32_t* token_ids, const int32_t* lens, int
   if (st != QC_OK) return st;
   std::vector<PendingOut> pend;
   size_t ooff = 0;
+  if ((st = d2h(c, out_emb, c->emb.p, embb, &ooff, &pend)) != QC_OK) return st;
+  if ((st = check_token_flag(c)) != QC_OK) return st;
+  for (const PendingOut& p : pend) memcpy(p.user, p.staged, p.bytes);
+  return QC_OK;
+}
+
+// ---- ragged (CSR) input: no padding on the host, none on the wire -------------------------------
+// tokens of candidate r are tokens[offsets[r] .. offsets[r+1]).  The flat array goes to the device as is; the packed
+// token stream (chunks of every candidate laid end to end) is built from it by the pack kernel, so the only padding
+// K1 ever sees is inside each candidate's last chunk.
+static int ragged_common(qc_ctx* c, const int32_t* tokens, const int32_t* offsets, int R, float* d_emb, cudaStream_t s) {
+  const long long total = offsets[R];
+  std::vector<int32_t> lens(static_cast<size_t>(R));
+  for (int r = 0; r < R; ++r) {
+    const long long l = static_cast<long long>(offsets[r + 1]) - offsets[r];
+    if (offsets[r] < 0 || l < 0) return QC_ERR_INVALID_INPUT;
+    if (l > QC_MAX_TOKENS) return QC_ERR_CONTEXT_LENGTH;
+    lens[static_cast<size_t>(r)] = static_cast<int32_t>(l);
+  }
+  const size_t tokb = static_cast<size_t>(total > 0 ? total : 1) * 4, lenb = static_cast<size_t>(R) * 4;
+  QC_CUDA(c->tok.ensure(tokb));
+  QC_CUDA(c->lens.ensure(lenb));
+  QC_CUDA(c->h_in.ensure(pad256(tokb) + pad256(lenb)));
+  size_t off = 0;
+  int st;
+  if (total > 0 && (st = h2d(c, c->tok.p, tokens, static_cast<size_t>(total) * 4, &off)) != QC_OK) return st;
+  if ((st = h2d(c, c->lens.p, lens.data(), lenb, &off)) != QC_OK) return st;
+  if (total == 0) {                                            // nothing to encode: zero rows
+    QC_CUDA(cudaMemsetAsync(d_emb, 0, static_cast<size_t>(R) * c->dim * 4, s));
+    return QC_OK;
+  }
+  // the plan of stage_block_map's packed branch, with flat offsets as chunk sources
+  const qc::EncoderVariant vp = c->variant_forced ? c->variant : qc::encoder_default_variant(c->dim);
+  const int CH = qc::encoder_chunk_tokens(vp.token_block), nch = vp.token_block / CH;
+  long long chunks = 0;
+  for (int r = 0; r < R; ++r) chunks += (lens[static_cast<size_t>(r)] + CH - 1) / CH;
+  const long long nchunks = (chunks + nch - 1) / nch * nch;
+  if (nchunks * CH > 0x7fffffffLL) return QC_ERR_UNSUPPORTED;
+  const size_t ints = static_cast<size_t>(2 * nchunks + R + 1);
+  QC_CUDA(c->h_map.ensure(ints * sizeof(int32_t)));
+  QC_CUDA(c->map.ensure(ints * sizeof(int32_t)));
+  int32_t* src = static_cast<int32_t*>(c->h_map.p);
+  int32_t* cnt = src + nchunks;
+  int32_t* row = cnt + nchunks;
+  long long k = 0;
+  for (int r = 0; r < R; ++r) {
+    row[r] = static_cast<int32_t>(k);
+    const int len = lens[static_cast<size_t>(r)];
+    for (int o = 0; o < len; o += CH) {
+      src[k] = offsets[r] + o;
+      cnt[k] = len - o < CH ? len - o : CH;
+      ++k;
+    }
+  }
+  row[R] = static_cast<int32_t>(k);
+  for (; k < nchunks; ++k) {
+    src[k] = 0;
+    cnt[k] = 0;
+  }
+  QC_CUDA(cudaMemcpyAsync(c->map.p, src, ints * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  HintGuard hg(c);
+  const int32_t* d = static_cast<const int32_t*>(c->map.p);
+  c->variant = vp;
+  c->hint_variant_set = true;
+  c->hint_chunk_src = d;
+  c->hint_chunk_n = d + nchunks;
+  c->hint_row_start = d + 2 * nchunks;
+  c->hint_nchunks = static_cast<int>(nchunks);
+  c->hint_packed_buf = &c->packed;
+  // T only sizes the dense walk, which the pack hint replaces
+  return encode_dev(c, static_cast<int32_t*>(c->tok.p), static_cast<int32_t*>(c->lens.p), R, vp.token_block, d_emb, s);
+}
+
+int qc_embed_ragged(qc_ctx* c, const int32_t* tokens, const int32_t* offsets, int R, float* out_emb) {
+  if (c == nullptr || offsets == nullptr || out_emb == nullptr || R < 0) return QC_ERR_INVALID_INPUT;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  if (R == 0) return QC_OK;
+  if (offsets[R] < 0 || (offsets[R] > 0 && tokens == nullptr)) return QC_ERR_INVALID_INPUT;
+  DeviceGuard g(c->device);
+  const size_t embb = static_cast<size_t>(R) * c->dim * 4;
+  QC_CUDA(c->emb.ensure(embb));
+  QC_CUDA(c->h_out.ensure(pad256(embb)));
+  int st = ragged_common(c, tokens, offsets, R, static_cast<float*>(c->emb.p), c->stream);
+  if (st != QC_OK) return st;
+  std::vector<PendingOut> pend;
+  size_t ooff = 0;
+  if ((st = d2h(c, out_emb, c->emb.p, embb, &ooff, &pend)) != QC_OK) return st;
+  if ((st = check_token_flag(c)) != QC_OK) return st;
+  for (const PendingOut& p : pend) memcpy(p.user, p.staged, p.bytes);
+  return QC_OK;
+}
+
+int qc_decide_ragged(qc_ctx* c, const int32_t* tokens, const int32_t* offsets, int B, int N, const float* thr,
+                     int32_t* out_ref_ok, int32_t* out_medoid, float* out_cos, float* out_emb) {
+  if (c == nullptr || offsets == nullptr || thr == nullptr || B < 0) return QC_ERR_INVALID_INPUT;
+  if (N < 1 || N > QC_MAX_POOL) return QC_ERR_UNSUPPORTED;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  if (B == 0) return QC_OK;
+  const int R = B * N;
+  if (offsets[R] < 0 || (offsets[R] > 0 && tokens == nullptr)) return QC_ERR_INVALID_INPUT;
+  DeviceGuard g(c->device);
+  const size_t thrb = static_cast<size_t>(B) * 4, ib = static_cast<size_t>(B) * 4;
+  const size_t embb = static_cast<size_t>(R) * c->dim * 4, cosb = static_cast<size_t>(B) * N * N * 4;
+  QC_CUDA(c->thr.ensure(thrb));
+  QC_CUDA(c->emb.ensure(embb));
+  QC_CUDA(c->refok.ensure(ib));
+  QC_CUDA(c->medoid.ensure(ib));
+  if (out_cos) QC_CUDA(c->cosm.ensure(cosb));
+  QC_CUDA(c->h_out.ensure(2 * pad256(ib) + pad256(cosb) + pad256(embb)));
+  int st = ragged_common(c, tokens, offsets, R, static_cast<float*>(c->emb.p), c->stream);
+  if (st != QC_OK) return st;
+  // thr rides after the tokens: stage it through its own small pinned copy on the same stream
+  QC_CUDA(cudaMemcpyAsync(c->thr.p, thr, thrb, cudaMemcpyHostToDevice, c->stream));
+  st = qc_similarity_batch_dev(c, static_cast<float*>(c->emb.p), B, N, c->dim, static_cast<float*>(c->thr.p),
+                               static_cast<int32_t*>(c->refok.p), static_cast<int32_t*>(c->medoid.p),
+                               out_cos ? static_cast<float*>(c->cosm.p) : nullptr, c->stream);
+  if (st != QC_OK) return st;
+  std::vector<PendingOut> pend;
+  size_t ooff = 0;
+  if ((st = d2h(c, out_ref_ok, c->refok.p, ib, &ooff, &pend)) != QC_OK) return st;
+  if ((st = d2h(c, out_medoid, c->medoid.p, ib, &ooff, &pend)) != QC_OK) return st;
+  if ((st = d2h(c, out_cos, c->cosm.p, cosb, &ooff, &pend)) != QC_OK) return st;
   if ((st = d2h(c, out_emb, c->emb.p, embb, &ooff, &pend)) != QC_OK) return st;
   if ((st = check_token_flag(c)) != QC_OK) return st;
   for (const PendingOut& p : pend) memcpy(p.user, p.staged, p.bytes);

@@ -26,7 +26,7 @@ struct EncoderLaunch {
   unsigned long long* stall;   // device [grid x 16] per-role stall cycles, or nullptr
   const int32_t* block_map;    // device: ids of the non-empty token blocks (cand * bpc + j), or nullptr = dense
   int nslots;                  // entries in block_map
-  int chunked;                 // 1: part is [R x bpc x (TB/32) x D], one row per 32-token chunk (packed token stream)
+  int chunked;                 // 1: part is [R x bpc x (TB/CH) x D], one row per CH-token chunk (packed token stream)
   int R, T, dim, vocab, num_sms;
   EncoderVariant variant;
   cudaStream_t stream;
@@ -61,9 +61,11 @@ inline FinalizeDst finalize_plain(float* emb) {
 }
 cudaError_t launch_finalize(const float* part, const int32_t* lens, const FinalizeDst& dst, const int32_t* row_start,
                             int R, int bpc, int TB, int dim, cudaStream_t stream);
-// Ragged batches: token ids copied into a stream of 32-slot chunks (each chunk belongs to one candidate).
+// Ragged batches: token ids copied into a stream of `chunk`-slot chunks (each chunk belongs to one candidate);
+// chunk = encoder_chunk_tokens(token block): the widest of 32 / 16 / 8 dividing it.
 cudaError_t launch_pack_tokens(const int32_t* token_ids, const int32_t* chunk_src, const int32_t* chunk_n,
-                               int32_t* packed, int nchunks, cudaStream_t stream);
+                               int32_t* packed, int nchunks, int chunk, cudaStream_t stream);
+inline int encoder_chunk_tokens(int tb) { return tb % 32 == 0 ? 32 : (tb % 16 == 0 ? 16 : 8); }
 
 // Candidates sharded on T: per-rank partial sums [world][max_rows][D] + token counts [world][max_rows] in every
 // rank's exchange buffer; psum[q] / lens[q] = rank q's copy (peer-mapped).

@@ -136,23 +136,30 @@ __device__ __forceinline__ float gelu_sum_columns(uint32_t taddr) {
   return sum;
 }
 
-// Same traversal, one sum per 32-column chunk: the packed token stream gives every 32-token chunk of a block to
-// one candidate, so chunk sums are what K2 adds up (NCOL must be a multiple of 32).
-template <int NCOL>
-__device__ __forceinline__ void gelu_sum_chunks(uint32_t taddr, float (&out)[NCOL / 32]) {
-  static_assert(NCOL % 32 == 0, "chunked sums need 32-column chunks");
-  constexpr int FULL = NCOL / 32;
-  uint32_t va[32], vb[32];
-  tmem_ld_32x32b_x32(taddr, va);
+// Same traversal, one sum per chunk of CH columns: the packed token stream gives every CH-token chunk of a block to
+// one candidate, so chunk sums are what K2 adds up.  CH is the widest of 32 / 16 / 8 that divides the token block.
+__host__ __device__ constexpr int chunk_tokens(int tb) { return tb % 32 == 0 ? 32 : (tb % 16 == 0 ? 16 : 8); }
+
+template <int NCOL, int CH>
+__device__ __forceinline__ void gelu_sum_chunks(uint32_t taddr, float (&out)[NCOL / CH]) {
+  static_assert(NCOL % CH == 0 && (CH == 32 || CH == 16 || CH == 8), "chunk width must divide the token block");
+  constexpr int NCHUNK = NCOL / CH;
+  uint32_t va[CH], vb[CH];
+  auto load = [](uint32_t addr, uint32_t (&v)[CH]) {
+    if constexpr (CH == 32) tmem_ld_32x32b_x32(addr, v);
+    else if constexpr (CH == 16) tmem_ld_32x32b_x16(addr, v);
+    else tmem_ld_32x32b_x8(addr, v);
+  };
+  load(taddr, va);
 #pragma unroll
-  for (int c = 0; c < FULL; ++c) {
+  for (int c = 0; c < NCHUNK; ++c) {
     tmem_ld_wait();
-    if (c + 1 < FULL) {
-      if (c & 1) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, va); else tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);
+    if (c + 1 < NCHUNK) {
+      if (c & 1) load(taddr + (c + 1) * CH, va); else load(taddr + (c + 1) * CH, vb);
     }
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) sum += gelu_tanh(__uint_as_float((c & 1) ? vb[i] : va[i]));
+    for (int i = 0; i < CH; ++i) sum += gelu_tanh(__uint_as_float((c & 1) ? vb[i] : va[i]));
     out[c] = sum;
   }
 }
@@ -168,7 +175,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
                  int32_t* __restrict__ dbg,                            // [0..3] watchdog, [4] token-range flag
                  unsigned long long* __restrict__ stall,               // optional [grid x 16] per-role stall cycles
                  const int32_t* __restrict__ block_map,                // optional compacted block list [nslots]
-                 int nslots, int chunked,                              // chunked: part holds one row per 32-token chunk
+                 int nslots, int chunked,                              // chunked: part holds one row per chunk_tokens(TB) tokens
                  int R, int T, int bpc, int vocab) {
   constexpr int D = Tr::D, TB = Tr::TB, CG = Tr::CG, KB = Tr::KB, NFT = Tr::NFT, WBK = Tr::WBK, NWS = Tr::NWS;
   constexpr int UMMA_N = Tr::UMMA_N, WS = Tr::W_STAGES, ACC_COLS = Tr::ACC_COLS;
@@ -243,28 +250,27 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
         const uint32_t as = acc_iter & 1u;
         st_wait += mbar_wait(&acc_full[as], (acc_iter >> 1) & 1u, dbg, 100 + ft);
         tcgen05_fence_after();
-        if constexpr (TB % 32 == 0) {
-          if (chunked) {
-            constexpr int NCH = TB / 32;
-            float csum[CG][NCH];
+        if (chunked) {
+          constexpr int CH = chunk_tokens(TB);
+          constexpr int NCH = TB / CH;
+          float csum[CG][NCH];
 #pragma unroll
-            for (int s = 0; s < CG; ++s) gelu_sum_chunks<TB>(tmem_base + lane_addr + as * ACC_COLS + s * TB, csum[s]);
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if constexpr (CG == 2) mbar_arrive_cluster(&acc_empty[as], 0); else mbar_arrive(&acc_empty[as]);
-            }
-#pragma unroll
-            for (int s = 0; s < CG; ++s) {
-              if (valid[s] > 0) {
-                const size_t blk = static_cast<size_t>(slot_block(block_map, item * CG + s, nslots, nblocks));
-#pragma unroll
-                for (int k = 0; k < NCH; ++k)
-                  part[(blk * NCH + k) * D + ft * Tr::MT + rank * 128 + row] = csum[s][k];
-              }
-            }
-            continue;
+          for (int s = 0; s < CG; ++s) gelu_sum_chunks<TB, CH>(tmem_base + lane_addr + as * ACC_COLS + s * TB, csum[s]);
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_cluster(&acc_empty[as], 0); else mbar_arrive(&acc_empty[as]);
           }
+#pragma unroll
+          for (int s = 0; s < CG; ++s) {
+            if (valid[s] > 0) {
+              const size_t blk = static_cast<size_t>(slot_block(block_map, item * CG + s, nslots, nblocks));
+#pragma unroll
+              for (int k = 0; k < NCH; ++k)
+                part[(blk * NCH + k) * D + ft * Tr::MT + rank * 128 + row] = csum[s][k];
+            }
+          }
+          continue;
         }
         float sums[CG];
 #pragma unroll
@@ -564,7 +570,6 @@ static cudaError_t launch_encode_t(const EncoderLaunch& a) {
   const int bpc = (a.T + Tr::TB - 1) / Tr::TB;
   int grid = a.num_sms;
   if (Tr::CG == 2) grid &= ~1;
-  if (a.chunked && (Tr::TB % 32 != 0)) return cudaErrorInvalidValue;
   const long long nblocks = static_cast<long long>(a.R) * bpc;
   if (nblocks > 0x7fffffffLL) return cudaErrorInvalidValue;
   const int nslots = a.block_map != nullptr ? a.nslots : static_cast<int>(nblocks);

@@ -94,24 +94,26 @@ cudaError_t launch_finalize(const float* part, const int32_t* lens, const Finali
 }
 
 // ------------------------------------------------------------------------------------------
-// Packed token stream for ragged batches: chunk c (32 token slots) of the stream takes chunk_n[c] ids from
+// Packed token stream for ragged batches: chunk c (`chunk` token slots) of the stream takes chunk_n[c] ids from
 // token_ids + chunk_src[c]; the rest of the chunk is padding (-1 -> zero embedding row -> GELU(0) = 0).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) qc_pack_tokens_kernel(const int32_t* __restrict__ token_ids,
                                                              const int32_t* __restrict__ chunk_src,
                                                              const int32_t* __restrict__ chunk_n,
-                                                             int32_t* __restrict__ packed, int nchunks) {
+                                                             int32_t* __restrict__ packed, int nchunks, int chunk) {
   const int idx = blockIdx.x * 256 + threadIdx.x;
-  const int c = idx >> 5, i = idx & 31;
+  const int c = idx / chunk, i = idx - c * chunk;
   if (c >= nchunks) return;
   packed[idx] = i < chunk_n[c] ? token_ids[static_cast<size_t>(chunk_src[c]) + i] : -1;
 }
 
 cudaError_t launch_pack_tokens(const int32_t* token_ids, const int32_t* chunk_src, const int32_t* chunk_n,
-                               int32_t* packed, int nchunks, cudaStream_t stream) {
+                               int32_t* packed, int nchunks, int chunk, cudaStream_t stream) {
   if (nchunks <= 0) return cudaSuccess;
-  const int blocks = (nchunks * 32 + 255) / 256;
-  qc_pack_tokens_kernel<<<blocks, 256, 0, stream>>>(token_ids, chunk_src, chunk_n, packed, nchunks);
+  const long long slots = static_cast<long long>(nchunks) * chunk;
+  if (slots > 0x7fffffffLL) return cudaErrorInvalidValue;
+  const int blocks = static_cast<int>((slots + 255) / 256);
+  qc_pack_tokens_kernel<<<blocks, 256, 0, stream>>>(token_ids, chunk_src, chunk_n, packed, nchunks, chunk);
   return cudaGetLastError();
 }
 

@@ -115,9 +115,9 @@ class Embeddings:
         uniq = list(todo.keys())
         chunk_lists = [chunk_text_by_tokens(t, self.limit) if tokenizer.count_tokens(t) > self.limit else [t] for t in uniq]
         flat = [c for cl in chunk_lists for c in cl]
-        ids, lens = tokenizer.pack(flat, self.vocab)
+        tokens, offsets = tokenizer.pack_ragged(flat, self.vocab)     # texts differ in length: CSR, nothing padded
         try:
-            emb = self.ctx.embed_batch(ids, lens)
+            emb = self.ctx.embed_ragged(tokens, offsets)
             self.gpu_calls += 1
         except QcError as e:
             for t in uniq:

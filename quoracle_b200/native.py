@@ -28,7 +28,7 @@ QC_PAD_TOKEN = -1
 ABI_SYMBOLS = (
     "qc_ctx_create", "qc_ctx_destroy", "qc_ctx_device", "qc_ctx_dim", "qc_ctx_synchronize",
     "qc_host_alloc", "qc_host_free",
-    "qc_decide_batch", "qc_decide_batch_submit", "qc_decide_batch_wait", "qc_embed_batch", "qc_similarity_batch", "qc_first_match_batch", "qc_chunk_mean",
+    "qc_decide_batch", "qc_embed_ragged", "qc_decide_ragged", "qc_decide_batch_submit", "qc_decide_batch_wait", "qc_embed_batch", "qc_similarity_batch", "qc_first_match_batch", "qc_chunk_mean",
     "qc_decide_batch_dev", "qc_embed_batch_dev", "qc_similarity_batch_dev",
     "qc_strerror", "qc_status_atom", "qc_abi_version",
     "qc_check_status", "qc_last_hang",
@@ -99,6 +99,10 @@ def load_library() -> ctypes.CDLL:
     lib.qc_embed_batch_dev.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.qc_similarity_batch_dev.restype = i32
     lib.qc_similarity_batch_dev.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.qc_embed_ragged.restype = i32
+    lib.qc_embed_ragged.argtypes = [vp, vp, vp, i32, vp]
+    lib.qc_decide_ragged.restype = i32
+    lib.qc_decide_ragged.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.qc_split_create.restype = i32
     lib.qc_split_create.argtypes = [vp, i32, i32, i32, i32, ctypes.POINTER(vp)]
     lib.qc_split_export.restype = i32
@@ -284,6 +288,33 @@ class Context:
         emb = np.empty((r, self.dim), np.float32)
         _check(self._lib.qc_embed_batch(self._h, _ptr(token_ids), _ptr(lens), r, t, _ptr(emb)))
         return emb
+
+    def embed_ragged(self, tokens: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+        """CSR form of embed_batch: candidate r is tokens[offsets[r]:offsets[r+1]]; nothing is padded."""
+        tokens = _as(tokens, np.int32).reshape(-1)
+        offsets = _as(offsets, np.int32).reshape(-1)
+        r = offsets.shape[0] - 1
+        emb = np.empty((r, self.dim), np.float32)
+        _check(self._lib.qc_embed_ragged(self._h, _ptr(tokens), _ptr(offsets), r, _ptr(emb)))
+        return emb
+
+    def decide_ragged(self, tokens: np.ndarray, offsets: np.ndarray, n: int, thr: np.ndarray, want_cos: bool = True,
+                      want_emb: bool = False) -> "DecideResult":
+        """CSR form of decide_batch: B = (len(offsets) - 1) / n decisions of n candidates each."""
+        tokens = _as(tokens, np.int32).reshape(-1)
+        offsets = _as(offsets, np.int32).reshape(-1)
+        r = offsets.shape[0] - 1
+        if r % n:
+            raise ValueError("len(offsets) - 1 must be a multiple of the pool size")
+        b = r // n
+        thr = _as(thr, np.float32).reshape(b)
+        res = DecideResult(np.empty(b, np.int32), np.empty(b, np.int32),
+                           np.empty((b, n, n), np.float32) if want_cos else None,
+                           np.empty((b, n, self.dim), np.float32) if want_emb else None)
+        _check(self._lib.qc_decide_ragged(self._h, _ptr(tokens), _ptr(offsets), b, int(n), _ptr(thr), _ptr(res.ref_ok),
+                                          _ptr(res.medoid), _ptr(res.cos) if want_cos else None,
+                                          _ptr(res.emb) if want_emb else None))
+        return res
 
     def similarity_batch(self, emb: np.ndarray, thr: np.ndarray, want_cos: bool = True):
         emb = _as(emb, np.float32)

@@ -43,3 +43,15 @@ def pack(texts: list[str], vocab: int = DEFAULT_VOCAB, max_tokens: int | None = 
         ids[i, : len(r)] = r
         lens[i] = len(r)
     return ids, lens
+
+
+def pack_ragged(texts: list[str], vocab: int = DEFAULT_VOCAB, max_tokens: int | None = None):
+    """-> (tokens [sum len] int32, offsets [R + 1] int32): the CSR form qc_embed_ragged / qc_decide_ragged take --
+    no padding is ever materialised, on the host or on the wire."""
+    rows = [tokenize(t, vocab) for t in texts]
+    if max_tokens is not None:
+        rows = [r[:max_tokens] for r in rows]
+    offsets = np.zeros(len(rows) + 1, dtype=np.int32)
+    np.cumsum([len(r) for r in rows], out=offsets[1:])
+    tokens = np.fromiter((t for r in rows for t in r), dtype=np.int32, count=int(offsets[-1]))
+    return tokens, offsets

@@ -16,6 +16,15 @@ class FakeContext:
         self.calls["embed"] += 1
         return oenc.encode(self.table, self.w, token_ids, lens).astype(np.float32)
 
+    def embed_ragged(self, tokens, offsets):
+        self.calls["embed"] += 1
+        lens = np.diff(offsets).astype(np.int32)
+        t = max(1, int(lens.max(initial=1)))
+        ids = np.full((len(lens), t), -1, np.int32)
+        for r, (o, n) in enumerate(zip(offsets[:-1], lens)):
+            ids[r, :n] = tokens[o:o + n]
+        return oenc.encode(self.table, self.w, ids, lens).astype(np.float32)
+
     def similarity_batch(self, emb, thr, want_cos=True):
         self.calls["similarity"] += 1
         ok, med, cos, _ = numeric.decide_batch(emb, np.asarray(thr, dtype=np.float64))

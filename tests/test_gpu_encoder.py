@@ -324,3 +324,45 @@ def test_packed_token_stream_matches_unpacked(dim, t):
             assert np.array_equal(a.emb, c2.emb)
         else:
             assert np.max(np.abs(a.emb - c2.emb)) < 1e-6
+
+
+@pytest.mark.parametrize("dim", [384, 768, 1536])
+def test_ragged_csr_entry_points(dim):
+    """qc_embed_ragged / qc_decide_ragged: candidates as a flat token array + offsets (nothing padded).  Checked
+    against the f64 oracle on the padded form and against qc_decide_batch on the same data; D = 1536 exercises the
+    8-token chunk variant of the packed stream (token block 56)."""
+    w = weights(dim, vocab=8192)
+    rng = np.random.default_rng(dim)
+    b, n, tmax = 20, 8, 300
+    lens = rng.integers(0, tmax + 1, size=b * n).astype(np.int32)
+    lens[:6] = (0, 1, 7, 8, 9, tmax)
+    offsets = np.zeros(b * n + 1, np.int32)
+    np.cumsum(lens, out=offsets[1:])
+    tokens = rng.integers(0, 8192, size=int(offsets[-1]), dtype=np.int32)
+    padded = np.full((b * n, tmax), -1, np.int32)
+    for r in range(b * n):
+        padded[r, :lens[r]] = tokens[offsets[r]:offsets[r + 1]]
+    thr = np.full(b, 0.9995, np.float32)
+    with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+        emb = ctx.embed_ragged(tokens, offsets)
+        want = oenc.encode(w.table_bf16, w.w_bf16, padded, lens)
+        assert np.max(np.abs(emb - want)) < EMB_TOL
+        assert np.all(emb[lens == 0] == 0.0)
+        res = ctx.decide_ragged(tokens, offsets, n, thr, want_cos=True, want_emb=True)
+        assert np.array_equal(res.emb.reshape(b * n, dim), emb)
+        ctx.set_packing(1)
+        ref = ctx.decide_batch(padded.reshape(b, n, tmax), lens.reshape(b, n), thr, want_cos=True, want_emb=True)
+        ctx.set_packing(0)
+        assert np.max(np.abs(res.emb - ref.emb)) < 1e-6 and np.max(np.abs(res.cos - ref.cos)) < 1e-5
+        o_ok, o_med, _, margins = numeric.decide_batch(want.reshape(b, n, dim), thr)
+        safe_t, safe_v = margins["thr"] > MARGIN, margins["vote"] > MARGIN
+        assert np.array_equal(res.ref_ok[safe_t], o_ok[safe_t]) and np.array_equal(res.medoid[safe_v], o_med[safe_v])
+        # offsets need not start at 0; an all-empty batch gives zero rows; a too-long candidate is refused
+        emb2 = ctx.embed_ragged(np.concatenate([np.full(5, 3, np.int32), tokens]), offsets + 5)
+        assert np.array_equal(emb2, emb)
+        assert np.all(ctx.embed_ragged(np.zeros(0, np.int32), np.zeros(4, np.int32)) == 0.0)
+        with pytest.raises(native.QcError) as e:
+            ctx.embed_ragged(np.zeros(9000, np.int32), np.array([0, 9000], np.int32))
+        assert e.value.atom == "context_length_exceeded"
+        with pytest.raises(native.QcError):
+            ctx.embed_ragged(tokens, offsets[::-1].copy())

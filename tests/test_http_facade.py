@@ -101,7 +101,7 @@ def test_context_length_maps_to_the_reference_atom():
     from quoracle_b200.native import QcError
 
     class TooLong(FakeContext):
-        def embed_batch(self, token_ids, lens):
+        def embed_ragged(self, tokens, offsets):
             raise QcError(-4, "too many tokens", "context_length_exceeded")
 
     w = synth.make_encoder(64, vocab=512, seed=3)
@@ -115,7 +115,7 @@ def test_context_length_maps_to_the_reference_atom():
 
 def test_device_failure_is_a_503_not_a_fallback():
     class Broken(FakeContext):
-        def embed_batch(self, token_ids, lens):
+        def embed_ragged(self, tokens, offsets):
             raise RuntimeError("libqconsensus.so is missing")
 
     w = synth.make_encoder(64, vocab=512, seed=3)
