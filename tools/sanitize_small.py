@@ -20,4 +20,25 @@ with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
     q = emb[:, 0]
     print(ctx.first_match_batch(q, emb, np.full(5, 0.9, np.float32))[0].tolist())
     print(ctx.chunk_mean(emb).shape)
+    # packed token stream (host entry point, forced), CSR entry points, tcgen05 K3 on a many-tile batch
+    ctx.set_variant(0, 0, 0, 0)
+    ctx.set_packing(2)
+    batch = synth.make_decisions(5, 8, 200, vocab=2048, seed=4, ragged=True)
+    r = ctx.decide_batch(batch.token_ids, batch.lens, batch.thr, want_cos=True, want_emb=True)
+    print("packed", r.medoid.tolist(), float(np.abs(r.emb).sum()))
+    ctx.set_packing(0)
+    lens = np.array([0, 1, 33, 200, 7, 64, 65, 128], np.int32)
+    off = np.zeros(9, np.int32)
+    np.cumsum(lens, out=off[1:])
+    toks = np.random.default_rng(1).integers(0, 2048, size=int(off[-1]), dtype=np.int32)
+    print("ragged", float(np.abs(ctx.embed_ragged(toks, off)).sum()),
+          ctx.decide_ragged(toks, off, 8, np.array([0.9], np.float32)).medoid.tolist())
+    for n, d in ((9, 100), (16, 384), (43, 96), (64, 128)):
+        e = synth.make_embeddings(40, n, d, seed=n)
+        print("tc", n, d, ctx.similarity_batch(e, np.full(40, 0.5, np.float32))[1][:4].tolist())
+w = synth.make_encoder(1536, vocab=2048, seed=2)
+with native.Context(0, w.table_bf16, w.w_bf16) as ctx:            # 56-token blocks: 8-token chunks
+    ctx.set_packing(2)
+    batch = synth.make_decisions(2, 4, 150, vocab=2048, seed=5, ragged=True)
+    print("packed 1536", ctx.decide_batch(batch.token_ids, batch.lens, batch.thr).medoid.tolist())
 print("sanitize run done")
