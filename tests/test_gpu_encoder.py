@@ -366,3 +366,35 @@ def test_ragged_csr_entry_points(dim):
         assert e.value.atom == "context_length_exceeded"
         with pytest.raises(native.QcError):
             ctx.embed_ragged(tokens, offsets[::-1].copy())
+
+
+def test_random_ragged_batches_against_the_oracle():
+    """Hypothesis sweep over candidate counts and lengths: the padded entry point (which picks dense walk, block
+    list or packed stream by itself) and the CSR entry point against the f64 oracle."""
+    from hypothesis import given, settings, strategies as st
+    w = weights(384, vocab=4096)
+    with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+
+        @settings(max_examples=30, deadline=None, derandomize=True)
+        @given(lens=st.lists(st.integers(0, 260), min_size=1, max_size=24), seed=st.integers(0, 2**31 - 1),
+               packing=st.sampled_from([0, 1, 2]))
+        def run(lens, seed, packing):
+            rng = np.random.default_rng(seed)
+            lens_a = np.array(lens, np.int32)
+            r, t = len(lens), max(1, int(lens_a.max()))
+            padded = np.full((r, t), -1, np.int32)
+            for i, n in enumerate(lens):
+                padded[i, :n] = rng.integers(0, 4096, size=n)
+            want = oenc.encode(w.table_bf16, w.w_bf16, padded, lens_a)
+            ctx.set_packing(packing)
+            got = ctx.embed_batch(padded, lens_a)
+            ctx.set_packing(0)
+            assert np.max(np.abs(got - want)) < EMB_TOL
+            off = np.zeros(r + 1, np.int32)
+            np.cumsum(lens_a, out=off[1:])
+            flat = np.concatenate([padded[i, :n] for i, n in enumerate(lens)]).astype(np.int32) if off[-1] else np.zeros(0, np.int32)
+            got2 = ctx.embed_ragged(flat, off)
+            assert np.max(np.abs(got2 - want)) < EMB_TOL
+            assert np.all(got2[lens_a == 0] == 0.0) and np.all(got[lens_a == 0] == 0.0)
+
+        run()

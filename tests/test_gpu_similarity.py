@@ -256,3 +256,35 @@ def test_full_size_properties(ctx, n, d, b):
     _, med_s, cos_s = ctx.similarity_batch(emb * scale, thr)
     assert np.max(np.abs(cos_s - cos)) < 2e-6
     assert np.array_equal(med_s[safe], med[safe])
+
+
+def test_random_shapes_against_the_oracle(ctx):
+    """Hypothesis sweep over (B, N, D), thresholds and awkward rows (zeros, exact duplicates, opposites, huge and
+    tiny norms) through every K3 kernel the dispatcher can pick (N <= 8, tcgen05, mma.sync fallback for D % 4 != 0)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(b=st.integers(1, 40), n=st.integers(1, 64), d=st.integers(1, 300), seed=st.integers(0, 2**31 - 1),
+           thr=st.sampled_from([-1.0, 0.0, 0.3, 0.85, 0.95, 1.0]))
+    def run(b, n, d, seed, thr):
+        rng = np.random.default_rng(seed)
+        emb = rng.standard_normal((b, n, d)).astype(np.float32)
+        emb *= rng.choice(np.array([1e-3, 1.0, 1e3], np.float32), size=(b, n, 1))
+        if n >= 2:
+            emb[::3, 1] = emb[::3, 0]                      # exact duplicate of the reference row
+        if n >= 3:
+            emb[1::3, 2] = -emb[1::3, 0]                   # exact opposite
+        if n >= 4:
+            emb[::4, 3] = 0.0                              # zero row -> cosines exactly 0
+        t = np.full(b, thr, np.float32)
+        ok, med, cos = ctx.similarity_batch(emb, t)
+        o_ok, o_med, o_cos, margins = numeric.decide_batch(emb, t)
+        assert np.all(np.isfinite(cos))
+        assert np.max(np.abs(cos - o_cos)) < TIGHT
+        if n >= 4:
+            assert np.all(cos[::4, 3, :] == 0.0)
+        safe_t, safe_v = margins["thr"] > MARGIN, margins["vote"] > MARGIN
+        assert np.array_equal(ok[safe_t], o_ok[safe_t])
+        assert np.array_equal(med[safe_v], o_med[safe_v])
+
+    run()
