@@ -22,6 +22,8 @@ defmodule Quoracle.Native do
   def ctx_create(_device, _vocab, _dim, _table_bf16, _w_bf16), do: :erlang.nif_error(:nif_not_loaded)
   def decide_batch(_ctx, _tok, _lens, _b, _n, _t, _thr, _want_cos), do: :erlang.nif_error(:nif_not_loaded)
   def embed_batch(_ctx, _tok, _lens, _r, _t), do: :erlang.nif_error(:nif_not_loaded)
+  def embed_ragged(_ctx, _tokens, _offsets), do: :erlang.nif_error(:nif_not_loaded)
+  def decide_ragged(_ctx, _tokens, _offsets, _n, _thr, _want_cos), do: :erlang.nif_error(:nif_not_loaded)
   def similarity_batch(_ctx, _emb, _b, _n, _d, _thr), do: :erlang.nif_error(:nif_not_loaded)
   def first_match_batch(_ctx, _query, _rows, _q, _m, _d, _thr), do: :erlang.nif_error(:nif_not_loaded)
   def chunk_mean(_ctx, _chunks, _g, _c, _d), do: :erlang.nif_error(:nif_not_loaded)
@@ -53,6 +55,22 @@ defmodule Quoracle.Native do
 
     lens = for toks <- token_lists, into: <<>>, do: <<length(toks)::little-signed-32>>
     {ids, lens, t}
+  end
+
+  @doc """
+  Pack token id lists into the CSR layout of `embed_ragged/3` / `decide_ragged/6`: `{tokens_bin, offsets_bin}`,
+  little-endian int32, offsets with one more entry than there are lists.  Nothing is padded.
+  """
+  def pack_ragged(token_lists) do
+    tokens = for toks <- token_lists, id <- toks, into: <<>>, do: <<id::little-signed-32>>
+
+    {offsets, _} =
+      Enum.reduce(token_lists, {<<0::little-signed-32>>, 0}, fn toks, {bin, acc} ->
+        acc = acc + length(toks)
+        {<<bin::binary, acc::little-signed-32>>, acc}
+      end)
+
+    {tokens, offsets}
   end
 
   defp floats(bin), do: for(<<f::little-float-32 <- bin>>, do: f)
@@ -115,12 +133,12 @@ defmodule Quoracle.Native do
       |> Enum.group_by(fn {{values, _}, _} -> length(values) end)
       |> Enum.flat_map(fn {n, group} ->
         texts = Enum.flat_map(group, fn {{values, _}, _} -> Enum.map(values, &stringify/1) end)
-        {ids, lens, t} = pack(Enum.map(texts, &tokenize/1))
+        {tokens, offsets} = pack_ragged(Enum.map(texts, &tokenize/1))
         thr = for {{_, th}, _} <- group, into: <<>>, do: <<th::little-float-32>>
-        b = length(group)
+        _ = dim
 
-        with {:ok, emb} <- embed_batch(ctx, ids, lens, b * n, t),
-             {:ok, ref_ok, _medoid, _cos} <- similarity_batch(ctx, emb, b, n, dim, thr) do
+        # one dirty-scheduler NIF entry per pool size: values of different lengths, nothing padded
+        with {:ok, ref_ok, _medoid, _cos} <- decide_ragged(ctx, tokens, offsets, n, thr, 0) do
           Enum.zip(group, ints(ref_ok))
           |> Enum.map(fn
             {{{[v0 | _], _}, i}, 1} -> {i, {:ok, v0}}

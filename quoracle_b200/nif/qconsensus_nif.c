@@ -114,6 +114,53 @@ static ERL_NIF_TERM nif_embed_batch(ErlNifEnv* env, int argc, const ERL_NIF_TERM
   return enif_make_tuple2(env, enif_make_atom(env, "ok"), emb_t);
 }
 
+/* embed_ragged(ctx, tokens :: binary (int32), offsets :: binary (int32, r + 1 entries))
+ *   -> {:ok, emb :: binary (r*dim f32)} | {:error, atom}
+ * The collector's natural form: values of different lengths, nothing padded (qc_embed_ragged). */
+static ERL_NIF_TERM nif_embed_ragged(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
+  qc_ctx* ctx;
+  ErlNifBinary tok, off;
+  if (argc != 3 || !get_ctx(env, argv[0], &ctx) || !enif_inspect_binary(env, argv[1], &tok) ||
+      !enif_inspect_binary(env, argv[2], &off))
+    return enif_make_badarg(env);
+  const int dim = qc_ctx_dim(ctx);
+  if (dim <= 0) return err(env, QC_ERR_NOT_CONFIGURED);
+  if (off.size < 4 || off.size % 4 != 0 || tok.size % 4 != 0) return err(env, QC_ERR_INVALID_INPUT);
+  const int r = (int)(off.size / 4) - 1;
+  const int32_t* offsets = (const int32_t*)off.data;
+  if (offsets[r] < 0 || (size_t)offsets[r] * 4 > tok.size) return err(env, QC_ERR_INVALID_INPUT);
+  ERL_NIF_TERM emb_t;
+  float* emb = (float*)enif_make_new_binary(env, (size_t)r * dim * 4, &emb_t);
+  int st = qc_embed_ragged(ctx, (const int32_t*)tok.data, offsets, r, emb);
+  if (st != QC_OK) return err(env, st);
+  return enif_make_tuple2(env, enif_make_atom(env, "ok"), emb_t);
+}
+
+/* decide_ragged(ctx, tokens, offsets, n, thr, want_cos :: 0 | 1)
+ *   -> {:ok, ref_ok :: binary, medoid :: binary, cos :: binary | nil} | {:error, atom} */
+static ERL_NIF_TERM nif_decide_ragged(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
+  qc_ctx* ctx;
+  ErlNifBinary tok, off, thr;
+  int n, want_cos;
+  if (argc != 6 || !get_ctx(env, argv[0], &ctx) || !enif_inspect_binary(env, argv[1], &tok) ||
+      !enif_inspect_binary(env, argv[2], &off) || !enif_get_int(env, argv[3], &n) ||
+      !enif_inspect_binary(env, argv[4], &thr) || !enif_get_int(env, argv[5], &want_cos))
+    return enif_make_badarg(env);
+  if (n < 1 || off.size < 4 || off.size % 4 != 0 || tok.size % 4 != 0) return err(env, QC_ERR_INVALID_INPUT);
+  const int r = (int)(off.size / 4) - 1;
+  if (r % n != 0) return err(env, QC_ERR_INVALID_INPUT);
+  const int b = r / n;
+  const int32_t* offsets = (const int32_t*)off.data;
+  if (thr.size != (size_t)b * 4 || offsets[r] < 0 || (size_t)offsets[r] * 4 > tok.size) return err(env, QC_ERR_INVALID_INPUT);
+  ERL_NIF_TERM ok_t, med_t, cos_t = enif_make_atom(env, "nil");
+  int32_t* ref_ok = (int32_t*)enif_make_new_binary(env, (size_t)b * 4, &ok_t);
+  int32_t* medoid = (int32_t*)enif_make_new_binary(env, (size_t)b * 4, &med_t);
+  float* cos = want_cos ? (float*)enif_make_new_binary(env, (size_t)b * n * n * 4, &cos_t) : NULL;
+  int st = qc_decide_ragged(ctx, (const int32_t*)tok.data, offsets, b, n, (const float*)thr.data, ref_ok, medoid, cos, NULL);
+  if (st != QC_OK) return err(env, st);
+  return enif_make_tuple4(env, enif_make_atom(env, "ok"), ok_t, med_t, cos_t);
+}
+
 /* similarity_batch(ctx, emb, b, n, d, thr) -> {:ok, ref_ok, medoid, cos} | {:error, atom} */
 static ERL_NIF_TERM nif_similarity_batch(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
   qc_ctx* ctx;
@@ -192,6 +239,8 @@ static ErlNifFunc nif_funcs[] = {
     {"ctx_create", 5, nif_ctx_create, ERL_NIF_DIRTY_JOB_CPU_BOUND},
     {"decide_batch", 8, nif_decide_batch, ERL_NIF_DIRTY_JOB_CPU_BOUND},
     {"embed_batch", 5, nif_embed_batch, ERL_NIF_DIRTY_JOB_CPU_BOUND},
+    {"embed_ragged", 3, nif_embed_ragged, ERL_NIF_DIRTY_JOB_CPU_BOUND},
+    {"decide_ragged", 6, nif_decide_ragged, ERL_NIF_DIRTY_JOB_CPU_BOUND},
     {"similarity_batch", 6, nif_similarity_batch, ERL_NIF_DIRTY_JOB_CPU_BOUND},
     {"first_match_batch", 7, nif_first_match_batch, ERL_NIF_DIRTY_JOB_CPU_BOUND},
     {"chunk_mean", 5, nif_chunk_mean, ERL_NIF_DIRTY_JOB_CPU_BOUND},
