@@ -73,7 +73,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock and throttle reasons sampled during the timed region: NVML every 10 ms when pynvml is usable,
+    else `nvidia-smi -lms 200`."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -83,8 +84,31 @@ class ClockSampler:
         self.lines: list[str] = []
         self.proc = None
         self.thread = None
+        self.nvml = None                 # (module, handle) when NVML is usable: 10 ms sampling, no subprocess
+        self.samples: list[tuple] = []
+        self._stop = threading.Event()
+
+    def _nvml_loop(self):
+        nv, h = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+            except Exception:
+                pass
+            self._stop.wait(0.01)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nvml = (nv, nv.nvmlDeviceGetHandleByIndex(self.index))
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -100,6 +124,15 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            sm = [x[0] for x in self.samples]
+            reasons = {name for x in self.samples for bit, name in bits.items() if x[2] & bit}
+            return {"sm_mhz": statistics.median(sm) if sm else None,
+                    "sm_max_mhz": max(x[1] for x in self.samples) if self.samples else None,
+                    "samples": len(sm), "reasons": sorted(reasons), "source": "nvml, 10 ms"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
