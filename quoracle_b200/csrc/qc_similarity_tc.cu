@@ -40,9 +40,13 @@ constexpr int kSplitWarps = 4 * kSplitGroups;
 constexpr int kTcThreads = (4 + kSplitWarps + 2) * 32;   // epilogue, splitters, TMA producer, MMA issuer
 constexpr int kChunkBytes = 128 * 128;       // 128 rows x 32 fp32
 // Shared memory: alignment slack, kStages x (raw 16 KB + lo 16 KB), two [128][kWin] fp32 windows, norms and row
-// means, barriers, over-read padding.  Pools <= 32 need narrower windows and get a fifth stage.
+// means, barriers.  Pools <= 32 need narrower windows and get a fifth stage.
+// The epilogue reads up to 7 entries past a decision's last column / row (blocks of 8, results discarded); those
+// reads must land in memory nobody writes, so each array they can run off carries its own tail: 7 extra window rows
+// after the HL window, 16 extra entries after the norms and after the row means.
+constexpr int kVecLen = 144;                 // 128 + over-read tail
 constexpr int tc_smem_bytes(int stages, int win) {
-  return 1024 + stages * 2 * kChunkBytes + 2 * 128 * win * 4 + 128 * 4 * 2 + 256 + 2560;
+  return 1024 + stages * 2 * kChunkBytes + (2 * 128 + 7) * win * 4 + 2 * kVecLen * 4 + 8 + 256;
 }
 
 // kind::tf32, fp32 accumulate, both operands K-major: c_format=1 (bit 4), a/b_format=2 (bits 7, 10), N>>3, M>>4
@@ -82,9 +86,10 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
   uint8_t* stages = smem;                                     // kStages x (raw 16 KB, lo 16 KB)
   float* whh = reinterpret_cast<float*>(stages + kStages * 2 * kChunkBytes);   // [128][kWin] HH window
   float* whl = whh + 128 * kWin;                                             // [128][kWin] HL window
-  float* diag = whl + 128 * kWin;                                            // [128] Gram diagonal
-  float* rmean = diag + 128;                                                 // [128] row means
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rmean + 128);
+  float* diag = whl + (128 + 7) * kWin;                                      // [128 + tail] reciprocal row norms
+  float* rmean = diag + kVecLen;                                             // [128 + tail] row means
+  // (263 * kWin + 288) floats precede this point: odd kWin leaves it 4-byte aligned, mbarriers need 8
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rmean + kVecLen + ((263 * kWin) & 1));
   uint64_t* raw_full = bars;                                  // TMA landed the raw tile
   uint64_t* lo_full = raw_full + kStages;                     // splitters wrote the lo tile
   uint64_t* stage_empty = lo_full + kStages;                  // the MMAs that read the stage retired
@@ -186,8 +191,8 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
         // consecutive lanes (consecutive r) then write consecutive addresses
         float* cos_col = cos != nullptr ? cos + static_cast<size_t>(b) * N * N + r : nullptr;
         // Blocks of 8 columns, all loads of a block issued before use (shared memory is kept busy by the MMA
-        // operand reads, so its latency is long here).  Loads past column N - 1 stay inside the padded
-        // shared-memory carve-up and their results are discarded.
+        // operand reads, so its latency is long here).  Loads past column N - 1 land in another row of the window
+        // or in the arrays' own never-written tails, and their results are discarded.
         for (int j0 = 0; j0 < N; j0 += 8) {
           float up[8], lr[8], lc[8], nj[8];
 #pragma unroll
@@ -219,7 +224,7 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
         for (int j0 = 1; j0 < N; j0 += 8) {
           float m[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) m[k] = rmean[i + j0 + k];   // over-reads land in the padding
+          for (int k = 0; k < 8; ++k) m[k] = rmean[i + j0 + k];   // over-reads land in rmean's own tail
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             if (j0 + k < N && m[k] > best_mean) {             // strict: ties keep the lowest index
