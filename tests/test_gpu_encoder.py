@@ -398,3 +398,33 @@ def test_random_ragged_batches_against_the_oracle():
             assert np.all(got2[lens_a == 0] == 0.0) and np.all(got[lens_a == 0] == 0.0)
 
         run()
+
+
+def test_contexts_release_their_device_memory():
+    """Create / use / destroy in a loop: device memory returns to where it started (weights, workspaces, pipeline
+    slots, packed-stream buffers, split-pool exchange objects)."""
+    import torch
+    w = weights(768, vocab=32768)
+    batch = synth.make_decisions(16, 8, 256, seed=1, ragged=True)
+    out = native.DecideResult(np.empty(16, np.int32), np.empty(16, np.int32), None, None)
+
+    def cycle():
+        with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+            ctx.decide_batch(batch.token_ids, batch.lens, batch.thr)
+            for slot in range(4):
+                ctx.decide_batch_submit(slot, batch.token_ids, batch.lens, batch.thr, out)
+                ctx.decide_batch_wait(slot)
+            ctx.similarity_batch(synth.make_embeddings(64, 16, 256, seed=2), np.full(64, 0.5, np.float32))
+            sp = ctx.split_pool(1, 0, 16, 8)
+            ts = ctx.token_split(1, 0, 128)
+            sp.close()
+            ts.close()
+
+    cycle()
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info(0)
+    for _ in range(8):
+        cycle()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info(0)
+    assert free0 - free1 < 32 * 2**20, f"leaked {(free0 - free1) / 2**20:.1f} MiB over 8 context lifetimes"
