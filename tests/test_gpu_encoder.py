@@ -428,3 +428,35 @@ def test_contexts_release_their_device_memory():
     torch.cuda.synchronize()
     free1, _ = torch.cuda.mem_get_info(0)
     assert free0 - free1 < 32 * 2**20, f"leaked {(free0 - free1) / 2**20:.1f} MiB over 8 context lifetimes"
+
+
+def test_two_contexts_on_one_gpu_from_two_threads():
+    """Two host threads, each with its own context on the same GPU (a context is single-caller; processes that want
+    concurrency make more contexts): interleaved K1 / K3 launches from both give the single-threaded results."""
+    import threading
+    w = weights(768, vocab=32768)
+    batches = [synth.make_decisions(24, 8, 384, seed=100 + i, ragged=(i % 2 == 0)) for i in range(6)]
+    pools = [synth.make_embeddings(200, 16, 256, seed=i) for i in range(6)]
+    with native.Context(0, w.table_bf16, w.w_bf16) as ref:
+        want = [ref.decide_batch(x.token_ids, x.lens, x.thr, want_cos=True) for x in batches]
+        want_sim = [ref.similarity_batch(p, np.full(200, 0.5, np.float32)) for p in pools]
+    errors = []
+
+    def worker(order):
+        try:
+            with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+                for _ in range(3):
+                    for i in order:
+                        r = ctx.decide_batch(batches[i].token_ids, batches[i].lens, batches[i].thr, want_cos=True)
+                        assert np.array_equal(r.cos, want[i].cos) and np.array_equal(r.medoid, want[i].medoid)
+                        s = ctx.similarity_batch(pools[i], np.full(200, 0.5, np.float32))
+                        assert np.array_equal(s[2], want_sim[i][2])
+        except Exception as e:                                   # noqa: BLE001 - reported to the main thread
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(o,)) for o in ([0, 1, 2, 3, 4, 5], [5, 4, 3, 2, 1, 0])]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
