@@ -35,7 +35,10 @@
  *     status maps 1:1 to the Elixir error atom the reference uses on this path
  *     (lib/quoracle/models/embeddings.ex:49-50,184,228-229,300-331,344).
  *   - A context is bound to ONE device (one process per GPU); calls on one context
- *     are serialised by the caller.  No globals, no CPU fallback: every entry point
+ *     are serialised by the caller (one host thread at a time).  The WORK of `_dev`
+ *     calls enqueued on different streams may overlap on the GPU: each caller stream
+ *     (up to four at a time) gets its own K1->K2 partial-sum and embedding scratch.
+ *     No globals, no CPU fallback: every entry point
  *     fails with QC_ERR_NO_DEVICE when no sm_100 device is usable.
  *   - Zero-norm vectors give cosine 0.0 (never NaN), as both reference cosines do
  *     (consensus_rules.ex:205-209, aggregator.ex:343-347).

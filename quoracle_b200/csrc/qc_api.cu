@@ -77,6 +77,15 @@ struct Slot {
   bool busy = false;
 };
 
+// Workspaces of the device entry points, one set per caller stream (up to four): launches enqueued on different
+// streams may overlap on the GPU, so they must not share the K1 -> K2 partial-sum buffer or the embedding scratch.
+struct StreamWs {
+  cudaStream_t s = nullptr;
+  bool used = false;
+  unsigned long long tick = 0;
+  DevBuf part, emb;
+};
+
 }  // namespace
 
 struct qc_ctx {
@@ -92,6 +101,8 @@ struct qc_ctx {
   int hint_nslots = 0;
   DevBuf map, packed;
   HostBuf h_map;
+  StreamWs ws[4];
+  unsigned long long ws_tick = 0;
   // packed token stream of the NEXT encode_dev call (ragged batches; same life cycle as hint_map)
   const int32_t* hint_chunk_src = nullptr;
   const int32_t* hint_chunk_n = nullptr;
@@ -280,6 +291,30 @@ size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
 // (cand * bpc + j, in order) and K1 walks that list instead of skipping: no CTA pair runs half empty.  Batches
 // without an empty block need no list (dense enumeration is the same walk).  The list rides to the device on
 // the call's own stream through a pinned staging buffer that stays untouched until the call is waited for.
+StreamWs* ws_for(qc_ctx* c, cudaStream_t s) {
+  for (StreamWs& w : c->ws)
+    if (w.used && w.s == s) {
+      w.tick = ++c->ws_tick;
+      return &w;
+    }
+  for (StreamWs& w : c->ws)
+    if (!w.used) {
+      w.used = true;
+      w.s = s;
+      w.tick = ++c->ws_tick;
+      return &w;
+    }
+  // all sets taken: recycle the least recently used one once its stream has drained (a stream the caller has
+  // destroyed meanwhile reports an error here, which only means there is nothing left to wait for)
+  StreamWs* lru = &c->ws[0];
+  for (StreamWs& w : c->ws)
+    if (w.tick < lru->tick) lru = &w;
+  if (cudaStreamSynchronize(lru->s) != cudaSuccess) cudaGetLastError();
+  lru->s = s;
+  lru->tick = ++c->ws_tick;
+  return lru;
+}
+
 int stage_block_map(qc_ctx* c, const int32_t* lens, int R, int T, DevBuf* dmap, HostBuf* hmap, DevBuf* dpacked,
                     cudaStream_t s) {
   c->hint_map = nullptr;
@@ -373,7 +408,7 @@ struct HintGuard {
 int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, int T, float* d_emb, cudaStream_t s,
                DevBuf* part_buf = nullptr, const qc::FinalizeDst* scatter = nullptr,
                const qc::TsplitDst* tsplit = nullptr) {
-  DevBuf& part = part_buf ? *part_buf : c->part;
+  DevBuf& part = part_buf ? *part_buf : ws_for(c, s)->part;
   if (!c->variant_forced && !c->hint_variant_set) c->variant = qc::encoder_auto_variant(c->dim, T);
   c->hint_variant_set = false;
   const int TB = c->variant.token_block;
@@ -585,6 +620,10 @@ void qc_ctx_destroy(qc_ctx* c) {
   c->idx.release();
   c->stall.release();
   c->map.release();
+  for (StreamWs& w : c->ws) {
+    w.part.release();
+    w.emb.release();
+  }
   c->packed.release();
   c->h_map.release();
   for (Slot& sl : c->slots) {
@@ -814,8 +853,9 @@ int qc_decide_batch_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, 
   const int R = B * N;
   float* emb = d_emb;
   if (emb == nullptr) {
-    QC_CUDA(c->emb.ensure(static_cast<size_t>(R) * c->dim * sizeof(float)));
-    emb = static_cast<float*>(c->emb.p);
+    DevBuf& scratch = ws_for(c, s)->emb;
+    QC_CUDA(scratch.ensure(static_cast<size_t>(R) * c->dim * sizeof(float)));
+    emb = static_cast<float*>(scratch.p);
   }
   int st = encode_dev(c, d_tok, d_lens, R, T, emb, s);
   if (st != QC_OK) return st;
@@ -1189,8 +1229,9 @@ int qc_decide_tsplit_dev(qc_ctx* c, qc_split* sp, const int32_t* d_tok, const in
   float* emb = d_emb;
   if (emb == nullptr) {
     DeviceGuard g(c->device);
-    QC_CUDA(c->emb.ensure(static_cast<size_t>(B) * N * c->dim * sizeof(float)));
-    emb = static_cast<float*>(c->emb.p);
+    DevBuf& scratch = ws_for(c, stream ? static_cast<cudaStream_t>(stream) : c->stream)->emb;
+    QC_CUDA(scratch.ensure(static_cast<size_t>(B) * N * c->dim * sizeof(float)));
+    emb = static_cast<float*>(scratch.p);
   }
   int st = qc_embed_tsplit_dev(c, sp, d_tok, d_lens, B * N, T_local, emb, stream);
   if (st != QC_OK) return st;

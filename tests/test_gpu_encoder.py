@@ -460,3 +460,37 @@ def test_two_contexts_on_one_gpu_from_two_threads():
     for t in threads:
         t.join(timeout=300)
     assert not errors, errors
+
+
+def test_device_calls_on_different_streams_do_not_share_scratch():
+    """`_dev` launches enqueued on different caller streams may overlap on the GPU; each stream gets its own
+    K1->K2 partial sums and embedding scratch, so results equal the one-stream results (six streams also force
+    the recycling of a workspace set)."""
+    import torch
+    w = weights(768, vocab=32768)
+    dev = torch.device("cuda:0")
+    b, n, t = 48, 8, 384
+    batches = [synth.make_decisions(b, n, t, seed=200 + i, ragged=(i % 2 == 1)) for i in range(6)]
+    with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+        want = [ctx.decide_batch(x.token_ids, x.lens, x.thr, want_cos=True) for x in batches]
+        d_tok = [torch.from_numpy(x.token_ids).to(dev) for x in batches]
+        d_len = [torch.from_numpy(x.lens).to(dev) for x in batches]
+        d_thr = [torch.from_numpy(x.thr).to(dev) for x in batches]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(6)]
+        outs = [(torch.empty(b, dtype=torch.int32, device=dev), torch.empty(b, dtype=torch.int32, device=dev),
+                 torch.empty((b, n, n), dtype=torch.float32, device=dev)) for _ in range(6)]
+        ctx.set_packing(1)
+        ref = [ctx.decide_batch(x.token_ids, x.lens, x.thr, want_cos=True) for x in batches]   # unpacked reference bits
+        ctx.set_packing(0)
+        torch.cuda.synchronize()
+        for rep in range(3):
+            for i in range(6):                                   # enqueue everything, synchronise once
+                ok, med, cos = outs[i]
+                ctx.decide_batch_dev(d_tok[i].data_ptr(), d_len[i].data_ptr(), b, n, t, d_thr[i].data_ptr(),
+                                     ok.data_ptr(), med.data_ptr(), cos.data_ptr(), 0, streams[i].cuda_stream)
+            torch.cuda.synchronize()
+            ctx.check_status()
+            for i in range(6):
+                assert np.array_equal(outs[i][2].cpu().numpy(), ref[i].cos), (rep, i)
+                assert np.array_equal(outs[i][1].cpu().numpy(), ref[i].medoid)
+        del want
