@@ -144,6 +144,9 @@ int qc_decide_batch_wait(qc_ctx* ctx, int slot);
 int qc_embed_ragged(qc_ctx* ctx, const int32_t* tokens, const int32_t* offsets, int R, float* out_emb);
 int qc_decide_ragged(qc_ctx* ctx, const int32_t* tokens, const int32_t* offsets, int B, int N, const float* thr,
                      int32_t* out_ref_ok, int32_t* out_medoid, float* out_cos, float* out_emb);
+/* Pipelined form (slots and qc_decide_batch_wait as for qc_decide_batch_submit; buffers stay untouched until wait). */
+int qc_decide_ragged_submit(qc_ctx* ctx, int slot, const int32_t* tokens, const int32_t* offsets, int B, int N,
+                            const float* thr, int32_t* out_ref_ok, int32_t* out_medoid, float* out_cos);
 
 /* Embedding only: R candidate rows -> out_emb [R*dim] f32 (what an `:embedding_fn` returns). */
 int qc_embed_batch(qc_ctx* ctx, const int32_t* token_ids, const int32_t* lens, int R, int T,

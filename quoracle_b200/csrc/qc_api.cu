@@ -901,23 +901,40 @@ int qc_embed_batch(qc_ctx* c, const int32_t* token_ids, const int32_t* lens, int
 // tokens of candidate r are tokens[offsets[r] .. offsets[r+1]).  The flat array goes to the device as is; the packed
 // token stream (chunks of every candidate laid end to end) is built from it by the pack kernel, so the only padding
 // K1 ever sees is inside each candidate's last chunk.
-static int ragged_common(qc_ctx* c, const int32_t* tokens, const int32_t* offsets, int R, float* d_emb, cudaStream_t s) {
+struct RaggedBufs {           // the context's own buffers (synchronous calls) or one pipeline slot's
+  DevBuf* tok;
+  DevBuf* lens;
+  DevBuf* map;
+  DevBuf* packed;
+  DevBuf* part;
+  HostBuf* h_in;
+  HostBuf* h_map;
+};
+
+static int ragged_common(qc_ctx* c, const RaggedBufs& wb, const int32_t* tokens, const int32_t* offsets, int R,
+                         float* d_emb, cudaStream_t s) {
   const long long total = offsets[R];
-  std::vector<int32_t> lens(static_cast<size_t>(R));
+  const size_t tokb = static_cast<size_t>(total > 0 ? total : 1) * 4, lenb = static_cast<size_t>(R) * 4;
+  QC_CUDA(wb.tok->ensure(tokb));
+  QC_CUDA(wb.lens->ensure(lenb));
+  QC_CUDA(wb.h_in->ensure(pad256(tokb) + pad256(lenb)));
+  // lengths are built straight into the pinned staging area (it stays untouched until the call is waited for)
+  int32_t* lens = reinterpret_cast<int32_t*>(static_cast<char*>(wb.h_in->p) + pad256(tokb));
   for (int r = 0; r < R; ++r) {
     const long long l = static_cast<long long>(offsets[r + 1]) - offsets[r];
     if (offsets[r] < 0 || l < 0) return QC_ERR_INVALID_INPUT;
     if (l > QC_MAX_TOKENS) return QC_ERR_CONTEXT_LENGTH;
-    lens[static_cast<size_t>(r)] = static_cast<int32_t>(l);
+    lens[r] = static_cast<int32_t>(l);
   }
-  const size_t tokb = static_cast<size_t>(total > 0 ? total : 1) * 4, lenb = static_cast<size_t>(R) * 4;
-  QC_CUDA(c->tok.ensure(tokb));
-  QC_CUDA(c->lens.ensure(lenb));
-  QC_CUDA(c->h_in.ensure(pad256(tokb) + pad256(lenb)));
-  size_t off = 0;
-  int st;
-  if (total > 0 && (st = h2d(c, c->tok.p, tokens, static_cast<size_t>(total) * 4, &off)) != QC_OK) return st;
-  if ((st = h2d(c, c->lens.p, lens.data(), lenb, &off)) != QC_OK) return st;
+  if (total > 0) {
+    const void* src = tokens;
+    if (!is_pinned(tokens)) {
+      memcpy(wb.h_in->p, tokens, static_cast<size_t>(total) * 4);
+      src = wb.h_in->p;
+    }
+    QC_CUDA(cudaMemcpyAsync(wb.tok->p, src, static_cast<size_t>(total) * 4, cudaMemcpyHostToDevice, s));
+  }
+  QC_CUDA(cudaMemcpyAsync(wb.lens->p, lens, lenb, cudaMemcpyHostToDevice, s));
   if (total == 0) {                                            // nothing to encode: zero rows
     QC_CUDA(cudaMemsetAsync(d_emb, 0, static_cast<size_t>(R) * c->dim * 4, s));
     return QC_OK;
@@ -926,19 +943,19 @@ static int ragged_common(qc_ctx* c, const int32_t* tokens, const int32_t* offset
   const qc::EncoderVariant vp = c->variant_forced ? c->variant : qc::encoder_default_variant(c->dim);
   const int CH = qc::encoder_chunk_tokens(vp.token_block), nch = vp.token_block / CH;
   long long chunks = 0;
-  for (int r = 0; r < R; ++r) chunks += (lens[static_cast<size_t>(r)] + CH - 1) / CH;
+  for (int r = 0; r < R; ++r) chunks += (lens[r] + CH - 1) / CH;
   const long long nchunks = (chunks + nch - 1) / nch * nch;
   if (nchunks * CH > 0x7fffffffLL) return QC_ERR_UNSUPPORTED;
   const size_t ints = static_cast<size_t>(2 * nchunks + R + 1);
-  QC_CUDA(c->h_map.ensure(ints * sizeof(int32_t)));
-  QC_CUDA(c->map.ensure(ints * sizeof(int32_t)));
-  int32_t* src = static_cast<int32_t*>(c->h_map.p);
+  QC_CUDA(wb.h_map->ensure(ints * sizeof(int32_t)));
+  QC_CUDA(wb.map->ensure(ints * sizeof(int32_t)));
+  int32_t* src = static_cast<int32_t*>(wb.h_map->p);
   int32_t* cnt = src + nchunks;
   int32_t* row = cnt + nchunks;
   long long k = 0;
   for (int r = 0; r < R; ++r) {
     row[r] = static_cast<int32_t>(k);
-    const int len = lens[static_cast<size_t>(r)];
+    const int len = lens[r];
     for (int o = 0; o < len; o += CH) {
       src[k] = offsets[r] + o;
       cnt[k] = len - o < CH ? len - o : CH;
@@ -950,18 +967,23 @@ static int ragged_common(qc_ctx* c, const int32_t* tokens, const int32_t* offset
     src[k] = 0;
     cnt[k] = 0;
   }
-  QC_CUDA(cudaMemcpyAsync(c->map.p, src, ints * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  QC_CUDA(cudaMemcpyAsync(wb.map->p, src, ints * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   HintGuard hg(c);
-  const int32_t* d = static_cast<const int32_t*>(c->map.p);
+  const int32_t* d = static_cast<const int32_t*>(wb.map->p);
   c->variant = vp;
   c->hint_variant_set = true;
   c->hint_chunk_src = d;
   c->hint_chunk_n = d + nchunks;
   c->hint_row_start = d + 2 * nchunks;
   c->hint_nchunks = static_cast<int>(nchunks);
-  c->hint_packed_buf = &c->packed;
+  c->hint_packed_buf = wb.packed;
   // T only sizes the dense walk, which the pack hint replaces
-  return encode_dev(c, static_cast<int32_t*>(c->tok.p), static_cast<int32_t*>(c->lens.p), R, vp.token_block, d_emb, s);
+  return encode_dev(c, static_cast<int32_t*>(wb.tok->p), static_cast<int32_t*>(wb.lens->p), R, vp.token_block, d_emb, s,
+                    wb.part);
+}
+
+static RaggedBufs ctx_ragged_bufs(qc_ctx* c) {
+  return RaggedBufs{&c->tok, &c->lens, &c->map, &c->packed, nullptr, &c->h_in, &c->h_map};
 }
 
 int qc_embed_ragged(qc_ctx* c, const int32_t* tokens, const int32_t* offsets, int R, float* out_emb) {
@@ -973,7 +995,7 @@ int qc_embed_ragged(qc_ctx* c, const int32_t* tokens, const int32_t* offsets, in
   const size_t embb = static_cast<size_t>(R) * c->dim * 4;
   QC_CUDA(c->emb.ensure(embb));
   QC_CUDA(c->h_out.ensure(pad256(embb)));
-  int st = ragged_common(c, tokens, offsets, R, static_cast<float*>(c->emb.p), c->stream);
+  int st = ragged_common(c, ctx_ragged_bufs(c), tokens, offsets, R, static_cast<float*>(c->emb.p), c->stream);
   if (st != QC_OK) return st;
   std::vector<PendingOut> pend;
   size_t ooff = 0;
@@ -1000,7 +1022,7 @@ int qc_decide_ragged(qc_ctx* c, const int32_t* tokens, const int32_t* offsets, i
   QC_CUDA(c->medoid.ensure(ib));
   if (out_cos) QC_CUDA(c->cosm.ensure(cosb));
   QC_CUDA(c->h_out.ensure(2 * pad256(ib) + pad256(cosb) + pad256(embb)));
-  int st = ragged_common(c, tokens, offsets, R, static_cast<float*>(c->emb.p), c->stream);
+  int st = ragged_common(c, ctx_ragged_bufs(c), tokens, offsets, R, static_cast<float*>(c->emb.p), c->stream);
   if (st != QC_OK) return st;
   // thr rides after the tokens: stage it through its own small pinned copy on the same stream
   QC_CUDA(cudaMemcpyAsync(c->thr.p, thr, thrb, cudaMemcpyHostToDevice, c->stream));
@@ -1367,6 +1389,65 @@ int qc_decide_batch_submit(qc_ctx* c, int slot, const int32_t* token_ids, const 
   st = encode_dev(c, static_cast<int32_t*>(sl.tok.p), static_cast<int32_t*>(sl.lens.p), R, T,
                   static_cast<float*>(sl.emb.p), sl.stream, &sl.part);
   if (st != QC_OK) return st;
+  st = qc_similarity_batch_dev(c, static_cast<float*>(sl.emb.p), B, N, c->dim, static_cast<float*>(sl.thr.p),
+                               static_cast<int32_t*>(sl.refok.p), static_cast<int32_t*>(sl.medoid.p),
+                               out_cos ? static_cast<float*>(sl.cosm.p) : nullptr, sl.stream);
+  if (st != QC_OK) return st;
+  sl.pend.clear();
+  size_t ooff = 0;
+  auto outc = [&](void* user, const void* dsrc, size_t bytes) -> int {
+    if (user == nullptr || bytes == 0) return QC_OK;
+    if (is_pinned(user)) {
+      QC_CUDA(cudaMemcpyAsync(user, dsrc, bytes, cudaMemcpyDeviceToHost, sl.stream));
+    } else {
+      char* stg = static_cast<char*>(sl.h_out.p) + ooff;
+      ooff += pad256(bytes);
+      QC_CUDA(cudaMemcpyAsync(stg, dsrc, bytes, cudaMemcpyDeviceToHost, sl.stream));
+      sl.pend.push_back({user, stg, bytes});
+    }
+    return QC_OK;
+  };
+  if ((st = outc(out_ref_ok, sl.refok.p, ib)) != QC_OK) return st;
+  if ((st = outc(out_medoid, sl.medoid.p, ib)) != QC_OK) return st;
+  if ((st = outc(out_cos, sl.cosm.p, cosb)) != QC_OK) return st;
+  QC_CUDA(cudaMemcpyAsync(sl.h_flags.p, c->d_err, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+  sl.busy = true;
+  return QC_OK;
+}
+
+int qc_decide_ragged_submit(qc_ctx* c, int slot, const int32_t* tokens, const int32_t* offsets, int B, int N,
+                            const float* thr, int32_t* out_ref_ok, int32_t* out_medoid, float* out_cos) {
+  if (c == nullptr || slot < 0 || slot >= QC_PIPELINE_SLOTS || offsets == nullptr || thr == nullptr || B < 1)
+    return QC_ERR_INVALID_INPUT;
+  if (N < 1 || N > QC_MAX_POOL) return QC_ERR_UNSUPPORTED;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  Slot& sl = c->slots[slot];
+  if (sl.busy) return QC_ERR_INVALID_INPUT;   // the previous batch in this slot has not been waited for
+  const int R = B * N;
+  if (offsets[R] < 0 || (offsets[R] > 0 && tokens == nullptr)) return QC_ERR_INVALID_INPUT;
+  DeviceGuard g(c->device);
+  if (sl.stream == nullptr) QC_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+  const size_t thrb = static_cast<size_t>(B) * 4, ib = static_cast<size_t>(B) * 4;
+  const size_t embb = static_cast<size_t>(R) * c->dim * 4, cosb = static_cast<size_t>(B) * N * N * 4;
+  QC_CUDA(sl.thr.ensure(thrb));
+  QC_CUDA(sl.emb.ensure(embb));
+  QC_CUDA(sl.refok.ensure(ib));
+  QC_CUDA(sl.medoid.ensure(ib));
+  if (out_cos) QC_CUDA(sl.cosm.ensure(cosb));
+  QC_CUDA(sl.h_out.ensure(2 * pad256(ib) + pad256(cosb) + pad256(thrb)));
+  QC_CUDA(sl.h_flags.ensure(8 * sizeof(int32_t)));
+  const RaggedBufs wb{&sl.tok, &sl.lens, &sl.map, &sl.packed, &sl.part, &sl.h_in, &sl.h_map};
+  int st = ragged_common(c, wb, tokens, offsets, R, static_cast<float*>(sl.emb.p), sl.stream);
+  if (st != QC_OK) return st;
+  {  // thresholds: staged at the tail of the slot's pinned output area unless the caller's buffer is pinned
+    const void* src = thr;
+    if (!is_pinned(thr)) {
+      char* stg = static_cast<char*>(sl.h_out.p) + 2 * pad256(ib) + pad256(cosb);
+      memcpy(stg, thr, thrb);
+      src = stg;
+    }
+    QC_CUDA(cudaMemcpyAsync(sl.thr.p, src, thrb, cudaMemcpyHostToDevice, sl.stream));
+  }
   st = qc_similarity_batch_dev(c, static_cast<float*>(sl.emb.p), B, N, c->dim, static_cast<float*>(sl.thr.p),
                                static_cast<int32_t*>(sl.refok.p), static_cast<int32_t*>(sl.medoid.p),
                                out_cos ? static_cast<float*>(sl.cosm.p) : nullptr, sl.stream);

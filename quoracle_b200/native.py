@@ -28,7 +28,7 @@ QC_PAD_TOKEN = -1
 ABI_SYMBOLS = (
     "qc_ctx_create", "qc_ctx_destroy", "qc_ctx_device", "qc_ctx_dim", "qc_ctx_synchronize",
     "qc_host_alloc", "qc_host_free",
-    "qc_decide_batch", "qc_embed_ragged", "qc_decide_ragged", "qc_decide_batch_submit", "qc_decide_batch_wait", "qc_embed_batch", "qc_similarity_batch", "qc_first_match_batch", "qc_chunk_mean",
+    "qc_decide_batch", "qc_embed_ragged", "qc_decide_ragged", "qc_decide_ragged_submit", "qc_decide_batch_submit", "qc_decide_batch_wait", "qc_embed_batch", "qc_similarity_batch", "qc_first_match_batch", "qc_chunk_mean",
     "qc_decide_batch_dev", "qc_embed_batch_dev", "qc_similarity_batch_dev",
     "qc_strerror", "qc_status_atom", "qc_abi_version",
     "qc_check_status", "qc_last_hang",
@@ -101,6 +101,8 @@ def load_library() -> ctypes.CDLL:
     lib.qc_similarity_batch_dev.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.qc_embed_ragged.restype = i32
     lib.qc_embed_ragged.argtypes = [vp, vp, vp, i32, vp]
+    lib.qc_decide_ragged_submit.restype = i32
+    lib.qc_decide_ragged_submit.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp, vp, vp]
     lib.qc_decide_ragged.restype = i32
     lib.qc_decide_ragged.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.qc_split_create.restype = i32
@@ -277,6 +279,16 @@ class Context:
                 raise ValueError("submit needs C-contiguous arrays of the exact dtype (they are read asynchronously)")
         _check(self._lib.qc_decide_batch_submit(self._h, int(slot), _ptr(token_ids), _ptr(lens), b, n, t, _ptr(thr),
                                                 _ptr(out.ref_ok), _ptr(out.medoid), _ptr(out.cos)))
+
+    def decide_ragged_submit(self, slot: int, tokens: np.ndarray, offsets: np.ndarray, n: int, thr: np.ndarray,
+                             out: "DecideResult") -> None:
+        """Pipelined CSR form; arrays must be C-contiguous and stay alive and untouched until ``decide_batch_wait``."""
+        for a, dt in ((tokens, np.int32), (offsets, np.int32), (thr, np.float32), (out.ref_ok, np.int32), (out.medoid, np.int32)):
+            if a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("pipelined calls take C-contiguous arrays of the exact dtype (no copies are made)")
+        b = (offsets.shape[0] - 1) // int(n)
+        _check(self._lib.qc_decide_ragged_submit(self._h, int(slot), _ptr(tokens), _ptr(offsets), b, int(n), _ptr(thr),
+                                                 _ptr(out.ref_ok), _ptr(out.medoid), _ptr(out.cos)))
 
     def decide_batch_wait(self, slot: int) -> None:
         _check(self._lib.qc_decide_batch_wait(self._h, int(slot)))

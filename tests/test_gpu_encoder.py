@@ -357,6 +357,17 @@ def test_ragged_csr_entry_points(dim):
         o_ok, o_med, _, margins = numeric.decide_batch(want.reshape(b, n, dim), thr)
         safe_t, safe_v = margins["thr"] > MARGIN, margins["vote"] > MARGIN
         assert np.array_equal(res.ref_ok[safe_t], o_ok[safe_t]) and np.array_equal(res.medoid[safe_v], o_med[safe_v])
+        # pipelined CSR form over all four slots
+        outs = [native.DecideResult(np.empty(b, np.int32), np.empty(b, np.int32), np.empty((b, n, n), np.float32), None)
+                for _ in range(6)]
+        for i in range(6):
+            if i >= 4:
+                ctx.decide_batch_wait(i % 4)
+            ctx.decide_ragged_submit(i % 4, tokens, offsets, n, thr, outs[i])
+        for i in range(2, 6):
+            ctx.decide_batch_wait(i % 4)
+        for o in outs:
+            assert np.array_equal(o.cos, res.cos) and np.array_equal(o.medoid, res.medoid) and np.array_equal(o.ref_ok, res.ref_ok)
         # offsets need not start at 0; an all-empty batch gives zero rows; a too-long candidate is refused
         emb2 = ctx.embed_ragged(np.concatenate([np.full(5, 3, np.int32), tokens]), offsets + 5)
         assert np.array_equal(emb2, emb)

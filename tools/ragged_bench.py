@@ -81,6 +81,34 @@ def main():
         print(f"{name:36s} {dt / 200 * 1e3:.4f} ms/step  {200 * b / dt:9.0f} decisions/s  "
               f"{flops * 200 / dt / 1e12:7.1f} TFLOP/s on valid tokens")
     ctx.set_packing(0)
+    # CSR entry point, pipelined: nothing padded on the host or on the wire
+    csr = []
+    for x in batches:
+        lens = x.lens.reshape(-1)
+        off = np.zeros(lens.shape[0] + 1, np.int32)
+        np.cumsum(lens, out=off[1:])
+        flat = np.concatenate([x.token_ids.reshape(-1, t)[r, :lens[r]] for r in range(lens.shape[0])]).astype(np.int32)
+        pt, po, pth = native.PinnedArray(flat.shape, np.int32), native.PinnedArray(off.shape, np.int32), native.PinnedArray((b,), np.float32)
+        pt.array[...], po.array[...], pth.array[...] = flat, off, x.thr
+        csr.append((pt, po, pth))
+
+    def csr_pipeline(steps):
+        for i in range(steps):
+            k = i % 4
+            if i >= 4:
+                ctx.decide_batch_wait(k)
+            pt, po, pth = csr[i % 8]
+            ctx.decide_ragged_submit(k, pt.array, po.array, n, pth.array, outs[k])
+        for i in range(max(0, steps - 4), steps):
+            ctx.decide_batch_wait(i % 4)
+
+    csr_pipeline(8)
+    t0 = time.perf_counter()
+    csr_pipeline(200)
+    dt = time.perf_counter() - t0
+    print(f"{'host API, CSR input (pipelined)':36s} {dt / 200 * 1e3:.4f} ms/step  {200 * b / dt:9.0f} decisions/s  "
+          f"{flops * 200 / dt / 1e12:7.1f} TFLOP/s on valid tokens; H2D {csr[0][0].array.nbytes / 2**20:.1f} MiB/step "
+          f"against {b * n * t * 4 / 2**20:.1f} MiB padded")
     full = 2.0 * b * n * t * d * d
     print(f"valid tokens: {flops / full:.3f} of the padded shape; blocks of 128: "
           f"{np.mean([np.ceil(x.lens / 128).sum() for x in batches]) / (b * n * 4):.3f} non-empty")
