@@ -107,6 +107,8 @@ struct qc_ctx {
   const int32_t* hint_chunk_src = nullptr;
   const int32_t* hint_chunk_n = nullptr;
   const int32_t* hint_row_start = nullptr;
+  const int32_t* hint_chunk_row = nullptr;
+  int hint_nruns = 0;
   int hint_nchunks = 0;
   DevBuf* hint_packed_buf = nullptr;
   bool hint_variant_set = false;  // the staged plan was made for c->variant: encode_dev must not re-pick it
@@ -291,6 +293,35 @@ size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
 // (cand * bpc + j, in order) and K1 walks that list instead of skipping: no CTA pair runs half empty.  Batches
 // without an empty block need no list (dense enumeration is the same walk).  The list rides to the device on
 // the call's own stream through a pinned staging buffer that stays untouched until the call is waited for.
+// Packed-stream plan.  Candidate r contributes ceil(len[r] / CH) chunks, laid end to end; chunk c belongs to block
+// c / nch.  src[c] = index of the chunk's first token in the caller's token array, cnt[c] = its valid tokens,
+// crow[c] = id of the partial row its sum is added to (consecutive chunks of one candidate inside one block share a
+// row; -1 for the padding chunks that fill the last block), row[r] .. row[r+1] = the candidate's rows.
+// Returns the number of partial rows.
+template <class BaseOf>
+long long fill_pack_plan(const int32_t* lens, int R, int CH, int nch, long long nchunks, BaseOf base_of, int32_t* src,
+                         int32_t* cnt, int32_t* crow, int32_t* row) {
+  long long k = 0, runs = 0;
+  for (int r = 0; r < R; ++r) {
+    row[r] = static_cast<int32_t>(runs);
+    const int len = lens[r];
+    const long long base = base_of(r);
+    for (int o = 0; o < len; o += CH, ++k) {
+      src[k] = static_cast<int32_t>(base + o);
+      cnt[k] = len - o < CH ? len - o : CH;
+      if (o == 0 || k % nch == 0) ++runs;                      // new candidate, or the candidate crosses a block edge
+      crow[k] = static_cast<int32_t>(runs - 1);
+    }
+  }
+  row[R] = static_cast<int32_t>(runs);
+  for (; k < nchunks; ++k) {
+    src[k] = 0;
+    cnt[k] = 0;
+    crow[k] = -1;
+  }
+  return runs;
+}
+
 StreamWs* ws_for(qc_ctx* c, cudaStream_t s) {
   for (StreamWs& w : c->ws)
     if (w.used && w.s == s) {
@@ -345,32 +376,20 @@ int stage_block_map(qc_ctx* c, const int32_t* lens, int R, int T, DevBuf* dmap, 
       c->variant = vp;
       c->hint_variant_set = true;
       const long long nchunks = pblocks * nch;
-      const size_t ints = static_cast<size_t>(2 * nchunks + R + 1);
+      const size_t ints = static_cast<size_t>(3 * nchunks + R + 1);
       QC_CUDA(hmap->ensure(ints * sizeof(int32_t)));
       QC_CUDA(dmap->ensure(ints * sizeof(int32_t)));
       int32_t* src = static_cast<int32_t*>(hmap->p);
-      int32_t* cnt = src + nchunks;
-      int32_t* row = cnt + nchunks;
-      long long k = 0;
-      for (int r = 0; r < R; ++r) {
-        row[r] = static_cast<int32_t>(k);
-        for (int o = 0; o < lens[r]; o += CH) {
-          src[k] = static_cast<int32_t>(static_cast<long long>(r) * T + o);
-          cnt[k] = lens[r] - o < CH ? lens[r] - o : CH;
-          ++k;
-        }
-      }
-      row[R] = static_cast<int32_t>(k);
-      for (; k < nchunks; ++k) {
-        src[k] = 0;
-        cnt[k] = 0;
-      }
+      const long long runs = fill_pack_plan(lens, R, CH, nch, nchunks, [T](int r) { return static_cast<long long>(r) * T; },
+                                            src, src + nchunks, src + 2 * nchunks, src + 3 * nchunks);
       QC_CUDA(cudaMemcpyAsync(dmap->p, src, ints * sizeof(int32_t), cudaMemcpyHostToDevice, s));
       const int32_t* d = static_cast<const int32_t*>(dmap->p);
       c->hint_chunk_src = d;
       c->hint_chunk_n = d + nchunks;
-      c->hint_row_start = d + 2 * nchunks;
+      c->hint_chunk_row = d + 2 * nchunks;
+      c->hint_row_start = d + 3 * nchunks;
       c->hint_nchunks = static_cast<int>(nchunks);
+      c->hint_nruns = static_cast<int>(runs);
       c->hint_packed_buf = dpacked;
       return QC_OK;
     }
@@ -419,6 +438,8 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
   const int32_t* chunk_src = c->hint_chunk_src;
   const int32_t* chunk_n = c->hint_chunk_n;
   const int32_t* row_start = c->hint_row_start;
+  const int32_t* chunk_row = c->hint_chunk_row;
+  const int nruns = c->hint_nruns;
   const int nchunks = c->hint_nchunks;
   DevBuf* packed = c->hint_packed_buf;
   c->hint_map = nullptr;
@@ -430,7 +451,7 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
   if (pack) {
     // token ids -> stream of CH-slot chunks; K1 sees nchunks / (TB/CH) full blocks and writes one partial row per chunk
     QC_CUDA(packed->ensure(static_cast<size_t>(nchunks) * CH * sizeof(int32_t)));
-    QC_CUDA(part.ensure(static_cast<size_t>(nchunks) * c->dim * sizeof(float)));
+    QC_CUDA(part.ensure(static_cast<size_t>(nruns > 0 ? nruns : 1) * c->dim * sizeof(float)));
     c->launches++;
     QC_CUDA(qc::launch_pack_tokens(d_tok, chunk_src, chunk_n, static_cast<int32_t*>(packed->p), nchunks, CH, s));
   } else {
@@ -449,6 +470,7 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
       a.R = nchunks / (TB / CH);
       a.T = TB;
       a.chunked = 1;
+      a.chunk_row = chunk_row;
     } else {
       a.token_ids = d_tok;
       a.lens = d_lens;
@@ -946,27 +968,12 @@ static int ragged_common(qc_ctx* c, const RaggedBufs& wb, const int32_t* tokens,
   for (int r = 0; r < R; ++r) chunks += (lens[r] + CH - 1) / CH;
   const long long nchunks = (chunks + nch - 1) / nch * nch;
   if (nchunks * CH > 0x7fffffffLL) return QC_ERR_UNSUPPORTED;
-  const size_t ints = static_cast<size_t>(2 * nchunks + R + 1);
+  const size_t ints = static_cast<size_t>(3 * nchunks + R + 1);
   QC_CUDA(wb.h_map->ensure(ints * sizeof(int32_t)));
   QC_CUDA(wb.map->ensure(ints * sizeof(int32_t)));
   int32_t* src = static_cast<int32_t*>(wb.h_map->p);
-  int32_t* cnt = src + nchunks;
-  int32_t* row = cnt + nchunks;
-  long long k = 0;
-  for (int r = 0; r < R; ++r) {
-    row[r] = static_cast<int32_t>(k);
-    const int len = lens[r];
-    for (int o = 0; o < len; o += CH) {
-      src[k] = offsets[r] + o;
-      cnt[k] = len - o < CH ? len - o : CH;
-      ++k;
-    }
-  }
-  row[R] = static_cast<int32_t>(k);
-  for (; k < nchunks; ++k) {
-    src[k] = 0;
-    cnt[k] = 0;
-  }
+  const long long runs = fill_pack_plan(lens, R, CH, nch, nchunks, [offsets](int r) { return static_cast<long long>(offsets[r]); },
+                                        src, src + nchunks, src + 2 * nchunks, src + 3 * nchunks);
   QC_CUDA(cudaMemcpyAsync(wb.map->p, src, ints * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   HintGuard hg(c);
   const int32_t* d = static_cast<const int32_t*>(wb.map->p);
@@ -974,8 +981,10 @@ static int ragged_common(qc_ctx* c, const RaggedBufs& wb, const int32_t* tokens,
   c->hint_variant_set = true;
   c->hint_chunk_src = d;
   c->hint_chunk_n = d + nchunks;
-  c->hint_row_start = d + 2 * nchunks;
+  c->hint_chunk_row = d + 2 * nchunks;
+  c->hint_row_start = d + 3 * nchunks;
   c->hint_nchunks = static_cast<int>(nchunks);
+  c->hint_nruns = static_cast<int>(runs);
   c->hint_packed_buf = wb.packed;
   // T only sizes the dense walk, which the pack hint replaces
   return encode_dev(c, static_cast<int32_t*>(wb.tok->p), static_cast<int32_t*>(wb.lens->p), R, vp.token_block, d_emb, s,

@@ -26,7 +26,8 @@ struct EncoderLaunch {
   unsigned long long* stall;   // device [grid x 16] per-role stall cycles, or nullptr
   const int32_t* block_map;    // device: ids of the non-empty token blocks (cand * bpc + j), or nullptr = dense
   int nslots;                  // entries in block_map
-  int chunked;                 // 1: part is [R x bpc x (TB/CH) x D], one row per CH-token chunk (packed token stream)
+  int chunked;                 // 1: packed token stream; part rows are addressed through chunk_row
+  const int32_t* chunk_row;    // device [R x bpc x (TB/CH)]: partial-row id of every CH-token chunk, -1 for padding
   int R, T, dim, vocab, num_sms;
   EncoderVariant variant;
   cudaStream_t stream;

@@ -175,7 +175,9 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
                  int32_t* __restrict__ dbg,                            // [0..3] watchdog, [4] token-range flag
                  unsigned long long* __restrict__ stall,               // optional [grid x 16] per-role stall cycles
                  const int32_t* __restrict__ block_map,                // optional compacted block list [nslots]
-                 int nslots, int chunked,                              // chunked: part holds one row per chunk_tokens(TB) tokens
+                 int nslots,
+                 const int32_t* __restrict__ chunk_row,                // packed stream: partial-row id per chunk (-1 = padding)
+                 int chunked,                                          // chunked: part rows come from chunk_row
                  int R, int T, int bpc, int vocab) {
   constexpr int D = Tr::D, TB = Tr::TB, CG = Tr::CG, KB = Tr::KB, NFT = Tr::NFT, WBK = Tr::WBK, NWS = Tr::NWS;
   constexpr int UMMA_N = Tr::UMMA_N, WS = Tr::W_STAGES, ACC_COLS = Tr::ACC_COLS;
@@ -261,13 +263,27 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
           if (lane == 0) {
             if constexpr (CG == 2) mbar_arrive_cluster(&acc_empty[as], 0); else mbar_arrive(&acc_empty[as]);
           }
+          // consecutive chunks of one candidate inside a block share a partial row (chunk_row, warp-uniform)
 #pragma unroll
           for (int s = 0; s < CG; ++s) {
             if (valid[s] > 0) {
               const size_t blk = static_cast<size_t>(slot_block(block_map, item * CG + s, nslots, nblocks));
+              const int32_t* cr = chunk_row + blk * NCH;
+              const size_t col = static_cast<size_t>(ft) * Tr::MT + rank * 128 + row;
+              int prev = cr[0];
+              float acc = csum[s][0];
 #pragma unroll
-              for (int k = 0; k < NCH; ++k)
-                part[(blk * NCH + k) * D + ft * Tr::MT + rank * 128 + row] = csum[s][k];
+              for (int k = 1; k < NCH; ++k) {
+                const int rk = cr[k];
+                if (rk == prev) {
+                  acc += csum[s][k];
+                } else {
+                  if (prev >= 0) part[static_cast<size_t>(prev) * D + col] = acc;
+                  prev = rk;
+                  acc = csum[s][k];
+                }
+              }
+              if (prev >= 0) part[static_cast<size_t>(prev) * D + col] = acc;
             }
           }
           continue;
@@ -570,6 +586,7 @@ static cudaError_t launch_encode_t(const EncoderLaunch& a) {
   const int bpc = (a.T + Tr::TB - 1) / Tr::TB;
   int grid = a.num_sms;
   if (Tr::CG == 2) grid &= ~1;
+  if (a.chunked && a.chunk_row == nullptr) return cudaErrorInvalidValue;
   const long long nblocks = static_cast<long long>(a.R) * bpc;
   if (nblocks > 0x7fffffffLL) return cudaErrorInvalidValue;
   const int nslots = a.block_map != nullptr ? a.nslots : static_cast<int>(nblocks);
@@ -593,7 +610,7 @@ static cudaError_t launch_encode_t(const EncoderLaunch& a) {
   cfg.numAttrs = 1;
   const CUtensorMap* tm = Tr::WBK == 64 ? a.w_tmap64 : a.w_tmap32;
   return cudaLaunchKernelEx(&cfg, kern, *tm, *a.e_tmap, a.table, a.token_ids, a.lens, a.part, a.err_flag, a.stall,
-                            a.block_map, nslots, a.chunked, a.R, a.T, bpc, a.vocab);
+                            a.block_map, nslots, a.chunk_row, a.chunked, a.R, a.T, bpc, a.vocab);
 }
 
 // The instantiated variants.  {dim, token block, cta group, W stage width, gather mode}
