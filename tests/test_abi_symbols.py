@@ -55,3 +55,14 @@ def test_null_arguments_are_rejected_not_dereferenced():
     assert lib.qc_similarity_batch(None, None, 1, 2, 3, None, None, None, None) == -1
     assert lib.qc_launch_count(None) == 0
     lib.qc_ctx_destroy(None)
+
+
+def test_c_example_compiles_and_links_against_the_header(tmp_path):
+    """examples/c_abi_decide.c is plain C against include/qconsensus.h: it must build with -Wall -Werror and link
+    against the in-tree library without any Python or torch in sight (no GPU needed to link)."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    lib = root / "quoracle_b200" / "lib"
+    subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-std=c11", f"-I{root / 'include'}", str(root / "examples" / "c_abi_decide.c"),
+                    f"-L{lib}", "-lqconsensus", f"-Wl,-rpath,{lib}", "-o", str(tmp_path / "c_abi_decide")], check=True)
