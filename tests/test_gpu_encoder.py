@@ -505,3 +505,31 @@ def test_device_calls_on_different_streams_do_not_share_scratch():
                 assert np.array_equal(outs[i][2].cpu().numpy(), ref[i].cos), (rep, i)
                 assert np.array_equal(outs[i][1].cpu().numpy(), ref[i].medoid)
         del want
+
+
+def test_block_map_hint_for_device_callers():
+    """qc_encoder_token_block + qc_encoder_hint_block_map: a caller of the *_dev entry points lists the non-empty token
+    blocks itself; same bits as the walk that skips, and the hint is consumed by exactly one launch."""
+    import torch
+    w = weights(768, vocab=8192)
+    dev = torch.device("cuda:0")
+    b, n, t = 12, 8, 400
+    batch = synth.make_decisions(b, n, t, vocab=8192, seed=77, ragged=True)
+    with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+        tb = ctx.token_block(t)
+        bpc = -(-t // tb)
+        lens = batch.lens.reshape(-1)
+        ids = np.concatenate([r * bpc + np.arange(-(-int(l) // tb), dtype=np.int32) for r, l in enumerate(lens)]).astype(np.int32)
+        assert ids.shape[0] < lens.shape[0] * bpc                       # there are empty blocks to skip
+        d_tok, d_len = torch.from_numpy(batch.token_ids).to(dev), torch.from_numpy(batch.lens).to(dev)
+        d_map = torch.from_numpy(ids).to(dev)
+        dense, listed, after = (torch.empty((b * n, 768), dtype=torch.float32, device=dev) for _ in range(3))
+        ctx.embed_batch_dev(d_tok.data_ptr(), d_len.data_ptr(), b * n, t, dense.data_ptr())
+        ctx.hint_block_map(d_map.data_ptr(), d_map.numel())
+        ctx.embed_batch_dev(d_tok.data_ptr(), d_len.data_ptr(), b * n, t, listed.data_ptr())
+        ctx.embed_batch_dev(d_tok.data_ptr(), d_len.data_ptr(), b * n, t, after.data_ptr())   # hint already consumed
+        ctx.synchronize()
+        ctx.check_status()
+        assert torch.equal(dense, listed) and torch.equal(dense, after)
+        want = oenc.encode(w.table_bf16, w.w_bf16, batch.token_ids.reshape(b * n, t), lens)
+        assert np.max(np.abs(listed.cpu().numpy() - want)) < EMB_TOL
