@@ -40,7 +40,7 @@ constexpr int kSplitWarps = 4 * kSplitGroups;
 constexpr int kTcThreads = (4 + kSplitWarps + 2) * 32;   // epilogue, splitters, TMA producer, MMA issuer
 constexpr int kChunkBytes = 128 * 128;       // 128 rows x 32 fp32
 // Shared memory: alignment slack, kStages x (raw 16 KB + lo 16 KB), two [128][kWin] fp32 windows, norms and row
-// means, barriers.  Pools <= 32 need narrower windows and get a fifth stage.
+// means, barriers.  Pools <= 48 need narrower windows and get a fifth stage.
 // The epilogue reads up to 7 entries past a decision's last column / row (blocks of 8, results discarded); those
 // reads must land in memory nobody writes, so each array they can run off carries its own tail: 7 extra window rows
 // after the HL window, 16 extra entries after the norms and after the row means.
@@ -372,6 +372,7 @@ cudaError_t launch_similarity_tc(const CUtensorMap* x_tmap, int B, int N, int D,
                                  int32_t* medoid, float* cos, int32_t* dbg, unsigned long long* stall, int num_sms,
                                  cudaStream_t stream) {
   if (N <= 32) return launch_tc<5, 33>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream);
+  if (N <= 48) return launch_tc<5, 49>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream);
   return launch_tc<4, 65>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream);
 }
 
