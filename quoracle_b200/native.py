@@ -271,7 +271,7 @@ class Context:
 
     def decide_batch_submit(self, slot: int, token_ids: np.ndarray, lens: np.ndarray, thr: np.ndarray,
                             out: DecideResult) -> None:
-        """Pipelined form: enqueue one batch on slot 0/1; arrays must be C-contiguous int32/float32 and stay
+        """Pipelined form: enqueue one batch on slot 0..3 (QC_PIPELINE_SLOTS); arrays must be C-contiguous int32/float32 and stay
         alive and untouched until ``decide_batch_wait(slot)`` returns (no copies are made here)."""
         b, n, t = token_ids.shape
         for a, dt in ((token_ids, np.int32), (lens, np.int32), (thr, np.float32)):
