@@ -40,13 +40,19 @@ constexpr int kSplitWarps = 4 * kSplitGroups;
 constexpr int kTcThreads = (4 + kSplitWarps + 2) * 32;   // epilogue, splitters, TMA producer, MMA issuer
 constexpr int kChunkBytes = 128 * 128;       // 128 rows x 32 fp32
 // Shared memory: alignment slack, kStages x (raw 16 KB + lo 16 KB), two [128][kWin] fp32 windows, norms and row
-// means, barriers.  Pools <= 48 need narrower windows and get a fifth stage.
+// means, barriers; five stages for every pool size (the widest windows only just fit, see kTail).
 // The epilogue reads up to 7 entries past a decision's last column / row (blocks of 8, results discarded); those
 // reads must land in memory nobody writes, so each array they can run off carries its own tail: 7 extra window rows
 // after the HL window, 16 extra entries after the norms and after the row means.
 constexpr int kVecLen = 144;                 // 128 + over-read tail
-constexpr int tc_smem_bytes(int stages, int win) {
-  return 1024 + stages * 2 * kChunkBytes + (2 * 128 + 7) * win * 4 + 2 * kVecLen * 4 + 8 + 256;
+// kTail = 7: the HL window carries seven never-written rows for the transposed over-reads.  kTail = 0 (pools of
+// 49..64, where five stages and 65-column windows fill the 227 KB to the last few hundred bytes): those reads are
+// clamped to the decision's last row instead, and the alignment slack is 512 bytes -- the dynamic shared window of a
+// kernel without static shared memory starts 1 KB into the SM's shared memory, i.e. already 1024-aligned; the
+// kernel checks and bails out through the watchdog record if that ever stops being true.
+__host__ __device__ constexpr int tc_slack(int tail) { return tail == 0 ? 512 : 1024; }
+constexpr int tc_smem_bytes(int stages, int win, int tail) {
+  return tc_slack(tail) + stages * 2 * kChunkBytes + (2 * 128 + tail) * win * 4 + 2 * kVecLen * 4 + 8 + 256;
 }
 
 // kind::tf32, fp32 accumulate, both operands K-major: c_format=1 (bit 4), a/b_format=2 (bits 7, 10), N>>3, M>>4
@@ -75,21 +81,30 @@ __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__
 
 }  // namespace
 
-template <int kStages, int kWin>
+template <int kStages, int kWin, int kTail>
 __global__ void __launch_bounds__(kTcThreads, 1)
 qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N rows x D cols] fp32, box 32 x (128/N)*N
                  int B, int N, int D, const float* __restrict__ thr, int32_t* __restrict__ ref_ok,
                  int32_t* __restrict__ medoid, float* __restrict__ cos, int32_t* __restrict__ dbg,
                  unsigned long long* __restrict__ stall) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
+  const uint32_t misalign = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  if (misalign > static_cast<uint32_t>(tc_slack(kTail))) {    // uniform: every thread leaves before any barrier
+    if (threadIdx.x == 0 && atomicCAS(dbg, 0, 1) == 0) {
+      dbg[1] = 799;
+      dbg[2] = static_cast<int32_t>(blockIdx.x);
+      dbg[3] = static_cast<int32_t>(misalign);
+    }
+    return;
+  }
+  uint8_t* smem = smem_raw + misalign;                        // pointer arithmetic keeps the shared address space
   uint8_t* stages = smem;                                     // kStages x (raw 16 KB, lo 16 KB)
   float* whh = reinterpret_cast<float*>(stages + kStages * 2 * kChunkBytes);   // [128][kWin] HH window
   float* whl = whh + 128 * kWin;                                             // [128][kWin] HL window
-  float* diag = whl + (128 + 7) * kWin;                                      // [128 + tail] reciprocal row norms
+  float* diag = whl + (128 + kTail) * kWin;                                  // [128 + tail] reciprocal row norms
   float* rmean = diag + kVecLen;                                             // [128 + tail] row means
-  // (263 * kWin + 288) floats precede this point: odd kWin leaves it 4-byte aligned, mbarriers need 8
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rmean + kVecLen + ((263 * kWin) & 1));
+  // ((256 + kTail) * kWin + 288) floats precede this point: an odd count leaves it 4-byte aligned, mbarriers need 8
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rmean + kVecLen + (((256 + kTail) * kWin) & 1));
   uint64_t* raw_full = bars;                                  // TMA landed the raw tile
   uint64_t* lo_full = raw_full + kStages;                     // splitters wrote the lo tile
   uint64_t* stage_empty = lo_full + kStages;                  // the MMAs that read the stage retired
@@ -199,7 +214,8 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
           for (int k = 0; k < 8; ++k) {
             up[k] = hh_row[j0 + k];
             lr[k] = hl_row[j0 + k];
-            lc[k] = hl_col[(j0 + k) * kWin];
+            // without tail rows the transposed read is clamped to the decision's last row (result discarded)
+            lc[k] = hl_col[(kTail == 0 ? (j0 + k < N ? j0 + k : N - 1) : j0 + k) * kWin];
             nj[k] = nrm[j0 + k];
           }
           // branch-free so the eight dependency chains interleave
@@ -347,33 +363,33 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
   }
 }
 
-template <int kStages, int kWin>
+template <int kStages, int kWin, int kTail>
 static cudaError_t launch_tc(const CUtensorMap* x_tmap, int B, int N, int D, const float* thr, int32_t* ref_ok,
                              int32_t* medoid, float* cos, int32_t* dbg, unsigned long long* stall, int num_sms,
                              cudaStream_t stream) {
-  constexpr int smem = tc_smem_bytes(kStages, kWin);
+  constexpr int smem = tc_smem_bytes(kStages, kWin, kTail);
   static_assert(smem <= 232448, "tcgen05 K3: shared-memory carve-up exceeds the 227 KB opt-in limit");
   static bool attr_set[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(qc_sim_tc_kernel<kStages, kWin>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(qc_sim_tc_kernel<kStages, kWin, kTail>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
   const int q = 128 / N;
   const int ntiles = (B + q - 1) / q;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  qc_sim_tc_kernel<kStages, kWin><<<grid, kTcThreads, smem, stream>>>(*x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall);
+  qc_sim_tc_kernel<kStages, kWin, kTail><<<grid, kTcThreads, smem, stream>>>(*x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall);
   return cudaGetLastError();
 }
 
 cudaError_t launch_similarity_tc(const CUtensorMap* x_tmap, int B, int N, int D, const float* thr, int32_t* ref_ok,
                                  int32_t* medoid, float* cos, int32_t* dbg, unsigned long long* stall, int num_sms,
                                  cudaStream_t stream) {
-  if (N <= 32) return launch_tc<5, 33>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream);
-  if (N <= 48) return launch_tc<5, 49>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream);
-  return launch_tc<4, 65>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream);
+  if (N <= 32) return launch_tc<5, 33, 7>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream);
+  if (N <= 48) return launch_tc<5, 49, 7>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream);
+  return launch_tc<5, 65, 0>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream);
 }
 
 }  // namespace qc
