@@ -86,6 +86,26 @@ struct StreamWs {
   DevBuf part, emb;
 };
 
+// How the NEXT encoder launch of a context walks its tokens.  The host entry points (which hold the lengths) fill it
+// right before they call encode_dev, which consumes it exactly once; device callers can set the block list through
+// qc_encoder_hint_block_map.  Everything points into device memory that stays valid until that launch has run.
+struct EncodePlan {
+  // compacted list of the non-empty token blocks (dense walk when null)
+  const int32_t* block_map = nullptr;
+  int nslots = 0;
+  // packed token stream (ragged batches): per chunk its source offset, valid count and partial-row id; per
+  // candidate the range of its partial rows
+  const int32_t* chunk_src = nullptr;
+  const int32_t* chunk_n = nullptr;
+  const int32_t* chunk_row = nullptr;
+  const int32_t* row_start = nullptr;
+  int nchunks = 0;
+  int nruns = 0;
+  DevBuf* packed_buf = nullptr;   // where the pack kernel writes the stream
+  bool variant_set = false;       // the plan was made for ctx->variant: encode_dev must not re-pick the tiling
+  void clear() { *this = EncodePlan(); }
+};
+
 }  // namespace
 
 struct qc_ctx {
@@ -96,22 +116,11 @@ struct qc_ctx {
   bool has_encoder = false;
   int dim = 0, vocab = 0;
   qc::EncoderVariant variant{0, 0, 0, 0};
-  // compacted block list of the NEXT encode_dev call (set by the host entry points, consumed once)
-  const int32_t* hint_map = nullptr;
-  int hint_nslots = 0;
+  EncodePlan plan;               // one-shot plan of the next encoder launch (see EncodePlan)
   DevBuf map, packed;
   HostBuf h_map;
   StreamWs ws[4];
   unsigned long long ws_tick = 0;
-  // packed token stream of the NEXT encode_dev call (ragged batches; same life cycle as hint_map)
-  const int32_t* hint_chunk_src = nullptr;
-  const int32_t* hint_chunk_n = nullptr;
-  const int32_t* hint_row_start = nullptr;
-  const int32_t* hint_chunk_row = nullptr;
-  int hint_nruns = 0;
-  int hint_nchunks = 0;
-  DevBuf* hint_packed_buf = nullptr;
-  bool hint_variant_set = false;  // the staged plan was made for c->variant: encode_dev must not re-pick it
   int packing = 0;               // 0 auto, 1 never, 2 whenever the tiling allows (test hook)
   int sim_path = 0;              // K3 for pools 9..64: 0 auto (tcgen05 when the layout allows), 1 mma.sync, 2 tcgen05
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved once at create
@@ -348,11 +357,7 @@ StreamWs* ws_for(qc_ctx* c, cudaStream_t s) {
 
 int stage_block_map(qc_ctx* c, const int32_t* lens, int R, int T, DevBuf* dmap, HostBuf* hmap, DevBuf* dpacked,
                     cudaStream_t s) {
-  c->hint_map = nullptr;
-  c->hint_nslots = 0;
-  c->hint_chunk_src = nullptr;
-  c->hint_nchunks = 0;
-  c->hint_variant_set = false;
+  c->plan.clear();
   // tiling for the unpacked walks: the one chosen for T (least padding of full-length candidates)
   const qc::EncoderVariant va = c->variant_forced ? c->variant : qc::encoder_auto_variant(c->dim, T);
   // tiling for the packed stream: padding no longer depends on T, so the fastest full-block tiling
@@ -374,7 +379,7 @@ int stage_block_map(qc_ctx* c, const int32_t* lens, int R, int T, DevBuf* dmap, 
     const long long pblocks = (chunks + nch - 1) / nch;
     if (c->packing == 2 || pblocks * vp.token_block * 100 <= used * TB * 95) {
       c->variant = vp;
-      c->hint_variant_set = true;
+      c->plan.variant_set = true;
       const long long nchunks = pblocks * nch;
       const size_t ints = static_cast<size_t>(3 * nchunks + R + 1);
       QC_CUDA(hmap->ensure(ints * sizeof(int32_t)));
@@ -384,18 +389,18 @@ int stage_block_map(qc_ctx* c, const int32_t* lens, int R, int T, DevBuf* dmap, 
                                             src, src + nchunks, src + 2 * nchunks, src + 3 * nchunks);
       QC_CUDA(cudaMemcpyAsync(dmap->p, src, ints * sizeof(int32_t), cudaMemcpyHostToDevice, s));
       const int32_t* d = static_cast<const int32_t*>(dmap->p);
-      c->hint_chunk_src = d;
-      c->hint_chunk_n = d + nchunks;
-      c->hint_chunk_row = d + 2 * nchunks;
-      c->hint_row_start = d + 3 * nchunks;
-      c->hint_nchunks = static_cast<int>(nchunks);
-      c->hint_nruns = static_cast<int>(runs);
-      c->hint_packed_buf = dpacked;
+      c->plan.chunk_src = d;
+      c->plan.chunk_n = d + nchunks;
+      c->plan.chunk_row = d + 2 * nchunks;
+      c->plan.row_start = d + 3 * nchunks;
+      c->plan.nchunks = static_cast<int>(nchunks);
+      c->plan.nruns = static_cast<int>(runs);
+      c->plan.packed_buf = dpacked;
       return QC_OK;
     }
   }
   c->variant = va;
-  c->hint_variant_set = true;
+  c->plan.variant_set = true;
   if (used == static_cast<long long>(R) * bpc || used > 0x7fffffffLL) return QC_OK;
   QC_CUDA(hmap->ensure(static_cast<size_t>(used > 0 ? used : 1) * sizeof(int32_t)));
   QC_CUDA(dmap->ensure(static_cast<size_t>(used > 0 ? used : 1) * sizeof(int32_t)));
@@ -406,8 +411,8 @@ int stage_block_map(qc_ctx* c, const int32_t* lens, int R, int T, DevBuf* dmap, 
     for (int j = 0; j < nb; ++j) h[k++] = r * bpc + j;
   }
   if (used > 0) QC_CUDA(cudaMemcpyAsync(dmap->p, h, static_cast<size_t>(used) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-  c->hint_map = static_cast<const int32_t*>(dmap->p);
-  c->hint_nslots = static_cast<int>(used);
+  c->plan.block_map = static_cast<const int32_t*>(dmap->p);
+  c->plan.nslots = static_cast<int>(used);
   return QC_OK;
 }
 
@@ -415,37 +420,27 @@ int stage_block_map(qc_ctx* c, const int32_t* lens, int R, int T, DevBuf* dmap, 
 struct HintGuard {
   qc_ctx* c;
   explicit HintGuard(qc_ctx* c_) : c(c_) {}
-  ~HintGuard() {
-    c->hint_map = nullptr;
-    c->hint_nslots = 0;
-    c->hint_chunk_src = nullptr;
-    c->hint_nchunks = 0;
-    c->hint_variant_set = false;
-  }
+  ~HintGuard() { c->plan.clear(); }
 };
 
 int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, int T, float* d_emb, cudaStream_t s,
                DevBuf* part_buf = nullptr, const qc::FinalizeDst* scatter = nullptr,
                const qc::TsplitDst* tsplit = nullptr) {
   DevBuf& part = part_buf ? *part_buf : ws_for(c, s)->part;
-  if (!c->variant_forced && !c->hint_variant_set) c->variant = qc::encoder_auto_variant(c->dim, T);
-  c->hint_variant_set = false;
+  const EncodePlan plan = c->plan;                             // consumed: the next launch starts from a clean plan
+  c->plan.clear();
+  if (!c->variant_forced && !plan.variant_set) c->variant = qc::encoder_auto_variant(c->dim, T);
   const int TB = c->variant.token_block;
   const int bpc = (T + TB - 1) / TB;
-  // one-shot hints of the host entry points (ragged batches)
-  const int32_t* map = c->hint_map;
-  const int nslots = c->hint_nslots;
-  const int32_t* chunk_src = c->hint_chunk_src;
-  const int32_t* chunk_n = c->hint_chunk_n;
-  const int32_t* row_start = c->hint_row_start;
-  const int32_t* chunk_row = c->hint_chunk_row;
-  const int nruns = c->hint_nruns;
-  const int nchunks = c->hint_nchunks;
-  DevBuf* packed = c->hint_packed_buf;
-  c->hint_map = nullptr;
-  c->hint_nslots = 0;
-  c->hint_chunk_src = nullptr;
-  c->hint_nchunks = 0;
+  const int32_t* map = plan.block_map;
+  const int nslots = plan.nslots;
+  const int32_t* chunk_src = plan.chunk_src;
+  const int32_t* chunk_n = plan.chunk_n;
+  const int32_t* row_start = plan.row_start;
+  const int32_t* chunk_row = plan.chunk_row;
+  const int nruns = plan.nruns;
+  const int nchunks = plan.nchunks;
+  DevBuf* packed = plan.packed_buf;
   const int CH = qc::encoder_chunk_tokens(TB);
   const bool pack = chunk_src != nullptr && nchunks > 0 && tsplit == nullptr && packed != nullptr;
   if (pack) {
@@ -843,8 +838,8 @@ int qc_encoder_set_packing(qc_ctx* c, int mode) {
 int qc_encoder_hint_block_map(qc_ctx* c, const int32_t* d_block_map, int nslots) {
   if (c == nullptr || nslots < 0 || (d_block_map == nullptr && nslots != 0)) return QC_ERR_INVALID_INPUT;
   if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
-  c->hint_map = d_block_map;
-  c->hint_nslots = d_block_map ? nslots : 0;
+  c->plan.block_map = d_block_map;
+  c->plan.nslots = d_block_map ? nslots : 0;
   return QC_OK;
 }
 
@@ -978,14 +973,14 @@ static int ragged_common(qc_ctx* c, const RaggedBufs& wb, const int32_t* tokens,
   HintGuard hg(c);
   const int32_t* d = static_cast<const int32_t*>(wb.map->p);
   c->variant = vp;
-  c->hint_variant_set = true;
-  c->hint_chunk_src = d;
-  c->hint_chunk_n = d + nchunks;
-  c->hint_chunk_row = d + 2 * nchunks;
-  c->hint_row_start = d + 3 * nchunks;
-  c->hint_nchunks = static_cast<int>(nchunks);
-  c->hint_nruns = static_cast<int>(runs);
-  c->hint_packed_buf = wb.packed;
+  c->plan.variant_set = true;
+  c->plan.chunk_src = d;
+  c->plan.chunk_n = d + nchunks;
+  c->plan.chunk_row = d + 2 * nchunks;
+  c->plan.row_start = d + 3 * nchunks;
+  c->plan.nchunks = static_cast<int>(nchunks);
+  c->plan.nruns = static_cast<int>(runs);
+  c->plan.packed_buf = wb.packed;
   // T only sizes the dense walk, which the pack hint replaces
   return encode_dev(c, static_cast<int32_t*>(wb.tok->p), static_cast<int32_t*>(wb.lens->p), R, vp.token_block, d_emb, s,
                     wb.part);
