@@ -20,7 +20,7 @@ from typing import Any, Optional, Sequence
 import numpy as np
 
 from . import tokenizer
-from .native import Context, QcError
+from .native import QC_MAX_TOKENS, Context, QcError
 
 DEFAULT_CACHE_TTL_MS = 3_600_000       # embeddings.ex:24
 MAX_CACHE_ENTRIES = 1000               # embeddings.ex:25
@@ -113,7 +113,7 @@ class Embeddings:
         if not todo:
             return out
         uniq = list(todo.keys())
-        chunk_lists = [chunk_text_by_tokens(t, self.limit) if tokenizer.count_tokens(t) > self.limit else [t] for t in uniq]
+        chunk_lists = [self._chunks_for(t) for t in uniq]
         flat = [c for cl in chunk_lists for c in cl]
         tokens, offsets = tokenizer.pack_ragged(flat, self.vocab)     # texts differ in length: CSR, nothing padded
         try:
@@ -126,6 +126,10 @@ class Embeddings:
             return out
         pos = 0
         for t, cl in zip(uniq, chunk_lists):
+            if not cl:
+                for i in todo[t]:
+                    out[i] = ("error", "all_chunks_failed")
+                continue
             rows = emb[pos:pos + len(cl)]
             pos += len(cl)
             vec = rows[0] if len(cl) == 1 else self.ctx.chunk_mean(rows[None])[0]   # unweighted, not re-normalised
@@ -134,6 +138,21 @@ class Embeddings:
             for i in todo[t]:
                 out[i] = ("ok", {"embedding": vec, "cached": False, "chunks": len(cl)})
         return out
+
+    def _chunks_for(self, text: str) -> list:
+        """get_embedding_with_chunking/2 (embeddings.ex:142-167) with the device in the provider's role: above the
+        effective limit the text is chunked by the limit; a text within the limit that the encoder would still
+        reject (more than QC_MAX_TOKENS token slots -- the reference's `:context_length_exceeded` answer) is
+        re-chunked at HALF its own token count (:159-164); chunks that are still too long are the reference's
+        failed chunks and are dropped (process_chunks/2, :170-192) -- an empty list means `:all_chunks_failed`."""
+        count = tokenizer.count_tokens(text)
+        if count > self.limit:
+            chunks = chunk_text_by_tokens(text, self.limit)
+        elif count > QC_MAX_TOKENS:
+            chunks = chunk_text_by_tokens(text, max(count // 2, 1))
+        else:
+            return [text]
+        return [c for c in chunks if tokenizer.count_tokens(c) <= QC_MAX_TOKENS]
 
     def get_embedding(self, value: Any, options: Optional[dict] = None):
         """Embeddings.get_embedding/2: 2-tuple, or 3-tuple with the accumulator when one is passed and the

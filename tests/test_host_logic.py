@@ -182,3 +182,33 @@ def test_batched_decide_step_matches_the_oracle_format_result():
             assert g["action"]["params"] == action["params"], (g["action"], action)
             assert g["action"]["wait"] == action["wait"] and g["action"]["reasoning"] == action["reasoning"]
             assert abs(g["confidence"] - opts["confidence"]) < 1e-12
+
+
+def test_rechunk_at_half_when_the_encoder_rejects_a_text_within_the_limit(monkeypatch):
+    """embeddings.ex:159-164: a text within the token limit that the provider still rejects with
+    :context_length_exceeded is re-chunked at half its own token count; chunks that still fail are dropped and
+    nothing left means :all_chunks_failed (:170-192).  The device's context limit plays the provider's part; the
+    oracle is driven with a provider that rejects the same texts."""
+    import quoracle_b200.embeddings as pe
+    monkeypatch.setattr(pe, "QC_MAX_TOKENS", 12)                  # a small "context window" keeps the test light
+    emb, ctx = make_emb(model_token_limit=100)                    # effective limit 90 > 12: the estimate says "fits"
+
+    def provider(text):                                           # what the oracle's embedding_fn sees
+        if tokenizer.count_tokens(text) > 12:
+            return ("error", "context_length_exceeded")
+        ids, lens = tokenizer.pack([text], 4096)
+        return ("ok", ctx.embed_batch(ids, lens)[0].astype(np.float64).tolist())   # 1-arity seam: {:ok, [float]}
+
+    texts = [" ".join(f"w{i}" for i in range(n)) for n in (5, 12, 13, 20, 24, 25, 60)]
+    got = emb.get_embeddings(texts, cache_ttl=0)
+    for text, g in zip(texts, got):
+        want = oemb.get_embedding(text, {"embedding_fn": provider, "model_token_limit": 100, "cache_ttl": 0,
+                                         "token_counter": tokenizer.count_tokens, "table": {}})
+        assert g[0] == want[0], (tokenizer.count_tokens(text), g, want)
+        if g[0] == "ok":
+            assert g[1]["chunks"] == want[1]["chunks"]
+            assert np.max(np.abs(g[1]["embedding"] - np.array(want[1]["embedding"]))) < 1e-6
+        else:
+            assert g[1] == want[1]
+    kinds = [g[0] if g[0] == "ok" else g[1] for g in got]
+    assert kinds[:3] == ["ok", "ok", "ok"] and "all_chunks_failed" in kinds     # 60 tokens -> halves of 30 still too long
