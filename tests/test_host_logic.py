@@ -212,3 +212,31 @@ def test_rechunk_at_half_when_the_encoder_rejects_a_text_within_the_limit(monkey
             assert g[1] == want[1]
     kinds = [g[0] if g[0] == "ok" else g[1] for g in got]
     assert kinds[:3] == ["ok", "ok", "ok"] and "all_chunks_failed" in kinds     # 60 tokens -> halves of 30 still too long
+
+
+def test_cache_ttl_and_eviction_follow_the_reference():
+    """embeddings.ex:65-95 (hit only while now - ts < ttl, expired entries deleted on lookup) and :402-426 (at >= 1000
+    entries the 100 oldest go before the insert)."""
+    from quoracle_b200.embeddings import EmbeddingCache, MAX_CACHE_ENTRIES
+    c = EmbeddingCache()
+    v = np.ones(4, np.float32)
+    for i in range(MAX_CACHE_ENTRIES):
+        c.insert(i.to_bytes(4, "big"), v, now_ms=1000 + i, ttl=50_000)
+    assert len(c.table) == MAX_CACHE_ENTRIES
+    c.insert(b"new!", v, now_ms=5000, ttl=50_000)
+    assert len(c.table) == MAX_CACHE_ENTRIES - 100 + 1
+    assert (0).to_bytes(4, "big") not in c.table and (99).to_bytes(4, "big") not in c.table
+    assert (100).to_bytes(4, "big") in c.table
+    assert c.lookup(b"new!", 5000 + 49_999) is not None
+    assert c.lookup(b"new!", 5000 + 50_000) is None and b"new!" not in c.table      # expired and removed
+    # the same sequence through the oracle's table gives the same survivors
+    table = {}
+    now = [0]
+    for i in range(MAX_CACHE_ENTRIES):
+        now[0] = 1000 + i
+        oemb.get_embedding(f"t{i}", {"embedding_fn": lambda t: ("ok", [1.0]), "cache_table": table, "cache_ttl": 50_000,
+                                     "now_ms": lambda: now[0], "token_counter": tokenizer.count_tokens})
+    now[0] = 5000
+    oemb.get_embedding("new", {"embedding_fn": lambda t: ("ok", [1.0]), "cache_table": table, "cache_ttl": 50_000,
+                               "now_ms": lambda: now[0], "token_counter": tokenizer.count_tokens})
+    assert len(table) == MAX_CACHE_ENTRIES - 100 + 1             # c.table lost b"new!" to the expiry check above
