@@ -187,7 +187,15 @@ def cluster(responses: Sequence[dict]) -> list:
     groups: "OrderedDict" = OrderedDict()
     for r in responses:
         groups.setdefault(fingerprint(r), []).append(r)
-    ordered = sorted(groups.items(), key=lambda kv: (str(kv[0][0]), repr(kv[0][1])))
+    # order among equal counts is BEAM map order in the reference, which is not reproducible; same documented choice
+    # as the oracle: by action, then by the canonical text of the signature (JSON for the
+    # action-type lists of batch fingerprints)
+    def order_key(kv):
+        action, sig = kv[0]
+        if action in ("batch_sync", "batch_async"):
+            return (str(action), json.dumps(list(sig)))
+        return (str(action), repr(sig))
+    ordered = sorted(groups.items(), key=order_key)
     clusters = [{"count": len(a), "actions": a, "representative": a[0], "fingerprint": fp} for fp, a in ordered]
     return sorted(clusters, key=lambda c: -c["count"])
 
@@ -238,6 +246,93 @@ def confidence(count, total, round_num, max_rounds=4):
 
 
 # ---- the batched decide step -----------------------------------------------------------------------------------
+# ---- :batch_sequence_merge (consensus_rules.ex:33-44,107-112,375-471) in two passes -----------------------------
+def _plan_batch_merge(collector: DecisionCollector, agent_id: str, tag: str, sequences: list):
+    """Host pass: shape checks and every rule that needs no embeddings; semantic parameters of the sub-actions are
+    queued on the collector (they ride in the same GPU flush as everything else in the tree).
+    -> ("done", result) when the outcome is already known, else ("plan", positions)."""
+    if sequences == []:
+        return ("done", ("ok", []))
+    if len(sequences) == 1:
+        return ("done", ("ok", sequences[0]))
+    if len({len(q) for q in sequences}) > 1:
+        return ("done", ("error", "sequence_length_mismatch"))
+    positions = []
+    for pos, actions in enumerate(zip(*sequences)):
+        norm = [{"action": a.get("action"), "params": a.get("params") if a.get("params") is not None else {}} for a in actions]
+        types = _uniq([a["action"] for a in norm])
+        if len(types) != 1:
+            positions.append({"error": "sequence_mismatch"})
+            break                                             # later positions are never looked at (:385-396)
+        schema = SCHEMAS.get(types[0])
+        if schema is None:
+            positions.append({"error": "unknown_action"})
+            break
+        plist = [a["params"] for a in norm]
+        keys = _uniq([k for prm in plist for k in prm.keys()])
+        entry = {"action": types[0], "keys": [], "merged": {}, "waiting": {}, "failed": False}
+        for key in keys:
+            vals = [prm.get(key) for prm in plist if prm.get(key) is not None]
+            if not vals:
+                continue
+            entry["keys"].append(key)
+            rule = schema["rules"].get(key, ["exact_match"])  # default differs from result.ex:334 (SURVEY Appendix A.4)
+            if rule[0] == "semantic_similarity":
+                name = f"{tag}[{pos}].{key}"
+                entry["waiting"][key] = name
+                collector.submit(agent_id, name, vals, rule[1] if len(rule) > 1 else DEFAULT_THRESHOLD)
+            else:
+                r = host_rule(rule, vals)
+                if r[0] == "ok":
+                    entry["merged"][key] = r[1]
+                else:
+                    entry["failed"] = True                    # any failing rule -> {:error, :no_consensus} for the merge
+        positions.append(entry)
+    return ("plan", positions)
+
+
+def _finish_batch_merge(positions: list, results: dict, agent_id: str):
+    """After the flush: -> ("ok", merged_actions) | ("error", reason), the first failure in position order wins."""
+    out = []
+    for entry in positions:
+        if "error" in entry:
+            return ("error", entry["error"])
+        merged = dict(entry["merged"])
+        failed = entry["failed"]
+        for key, name in entry["waiting"].items():
+            r = results[agent_id][name]["result"]
+            if r[0] == "ok":
+                merged[key] = r[1]
+            else:
+                failed = True
+        if failed:
+            return ("error", "no_consensus")
+        out.append({"action": entry["action"], "params": {k: merged[k] for k in entry["keys"]}})
+    return ("ok", out)
+
+
+def _merge_sequences_with_mode(sequences: list) -> list:
+    """merge_sequences_with_mode/1 (result.ex:163-228): position by position, the most frequent action type and,
+    among the actions of that type, the most frequent value of every parameter."""
+    out = []
+    for idx in range(max((len(q) for q in sequences), default=0)):
+        at = [q[idx] for q in sequences if idx < len(q) and q[idx] is not None]
+        if not at:
+            continue
+        if len(at) == 1:
+            out.append({"action": at[0].get("action"), "params": dict(at[0].get("params") or {})})
+            continue
+        action_type = mode_value([a.get("action") for a in at])
+        params = [a.get("params") or {} for a in at if a.get("action") == action_type]
+        merged = {}
+        for k in _uniq([k for prm in params for k in prm.keys()]):
+            vals = [prm.get(k) for prm in params if prm.get(k) is not None]
+            if vals:
+                merged[k] = mode_value(vals)
+        out.append({"action": action_type, "params": merged})
+    return out
+
+
 def decide_tree(collector: DecisionCollector, pending: Sequence[dict], round_num: int = 2,
                 max_refinement_rounds: int = 4) -> list:
     """pending: [{"agent_id", "responses": [ {action, params, reasoning, wait?} x N ]}] ->
@@ -256,21 +351,26 @@ def decide_tree(collector: DecisionCollector, pending: Sequence[dict], round_num
         kind, win = pick_winner(clusters, total)
         rep = win["representative"]
         schema = SCHEMAS.get(rep["action"])
-        merged, waiting = {}, {}
-        if schema is not None and rep["action"] != "batch_sync":
+        merged, waiting, batch = {}, {}, {}
+        if rep["action"] == "batch_sync":                     # result.ex:58-84: the whole action is one sequence merge
+            seqs = [((a.get("params") or {}).get("actions") or []) for a in win["actions"]]
+            batch["__sync__"] = (_plan_batch_merge(collector, d["agent_id"], "batch_sync", seqs), seqs)
+        elif schema is not None:
             for p in schema["required"] + schema["optional"]:
                 vals = [v for v in ((a.get("params") or {}).get(p) for a in win["actions"]) if v is not None]
                 if not vals:
                     continue
                 rule = schema["rules"].get(p, ["mode_selection"])
-                if rule[0] == "semantic_similarity":
+                if rule[0] == "batch_sequence_merge":         # batch_async: a parameter like any other, mode on failure
+                    batch[p] = (_plan_batch_merge(collector, d["agent_id"], f"batch:{p}", vals), vals)
+                elif rule[0] == "semantic_similarity":
                     waiting[p] = vals
                     collector.submit(d["agent_id"], p, vals, rule[1] if len(rule) > 1 else DEFAULT_THRESHOLD)
                 else:
                     r = host_rule(rule, vals)
                     merged[p] = r[1] if r[0] == "ok" else mode_value(vals)
         plans.append({"agent_id": d["agent_id"], "kind": kind, "win": win, "schema": schema, "merged": merged,
-                      "waiting": waiting, "total": total})
+                      "waiting": waiting, "batch": batch, "total": total})
     results = collector.flush()
     out = []
     for pl in plans:
@@ -282,9 +382,28 @@ def decide_tree(collector: DecisionCollector, pending: Sequence[dict], round_num
             r = results[pl["agent_id"]][p]["result"]
             merged[p] = r[1] if r[0] == "ok" else mode_value(vals)
         rep = win["representative"]
-        if pl["schema"] is None or rep["action"] == "batch_sync":
+        batch_results = {}
+        for p, ((state, payload), vals) in pl["batch"].items():
+            batch_results[p] = payload if state == "done" else _finish_batch_merge(payload, results, pl["agent_id"])
+        waits = [a.get("wait") for a in win["actions"] if a.get("wait") is not None]
+        if rep["action"] == "batch_sync":
+            r = batch_results["__sync__"]
+            seqs = pl["batch"]["__sync__"][1]
+            if r[0] == "ok" or r == ("error", "no_consensus"):
+                actions = r[1] if r[0] == "ok" else _merge_sequences_with_mode(seqs)
+                action = {"action": "batch_sync", "params": {"actions": actions},
+                          "reasoning": next((a.get("reasoning") for a in win["actions"] if a.get("reasoning") not in ("", None)), ""),
+                          "wait": wait_rule(waits) if waits else False}
+            else:
+                # the reference destructures {:error, reason} as {action, accumulator} here (result.ex:30-47 over
+                # :58-84), so the "action" it reports is the atom :error; kept visible rather than papered over
+                action = {"action": "error", "error": r[1]}
+        elif pl["schema"] is None:
             action = dict(rep)
         else:
+            for p, r in batch_results.items():
+                vals = pl["batch"][p][1]
+                merged[p] = r[1] if r[0] == "ok" else mode_value(vals)
             ordered = {p: merged[p] for p in pl["schema"]["required"] + pl["schema"]["optional"] if p in merged}
             waits = [a.get("wait") for a in win["actions"] if a.get("wait") is not None]
             action = {"action": rep["action"], "params": ordered,

@@ -155,6 +155,35 @@ def _random_proposals(rng, n):
     return out
 
 
+def _random_batch_proposals(rng, n):
+    """N batch proposals (batch_sync / batch_async) whose sub-action sequences mostly line up: same types per
+    position with parameters that agree, nearly agree (semantic rule) or conflict (exact-match rule -> the
+    mode-merge fallback); a few with a different length or a different type at one position."""
+    texts = ["analyze the customer data for patterns", "Analyze customer data patterns!", "deploy release to production"]
+    kind = ["batch_sync", "batch_async"][int(rng.integers(0, 2))]
+    out = []
+    for _ in range(n):
+        seq = [{"action": "send_message", "params": {"to": ["parent", "child"][int(rng.integers(0, 4) == 0)],
+                                                     "content": texts[int(rng.integers(0, len(texts)))]}},
+               {"action": "fetch_web", "params": {"url": ["https://example.com", "https://example.org"][int(rng.integers(0, 5) == 0)],
+                                                  "timeout": int(rng.integers(1, 60))}}]
+        roll = int(rng.integers(0, 12))
+        if roll == 0:
+            seq.append({"action": "orient", "params": {"current_situation": texts[0], "goal_clarity": texts[1],
+                                                       "available_resources": "cpu", "key_challenges": "latency",
+                                                       "delegation_consideration": "none"}})
+        elif roll == 1:
+            seq[1] = {"action": "file_read", "params": {"path": "/tmp/x"}}
+        if kind == "batch_async" and int(rng.integers(0, 6)) == 0:
+            seq = seq[::-1]                               # same cluster (sorted type list), positions no longer line up
+        r = {"action": kind, "params": {"actions": seq}, "reasoning": ["", "because"][int(rng.integers(0, 2))]}
+        w = [True, False, None, 3][int(rng.integers(0, 4))]
+        if w is not None:
+            r["wait"] = w
+        out.append(r)
+    return out
+
+
 def test_batched_decide_step_matches_the_oracle_format_result():
     """quoracle_b200.consensus.decide_tree == oracle Aggregator.cluster_responses + Result.format_result, decision
     by decision, when both see the same embedding function -- and the whole tree costs one embed call."""
@@ -166,6 +195,7 @@ def test_batched_decide_step_matches_the_oracle_format_result():
     ofn = lambda v, o: (lambda r: ("ok", {"embedding": r[1]["embedding"].astype(np.float64).tolist()}) if r[0] == "ok" else r)(fn(v, {}))  # noqa: E731
     rng = np.random.default_rng(11)
     pending = [{"agent_id": f"a{i}", "responses": _random_proposals(rng, int(rng.integers(3, 9)))} for i in range(60)]
+    pending += [{"agent_id": f"b{i}", "responses": _random_batch_proposals(rng, int(rng.integers(2, 7)))} for i in range(60)]
     for round_num in (1, 2, 6):
         emb2, ctx2 = make_emb()
         got = consensus.decide_tree(DecisionCollector(emb2), pending, round_num=round_num)
@@ -178,6 +208,9 @@ def test_batched_decide_step_matches_the_oracle_format_result():
                 continue
             kind, action, opts = ores.format_result(clusters, len(d["responses"]), round_num, {"embedding_fn": ofn})
             assert g["kind"] == kind, (d, g)
+            if action == "error":                        # the reference's {:error, reason} read as {action, acc}
+                assert g["action"]["action"] == "error" and g["action"]["error"] == opts.get("accumulator")
+                continue
             assert g["action"]["action"] == action["action"]
             assert g["action"]["params"] == action["params"], (g["action"], action)
             assert g["action"]["wait"] == action["wait"] and g["action"]["reasoning"] == action["reasoning"]
