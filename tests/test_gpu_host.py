@@ -89,13 +89,14 @@ def test_decide_tree_on_gpu_matches_oracle(emb):
     from oracle import aggregator as oagg
     from oracle import result as ores
     from quoracle_b200 import consensus
-    from tests.test_host_logic import _random_proposals
+    from tests.test_host_logic import _random_batch_proposals, _random_proposals
     fn = oracle_fn(emb)
     rng = np.random.default_rng(5)
     pending = [{"agent_id": f"a{i}", "responses": _random_proposals(rng, int(rng.integers(3, 9)))} for i in range(40)]
+    pending += [{"agent_id": f"b{i}", "responses": _random_batch_proposals(rng, int(rng.integers(2, 7)))} for i in range(30)]
     before = emb.ctx.launch_count()
     got = consensus.decide_tree(DecisionCollector(emb), pending, round_num=5)
-    assert emb.ctx.launch_count() - before <= 3 + 7                      # K1 + K2 + one K3 per pool size
+    assert emb.ctx.launch_count() - before <= 4 + 7                      # pack + K1 + K2 + one K3 per pool size
     for d, g in zip(pending, got):
         clusters = oagg.cluster_responses(d["responses"])
         kind, action, opts = ores.format_result(clusters, len(d["responses"]), 5, {"embedding_fn": fn})
