@@ -71,8 +71,9 @@ def term_order(v: Any):
         seq = [term_order(x) for x in v]
         return (rank, (len(seq),) if tag == "tuple" else (), tuple(seq))
     if tag == "map":
-        items = sorted(((term_order(kk), term_order(vv)) for kk, vv in v.items()))
-        return (rank, len(items), tuple(items))
+        # Erlang: maps compare by size, then by their keys in ascending term order, then by the values in key order
+        items = sorted(((term_order(kk), term_order(vv)) for kk, vv in v.items()), key=lambda kv: kv[0])
+        return (rank, len(items), tuple(k for k, _ in items), tuple(x for _, x in items))
     raise TypeError(tag)
 
 

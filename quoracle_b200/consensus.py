@@ -46,12 +46,28 @@ def _key(v):
     raise TypeError(type(v))
 
 
-_RANK = {"n": 0, "a": 1, "m": 3, "l": 4, "s": 5}
-
-
 def _order(v):
-    k = _key(v)
-    return (_RANK[k[0]],) + k[1:]
+    """Erlang term order, restated: number < atom < tuple < map < list < binary.  nil / true / false are atoms and
+    compare by name; lists compare element by element (a proper prefix is smaller); maps compare by size, then by
+    their keys in ascending term order, then by the values in key order."""
+    if isinstance(v, bool):
+        return (1, "true" if v else "false")
+    if v is None:
+        return (1, "nil")
+    if isinstance(v, int):
+        return (0, float(v), 0)
+    if isinstance(v, float):
+        return (0, v, 1)
+    if isinstance(v, str):
+        return (5, v.encode("utf-8"))
+    if isinstance(v, tuple):
+        return (2, len(v), tuple(_order(x) for x in v))
+    if isinstance(v, list):
+        return (4, tuple(_order(x) for x in v))
+    if isinstance(v, dict):
+        items = sorted(((_order(k), _order(x)) for k, x in v.items()), key=lambda kv: kv[0])
+        return (3, len(items), tuple(k for k, _ in items), tuple(x for _, x in items))
+    raise TypeError(type(v))
 
 
 def mode_value(values: Sequence[Any]):

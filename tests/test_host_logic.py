@@ -273,3 +273,44 @@ def test_cache_ttl_and_eviction_follow_the_reference():
     oemb.get_embedding("new", {"embedding_fn": lambda t: ("ok", [1.0]), "cache_table": table, "cache_ttl": 50_000,
                                "now_ms": lambda: now[0], "token_counter": tokenizer.count_tokens})
     assert len(table) == MAX_CACHE_ENTRIES - 100 + 1             # c.table lost b"new!" to the expiry check above
+
+
+def test_host_rules_agree_with_the_oracle_on_random_terms():
+    """Differential check of every rule that needs no embeddings (exact_match, mode_selection, union_merge,
+    structural_merge, percentile) on random nested terms: the product's restatement of Erlang term order and of the
+    rule arithmetic must give what the oracle's gives (ties between compound values are decided by term order)."""
+    import json
+    from quoracle_b200 import consensus
+    rng = np.random.default_rng(0)
+
+    def rand_val(depth=0):
+        k = int(rng.integers(0, 8))
+        if k == 0:
+            return int(rng.integers(-5, 50))
+        if k == 1:
+            return float(rng.integers(-5, 50)) / 2
+        if k == 2:
+            return bool(rng.integers(0, 2))
+        if k == 3:
+            return ["a", "b", "deploy now", "x y"][int(rng.integers(0, 4))]
+        if k == 4 and depth < 2:
+            return [rand_val(depth + 1) for _ in range(int(rng.integers(0, 4)))]
+        if k == 5 and depth < 2:
+            return {["k", "j", "m"][int(rng.integers(0, 3))]: rand_val(depth + 1) for _ in range(int(rng.integers(0, 3)))}
+        return int(rng.integers(0, 4))
+
+    rules = [("exact_match",), ("mode_selection",), ("union_merge",), ("structural_merge",), ("percentile", 50),
+             ("percentile", 75), ("percentile", 100), ("percentile", 10)]
+    for _ in range(6000):
+        rule = rules[int(rng.integers(0, len(rules)))]
+        vals = [rand_val() for _ in range(int(rng.integers(1, 7)))]
+        if rule[0] == "structural_merge":
+            vals = [v if isinstance(v, dict) else {"k": v} for v in vals]
+        want = orules.apply_rule(rule, vals)
+        got = consensus.host_rule(list(rule), vals)
+        assert want[0] == got[0], (rule, vals, want, got)
+        if want[0] == "ok":
+            assert type(want[1]) is type(got[1]) and json.dumps(want[1], sort_keys=True) == json.dumps(got[1], sort_keys=True), \
+                (rule, vals, want, got)
+        else:
+            assert want == got
