@@ -20,16 +20,17 @@ cosine_similarity = numeric.cosine_similarity_aggregator   # aggregator.ex:335-3
 def cluster_responses(responses: list) -> list:
     """cluster_responses/1 -- aggregator.ex:23-35.
 
-    group_by fingerprint, then a STABLE sort by count desc.  The order among equal counts is BEAM map
-    order over the fingerprint keys; oracle choice: sort keys by
-    (action, canonical JSON of the signature)."""
+    group_by fingerprint, then a STABLE sort by count desc.  The order among equal counts is BEAM map order over
+    the fingerprint keys `{action, signature}`: for the <= 32 clusters a pool can produce that is ascending Erlang
+    term order (flat maps keep their keys sorted), restated here as (action atom by name, term order of the
+    signature); above 32 keys BEAM iterates in hash order and the tie order is unpinned."""
     if not responses:
         return []
     groups: dict = {}
     for r in responses:
         fp = action_fingerprint(r)
         groups.setdefault(_fp_key(fp), (fp, []))[1].append(r)
-    ordered = sorted(groups.values(), key=lambda g: _fp_key(g[0]))
+    ordered = sorted(groups.values(), key=lambda g: (str(g[0][0]).encode("utf-8"), terms.term_order(g[0][1])))
     clusters = [{"count": len(actions), "actions": actions, "representative": actions[0], "fingerprint": fp}
                 for fp, actions in ordered]
     return sorted(clusters, key=lambda c: -c["count"])       # Python's sort is stable, like Enum.sort_by

@@ -172,15 +172,18 @@ def _key_terms(s: str, threshold: float) -> str:
 
 
 def fingerprint(response: dict):
+    """action_fingerprint/1 (aggregator.ex:72-103): (action, signature); the signature is the list of sub-action types
+    for batches, the map {param: normalised value} otherwise (create_action_signature/2, :366-421)."""
     action = response["action"]
     params = response.get("params") or {}
     if action in ("batch_sync", "batch_async"):
-        seq = [a.get("action", "unknown") if isinstance(a, dict) else "unknown" for a in (params.get("actions") or [])]
-        return (action, tuple(sorted(seq)) if action == "batch_async" else tuple(seq))
+        acts = params.get("actions") if isinstance(params, dict) and isinstance(params.get("actions"), list) else []
+        seq = [a["action"] if isinstance(a, dict) and isinstance(a.get("action"), str) else "unknown" for a in acts]
+        return (action, sorted(seq) if action == "batch_async" else seq)
     schema = SCHEMAS.get(action)
     if schema is None:
         return (action, "invalid")
-    sig = []
+    sig = {}
     for p in schema["required"] + schema["optional"]:
         v = params.get(p)
         if v is None:
@@ -195,23 +198,19 @@ def fingerprint(response: dict):
             v = "_percentile_mergeable"
         elif name == "union_merge" and isinstance(v, list):
             v = sorted(v, key=_order)
-        sig.append((p, _key(v)))
-    return (action, tuple(sig))
+        sig[p] = v
+    return (action, sig)
 
 
 def cluster(responses: Sequence[dict]) -> list:
+    """cluster_responses/1 (aggregator.ex:23-35): group by fingerprint, stable sort by count descending.  Equal counts
+    keep BEAM map order over the fingerprint keys, which for the <= 32 clusters of a pool is ascending Erlang term
+    order: action atom by name, then the signature (same restatement as the oracle)."""
     groups: "OrderedDict" = OrderedDict()
     for r in responses:
-        groups.setdefault(fingerprint(r), []).append(r)
-    # order among equal counts is BEAM map order in the reference, which is not reproducible; same documented choice
-    # as the oracle: by action, then by the canonical text of the signature (JSON for the
-    # action-type lists of batch fingerprints)
-    def order_key(kv):
-        action, sig = kv[0]
-        if action in ("batch_sync", "batch_async"):
-            return (str(action), json.dumps(list(sig)))
-        return (str(action), repr(sig))
-    ordered = sorted(groups.items(), key=order_key)
+        fp = fingerprint(r)
+        groups.setdefault((fp[0], _key(fp[1])), (fp, []))[1].append(r)
+    ordered = sorted(groups.values(), key=lambda g: (str(g[0][0]).encode("utf-8"), _order(g[0][1])))
     clusters = [{"count": len(a), "actions": a, "representative": a[0], "fingerprint": fp} for fp, a in ordered]
     return sorted(clusters, key=lambda c: -c["count"])
 

@@ -194,8 +194,8 @@ def test_batched_decide_step_matches_the_oracle_format_result():
     fn = emb.embedding_fn()
     ofn = lambda v, o: (lambda r: ("ok", {"embedding": r[1]["embedding"].astype(np.float64).tolist()}) if r[0] == "ok" else r)(fn(v, {}))  # noqa: E731
     rng = np.random.default_rng(11)
-    pending = [{"agent_id": f"a{i}", "responses": _random_proposals(rng, int(rng.integers(3, 9)))} for i in range(60)]
-    pending += [{"agent_id": f"b{i}", "responses": _random_batch_proposals(rng, int(rng.integers(2, 7)))} for i in range(60)]
+    pending = [{"agent_id": f"a{i}", "responses": _random_proposals(rng, int(rng.integers(2, 9)))} for i in range(400)]
+    pending += [{"agent_id": f"b{i}", "responses": _random_batch_proposals(rng, int(rng.integers(2, 7)))} for i in range(200)]
     for round_num in (1, 2, 6):
         emb2, ctx2 = make_emb()
         got = consensus.decide_tree(DecisionCollector(emb2), pending, round_num=round_num)
