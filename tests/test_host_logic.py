@@ -314,3 +314,28 @@ def test_host_rules_agree_with_the_oracle_on_random_terms():
                 (rule, vals, want, got)
         else:
             assert want == got
+
+
+def test_wait_rule_confidence_and_key_terms_agree_with_the_oracle():
+    """Differential checks of the three small pieces of Result / Aggregator arithmetic the product restates:
+    the wait-parameter merge (consensus_rules.ex:114-160 over result.ex:240-248; waits are true | false | integer),
+    calculate_confidence/4 (result.ex:261-286) and the key-term normalisation (aggregator.ex:423-454)."""
+    from oracle import aggregator as oagg
+    from oracle import result as ores
+    from quoracle_b200 import consensus
+    rng = np.random.default_rng(1)
+    for _ in range(5000):
+        vals = [[True, False, 0, 1, 5, 30, 60, 7, 2][int(rng.integers(0, 9))] for _ in range(int(rng.integers(1, 8)))]
+        want, got = ores._merge_wait_parameter(list(vals)), consensus.wait_rule(list(vals))
+        assert want == got and type(want) is type(got), (vals, want, got)
+    for _ in range(2000):
+        total = int(rng.integers(1, 12))
+        count, rnd, mx = int(rng.integers(1, total + 1)), int(rng.integers(1, 9)), int(rng.integers(1, 6))
+        want = ores.calculate_confidence({"count": count}, total, rnd, {"max_refinement_rounds": mx})
+        assert abs(want - consensus.confidence(count, total, rnd, mx)) < 1e-12
+    words = ["Deploy", "the", "build,", "to", "PRODUCTION!", "now", "please", "naïve", "x", "yyyy", "zzzzz", "a-b-c-d",
+             "foo_bar", "12345", "tab\\tsep", "new\\nline"]
+    for _ in range(5000):
+        s = " ".join(words[int(rng.integers(0, len(words)))] for _ in range(int(rng.integers(0, 9))))
+        thr = [0.8, 0.9, 0.95, 0.99][int(rng.integers(0, 4))]
+        assert oagg.normalize_semantic_string(s, thr) == consensus._key_terms(s, thr), (s, thr)
