@@ -27,71 +27,7 @@ PRIORITIES = _DATA["priorities"]
 DEFAULT_THRESHOLD = _DATA["default_semantic_threshold"]
 
 
-# ---- term helpers (strict equality / BEAM map order for small maps) -------------------------------------
-def _key(v):
-    if isinstance(v, bool):
-        return ("a", "true" if v else "false")
-    if v is None:
-        return ("a", "nil")
-    if isinstance(v, int):
-        return ("n", float(v), 0)
-    if isinstance(v, float):
-        return ("n", v, 1)
-    if isinstance(v, str):
-        return ("s", v.encode())
-    if isinstance(v, (list, tuple)):
-        return ("l", tuple(_key(x) for x in v))
-    if isinstance(v, dict):
-        return ("m", tuple(sorted((_key(k), _key(x)) for k, x in v.items())))
-    raise TypeError(type(v))
-
-
-def _order(v):
-    """Erlang term order, restated: number < atom < tuple < map < list < binary.  nil / true / false are atoms and
-    compare by name; lists compare element by element (a proper prefix is smaller); maps compare by size, then by
-    their keys in ascending term order, then by the values in key order."""
-    if isinstance(v, bool):
-        return (1, "true" if v else "false")
-    if v is None:
-        return (1, "nil")
-    if isinstance(v, int):
-        return (0, float(v), 0)
-    if isinstance(v, float):
-        return (0, v, 1)
-    if isinstance(v, str):
-        return (5, v.encode("utf-8"))
-    if isinstance(v, tuple):
-        return (2, len(v), tuple(_order(x) for x in v))
-    if isinstance(v, list):
-        return (4, tuple(_order(x) for x in v))
-    if isinstance(v, dict):
-        items = sorted(((_order(k), _order(x)) for k, x in v.items()), key=lambda kv: kv[0])
-        return (3, len(items), tuple(k for k, _ in items), tuple(x for _, x in items))
-    raise TypeError(type(v))
-
-
-def mode_value(values: Sequence[Any]):
-    """Most frequent value; ties -> first in term order (Enum.frequencies + Enum.max_by, result.ex:367-372)."""
-    counts: "OrderedDict" = OrderedDict()
-    for v in values:
-        k = _key(v)
-        c = counts.setdefault(k, [0, v])
-        c[0] += 1
-    best = None
-    for k in sorted(counts, key=lambda kk: _order(counts[kk][1])):
-        if best is None or counts[k][0] > counts[best][0]:
-            best = k
-    return counts[best][1]
-
-
-def _uniq(values):
-    seen, out = set(), []
-    for v in values:
-        k = _key(v)
-        if k not in seen:
-            seen.add(k)
-            out.append(v)
-    return out
+from .terms import key as _key, mode_value, order as _order, uniq as _uniq  # noqa: E402
 
 
 # ---- non-semantic rules (consensus_rules.ex:49-163) --------------------------------------------------------

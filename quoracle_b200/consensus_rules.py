@@ -14,18 +14,9 @@ from typing import Any, Optional, Sequence
 import numpy as np
 
 from .embeddings import Embeddings
+from .terms import uniq as _uniq
 
 DEFAULT_THRESHOLD = 0.9   # consensus_rules.ex:19
-
-
-def _uniq(values):
-    seen, out = set(), []
-    for v in values:
-        k = (type(v).__name__, repr(v))
-        if k not in seen:
-            seen.add(k)
-            out.append(v)
-    return out
 
 
 def decide_many(emb: Embeddings, merges: Sequence[tuple[Sequence[Any], float]]):
