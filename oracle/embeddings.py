@@ -92,7 +92,10 @@ def get_embedding(text: Any, options: Optional[dict] = None):
     -> ("ok", {"embedding", "cached", "chunks"}) | ("ok", result, acc) | ("error", atom)."""
     options = dict(options or {})
     if not isinstance(text, str):
-        text = json.dumps(text, separators=(",", ":"))            # Jason.encode!/1 (compact), embeddings.ex:46
+        # Jason.encode!/1 (compact), embeddings.ex:46.  Jason walks a map in BEAM iteration order, which for the small
+        # maps that occur as parameter values is ascending key order: two equal maps give the same text whatever order
+        # their keys were written in
+        text = json.dumps(text, separators=(",", ":"), sort_keys=True, ensure_ascii=False)
     if text == "":
         return ("error", "invalid_input")
     table = options.get("cache_table", _default_cache)

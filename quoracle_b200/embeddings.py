@@ -90,7 +90,8 @@ class Embeddings:
 
     @staticmethod
     def _stringify(value: Any) -> str:
-        return value if isinstance(value, str) else json.dumps(value, separators=(",", ":"))
+        # Jason.encode!/1 (embeddings.ex:46): compact, keys in BEAM map order (ascending for small maps), UTF-8 as is
+        return value if isinstance(value, str) else json.dumps(value, separators=(",", ":"), sort_keys=True, ensure_ascii=False)
 
     def get_embeddings(self, values: Sequence[Any], cache_ttl: int = DEFAULT_CACHE_TTL_MS) -> list:
         """Batched get_embedding: one GPU call for every uncached chunk of every value.

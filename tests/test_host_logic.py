@@ -339,3 +339,16 @@ def test_wait_rule_confidence_and_key_terms_agree_with_the_oracle():
         s = " ".join(words[int(rng.integers(0, len(words)))] for _ in range(int(rng.integers(0, 9))))
         thr = [0.8, 0.9, 0.95, 0.99][int(rng.integers(0, 4))]
         assert oagg.normalize_semantic_string(s, thr) == consensus._key_terms(s, thr), (s, thr)
+
+
+def test_equal_maps_embed_the_same_text_whatever_their_key_order():
+    """Jason.encode!/1 (embeddings.ex:46) walks a map in BEAM order, so equal maps give one text: same cache entry, one
+    row on the GPU, and a pool of equal maps short-circuits without any embedding call (consensus_rules.ex:251-256)."""
+    emb, ctx = make_emb()
+    a, b = {"path": "/tmp/x", "mode": "r"}, {"mode": "r", "path": "/tmp/x"}
+    r = emb.get_embeddings([a, b, {"path": "/tmp/y"}])
+    assert ctx.calls["embed"] == 1 and np.array_equal(r[0][1]["embedding"], r[1][1]["embedding"])
+    assert oemb.get_embedding(a, {"embedding_fn": lambda t: ("ok", [float(len(t))]), "cache_ttl": 0})[1]["embedding"] == \\
+        oemb.get_embedding(b, {"embedding_fn": lambda t: ("ok", [float(len(t))]), "cache_ttl": 0})[1]["embedding"]
+    res, _ = consensus_rules.decide_many(emb, [([a, b, dict(a)], 0.9)])
+    assert res == [("ok", a)] and ctx.calls["embed"] == 1                  # no further embedding call
