@@ -348,7 +348,8 @@ def test_equal_maps_embed_the_same_text_whatever_their_key_order():
     a, b = {"path": "/tmp/x", "mode": "r"}, {"mode": "r", "path": "/tmp/x"}
     r = emb.get_embeddings([a, b, {"path": "/tmp/y"}])
     assert ctx.calls["embed"] == 1 and np.array_equal(r[0][1]["embedding"], r[1][1]["embedding"])
-    assert oemb.get_embedding(a, {"embedding_fn": lambda t: ("ok", [float(len(t))]), "cache_ttl": 0})[1]["embedding"] == \\
-        oemb.get_embedding(b, {"embedding_fn": lambda t: ("ok", [float(len(t))]), "cache_ttl": 0})[1]["embedding"]
+    ofn = lambda t: ("ok", [float(len(t)), float(sum(t.encode()))])          # noqa: E731 - depends on the text only
+    assert oemb.get_embedding(a, {"embedding_fn": ofn, "cache_ttl": 0})[1]["embedding"] == \
+        oemb.get_embedding(b, {"embedding_fn": ofn, "cache_ttl": 0})[1]["embedding"]
     res, _ = consensus_rules.decide_many(emb, [([a, b, dict(a)], 0.9)])
     assert res == [("ok", a)] and ctx.calls["embed"] == 1                  # no further embedding call
