@@ -187,6 +187,76 @@ rule_vectors = {
     ],
 }
 
+# :batch_sequence_merge known answers (2-arity apply_rule: no embeddings needed, semantic values are identical).
+BATCH = "test/quoracle/actions/consensus_rules_batch_test.exs"
+_fr = lambda path, **kw: {"action": "file_read", "params": dict({"path": path}, **kw)}       # noqa: E731
+_todo = lambda op: {"action": "todo", "params": {"operation": op}}                           # noqa: E731
+_orient = lambda s: {"action": "orient", "params": {"current_situation": s}}                 # noqa: E731
+_spawn = {"action": "spawn_child", "params": {"task_description": "Process data", "success_criteria": "Complete",
+                                              "immediate_context": "Test", "approach_guidance": "Standard",
+                                              "profile": "test"}}
+batch_merge = [
+    {"src": f"{BATCH}:15-31", "sequences": [[_fr("/a.txt"), _todo("list")], [_fr("/a.txt"), _todo("list")]],
+     "expect": "ok", "length": 2},
+    {"src": f"{BATCH}:34-49", "sequences": [[_fr("/a.txt"), _todo("list")], [_fr("/b.txt")]],
+     "expect": ["error", "sequence_length_mismatch"]},
+    {"src": f"{BATCH}:52-68", "sequences": [[_fr("/a.txt"), _todo("list")], [_todo("add"), _fr("/b.txt")]],
+     "expect": ["error", "sequence_mismatch"]},
+    {"src": f"{BATCH}:71-98", "sequences": [[_fr("/a.txt", limit=100), _orient("Testing")],
+                                            [_fr("/a.txt", limit=200), _orient("Testing")]],
+     "expect": "ok", "length": 2,
+     "merged": [{"action": "file_read", "params": {"path": "/a.txt", "limit": 150}},
+                {"action": "orient", "params": {"current_situation": "Testing"}}],
+     "note": "path exact_match, limit percentile 50 of 100, 200 = 150, current_situation identical -> no embedding call"},
+    {"src": f"{BATCH}:101-116", "sequences": [[_fr("/a.txt")], [_fr("/b.txt")]], "expect": ["error", "no_consensus"],
+     "note": "exact_match on differing paths fails the whole merge"},
+    {"src": f"{BATCH}:119-137", "sequences": [[_todo("list"), _orient("Same")], [_todo("list"), _orient("Same")]],
+     "expect": "ok", "length": 2, "actions": ["todo", "orient"]},
+    {"src": f"{BATCH}:140-142", "sequences": [], "expect": "ok", "length": 0},
+    {"src": f"{BATCH}:145-156", "sequences": [[_fr("/a.txt"), _todo("list")]], "expect": "ok", "length": 2,
+     "actions": ["file_read", "todo"]},
+    {"src": f"{BATCH}:160-170", "sequences": [[_todo("list")], [_todo("list")], [_todo("list")]], "expect": "ok",
+     "length": 1, "actions": ["todo"]},
+    {"src": f"{BATCH}:172-203", "sequences": [[_spawn], [_spawn]], "expect": "ok", "length": 1, "actions": ["spawn_child"]},
+]
+
+# batch_sync clusters in Result (tie-break by the MAX priority of the sequence, structural errors propagate)
+RBATCH = "test/quoracle/consensus/result_batch_sync_test.exs"
+
+
+def _batch_cluster(actions, count=2, wait=False):
+    rep = {"action": "batch_sync", "params": {"actions": actions}, "reasoning": ""}
+    return {"representative": rep, "actions": [{"action": "batch_sync", "params": {"actions": actions}, "wait": wait}],
+            "count": count}
+
+
+batch_result = {
+    "break_tie": [
+        {"src": f"{RBATCH}:18-63",
+         "clusters": [_batch_cluster([{"action": "spawn_child", "params": {"task_description": "test"}},
+                                      {"action": "file_read", "params": {"path": "/tmp/a.txt"}}]),
+                      {"representative": {"action": "todo", "params": {"items": []}, "reasoning": ""},
+                       "actions": [{"action": "todo", "wait": False, "params": {"items": []}}], "count": 2}],
+         "expect_action": "todo", "note": "a batch ranks by the max priority of its members, not by batch_sync's own"},
+        {"src": f"{RBATCH}:65-127",
+         "clusters": [_batch_cluster([{"action": "file_read", "params": {"path": "/tmp/a.txt"}},
+                                      {"action": "todo", "params": {"items": []}}]),
+                      _batch_cluster([{"action": "file_read", "params": {"path": "/tmp/b.txt"}},
+                                      {"action": "spawn_child", "params": {"task_description": "test"}}])],
+         "expect_first_path": "/tmp/a.txt", "note": "lower max priority wins the tie"},
+    ],
+    "merge_error": {
+        "src": f"{RBATCH}:288-331",
+        "cluster": {"actions": [{"action": "batch_sync", "params": {"actions": [{"action": "file_read", "params": {"path": "/tmp/a.txt"}}]},
+                                 "reasoning": "One file", "wait": False},
+                                {"action": "batch_sync", "params": {"actions": [{"action": "file_read", "params": {"path": "/tmp/a.txt"}},
+                                                                                {"action": "file_read", "params": {"path": "/tmp/b.txt"}}]},
+                                 "reasoning": "Two files", "wait": False}],
+                    "representative": {"action": "batch_sync", "params": {"actions": [{"action": "file_read", "params": {"path": "/tmp/a.txt"}}]},
+                                       "reasoning": "One file"}},
+        "expect": ["error", "sequence_length_mismatch"]},
+}
+
 out = {
     "reference": "shelvick/quoracle @ 6c0f0eb7 (app 0.2.4)",
     "how": "transcribed from the reference's ExUnit tests by tests/golden/make_golden.py; the reference "
@@ -198,6 +268,8 @@ out = {
     "sha_embedding": sha_embedding,
     "constant_embedding_rule": constant_embedding_rule,
     "rules": rule_vectors,
+    "batch_merge": batch_merge,
+    "batch_result": batch_result,
 }
 
 if __name__ == "__main__":

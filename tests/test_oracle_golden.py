@@ -330,3 +330,51 @@ def test_numpy_batch_matches_scalar_oracle_and_c_port():
         assert numeric.medoid_vote(m) == med[b]
         assert numeric.reference_rule(e, 0.1) == bool(ok[b])
     assert np.all(cos[3, 2] == 0.0)
+
+
+@pytest.mark.parametrize("case", GOLD["batch_merge"], ids=lambda c: c["src"].split(":")[-1])
+def test_batch_sequence_merge_known_answers(case):
+    """The reference's own :batch_sequence_merge tests (consensus_rules_batch_test.exs) against the oracle AND the
+    product's two-pass restatement (quoracle_b200.consensus: plan on the host, semantic merges through the collector)."""
+    from oracle import consensus_rules as orules
+    from quoracle_b200 import consensus
+    from quoracle_b200.collector import DecisionCollector
+    from quoracle_b200.embeddings import Embeddings
+    from quoracle_b200 import synth
+    from tests.fake_ctx import FakeContext
+
+    def check(r):
+        if case["expect"] == "ok":
+            assert r[0] == "ok" and len(r[1]) == case["length"], r
+            if "actions" in case:
+                assert [a["action"] for a in r[1]] == case["actions"]
+            if "merged" in case:
+                assert r[1] == case["merged"]
+        else:
+            assert list(r) == case["expect"], r
+
+    check(orules.apply_rule(("batch_sequence_merge",), case["sequences"]))
+    w = synth.make_encoder(64, vocab=512, seed=1)
+    ctx = FakeContext(w.table_bf16, w.w_bf16)
+    col = DecisionCollector(Embeddings(ctx, vocab=512))
+    state, payload = consensus._plan_batch_merge(col, "agent", "batch_sync", case["sequences"])
+    results = col.flush()
+    check(payload if state == "done" else consensus._finish_batch_merge(payload, results, "agent"))
+    assert ctx.calls["embed"] == 0                       # identical semantic values never reach the encoder
+
+
+def test_batch_sync_clusters_in_result_known_answers():
+    """result_batch_sync_test.exs: a batch cluster ranks by the MAX priority of its sequence; structural merge errors
+    propagate out of merge_cluster_params.  Oracle and product."""
+    from quoracle_b200 import consensus
+    for case in GOLD["batch_result"]["break_tie"]:
+        for winner in (result.break_tie(case["clusters"]), consensus.pick_winner(case["clusters"], 4)[1]):
+            if "expect_action" in case:
+                assert winner["representative"]["action"] == case["expect_action"], case["src"]
+            else:
+                assert winner["representative"]["params"]["actions"][0]["params"]["path"] == case["expect_first_path"]
+    case = GOLD["batch_result"]["merge_error"]
+    assert list(result.merge_cluster_params(case["cluster"])) == case["expect"]
+    seqs = [a["params"]["actions"] for a in case["cluster"]["actions"]]
+    state, payload = consensus._plan_batch_merge(None, "agent", "batch_sync", seqs)   # decided before any collector use
+    assert state == "done" and list(payload) == case["expect"]
