@@ -378,3 +378,55 @@ def test_batch_sync_clusters_in_result_known_answers():
     seqs = [a["params"]["actions"] for a in case["cluster"]["actions"]]
     state, payload = consensus._plan_batch_merge(None, "agent", "batch_sync", seqs)   # decided before any collector use
     assert state == "done" and list(payload) == case["expect"]
+
+
+def test_batch_fingerprints_and_priorities_known_answers():
+    """batch_consensus_test.exs:26-137,209-255 and batch_async_consensus_test.exs:33-236,309-418: batch_sync
+    fingerprints are the ORDERED list of sub-action types, batch_async the SORTED one, the two never cluster together;
+    an empty or missing `actions` list ranks with the default priority 999.  Oracle and product."""
+    from quoracle_b200 import consensus
+
+    def batch(kind, types):
+        return {"action": kind, "params": {"actions": [{"action": t, "params": {}} for t in types]}, "reasoning": ""}
+
+    for fp, cluster_fn in ((aggregator.action_fingerprint, aggregator.cluster_responses),
+                           (consensus.fingerprint, consensus.cluster)):
+        norm = lambda x: (x[0], list(x[1]))                                       # noqa: E731
+        assert norm(fp(batch("batch_sync", ["file_read", "todo"]))) == ("batch_sync", ["file_read", "todo"])
+        assert norm(fp(batch("batch_async", ["todo", "file_read"]))) == ("batch_async", ["file_read", "todo"])
+        assert norm(fp(batch("batch_async", ["todo", "file_read", "fetch_web"]))) == \
+            ("batch_async", ["fetch_web", "file_read", "todo"])
+        assert fp(batch("batch_sync", ["file_read", "todo"]))[0] != fp(batch("batch_async", ["file_read", "todo"]))[0]
+        # same actions, different order: one cluster for batch_async, two for batch_sync
+        assert len(cluster_fn([batch("batch_async", ["file_read", "todo"]), batch("batch_async", ["todo", "file_read"])])) == 1
+        assert len(cluster_fn([batch("batch_sync", ["file_read", "todo"]), batch("batch_sync", ["todo", "file_read"])])) == 2
+        assert len(cluster_fn([batch("batch_async", ["file_read", "todo"]), batch("batch_async", ["file_read", "orient"])])) == 2
+        assert norm(fp({"action": "batch_sync", "params": {}, "reasoning": ""})) == ("batch_sync", [])
+    for kind in ("batch_sync", "batch_async"):
+        for rep in (batch(kind, []), {"action": kind, "params": {}, "reasoning": ""}):
+            c = {"representative": rep, "actions": [rep], "count": 1}
+            assert result.calculate_cluster_priority(c) == 999 and consensus._priority(c) == 999
+        c = {"representative": batch(kind, ["orient", "file_read"]), "actions": [], "count": 1}
+        assert result.calculate_cluster_priority(c) == consensus._priority(c) == 6          # max(orient 1, file_read 6)
+
+
+def test_round_penalty_uses_max_refinement_rounds_known_answers():
+    """max_refinement_rounds_test.exs:178-236: the -0.1 per round penalty counts rounds beyond `max_refinement_rounds`
+    (default 4): 2-of-3 at round 5 -> 2/3 + 0.10 - 0.10 = 0.667; max 0 penalises from round 1; the option threads
+    through format_result.  Oracle and product."""
+    from quoracle_b200 import consensus
+    action = {"action": "orient", "params": {"current_situation": "test", "goal_clarity": "test", "available_resources": "test",
+                                            "key_challenges": "test", "delegation_consideration": "none"},
+              "reasoning": "test reasoning"}
+    cluster = {"count": 2, "actions": [action, action], "representative": action}
+
+    def conf(rnd, mx=None):
+        opts = {} if mx is None else {"max_refinement_rounds": mx}
+        o = result.format_result([cluster], 3, rnd, opts)[2]["confidence"]
+        p = consensus.confidence(2, 3, rnd, 4 if mx is None else mx)
+        assert abs(o - p) < 1e-12
+        return o
+
+    assert abs(conf(5) - 0.667) < 0.001
+    assert conf(1, 0) < conf(1, 4)
+    assert conf(6, 2) < conf(6, 8)
