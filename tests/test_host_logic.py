@@ -353,3 +353,34 @@ def test_equal_maps_embed_the_same_text_whatever_their_key_order():
         oemb.get_embedding(b, {"embedding_fn": ofn, "cache_ttl": 0})[1]["embedding"]
     res, _ = consensus_rules.decide_many(emb, [([a, b, dict(a)], 0.9)])
     assert res == [("ok", a)] and ctx.calls["embed"] == 1                  # no further embedding call
+
+
+def test_semantic_similarity_mirror_agrees_with_the_oracle():
+    """Aggregator.calculate_semantic_similarity/3 (aggregator.ex:249-289): float for a pair, 0.0 when an embedding is
+    unavailable, `(float, acc)` with an accumulator; many pairs cost one embedding call."""
+    from oracle import aggregator as oagg
+    from quoracle_b200 import aggregator as pagg
+    emb, ctx = make_emb()
+    fn = emb.embedding_fn()
+    ofn = lambda t: (lambda r: ("ok", r[1]["embedding"].astype(np.float64).tolist()) if r[0] == "ok" else r)(fn(t, {}))  # noqa: E731
+    pairs = [("deploy the build", "deploy the new build"), ("alpha", "alpha"), ("", "x"), ({"k": 1}, {"k": 1}),
+             ("summarise revenue figures", "zebra quartz")]
+    emb2, ctx2 = make_emb()
+    got = pagg.semantic_similarity_many(emb2, pairs)
+    assert ctx2.calls["embed"] == 1 and ctx2.calls["similarity"] == 1
+    for (a, b), g in zip(pairs, got):
+        sa, sb = (x if isinstance(x, str) else oemb.json.dumps(x, separators=(",", ":"), sort_keys=True) for x in (a, b))
+        want = oagg.calculate_semantic_similarity(sa, sb, {"embedding_fn": ofn}) if sa and sb else 0.0
+        assert abs(g - want) < 1e-6, (a, b, g, want)
+    assert got[1] == pytest_approx_one(got[1]) and got[2] == 0.0
+    acc = orules.Accumulator()
+    emb3, _ = make_emb()
+    sim, acc2 = pagg.calculate_semantic_similarity(emb3, "first text", "second text", acc)
+    assert isinstance(sim, float) and acc2.count() == 2
+    sim_b, acc3 = pagg.calculate_semantic_similarity(emb3, "first text", "second text", acc2)
+    assert sim_b == sim and acc3.count() == 2                               # both cached: nothing accumulates
+
+
+def pytest_approx_one(x):
+    assert abs(x - 1.0) < 1e-6
+    return x
