@@ -140,3 +140,22 @@ def test_http_facade_serves_the_library_embeddings(emb):
         assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
     finally:
         srv.stop()
+
+
+def test_semantic_similarity_pairs_on_gpu(emb):
+    """Aggregator.calculate_semantic_similarity/3 mirror on the real GPU path vs the oracle's f64 cosine of the same
+    (f32) embeddings: many pairs, one embedding call, one K3 launch."""
+    from oracle import aggregator as oagg
+    from quoracle_b200 import aggregator as pagg
+    pairs = [(SENTENCES[0], SENTENCES[1]), (SENTENCES[2], SENTENCES[3]), (SENTENCES[4], SENTENCES[4]), ("", SENTENCES[0])]
+    before = emb.ctx.launch_count()
+    got = pagg.semantic_similarity_many(emb, pairs)
+    assert emb.ctx.launch_count() - before <= 4                       # (pack +) K1 + K2 + one K3
+    for (a, b), g in zip(pairs, got):
+        if not a or not b:
+            assert g == 0.0
+            continue
+        ea, eb = emb.get_embedding(a)[1]["embedding"], emb.get_embedding(b)[1]["embedding"]
+        want = oagg.cosine_similarity(ea.astype(np.float64).tolist(), eb.astype(np.float64).tolist())
+        assert abs(g - want) < 1e-6
+    assert abs(got[2] - 1.0) < 1e-6
