@@ -26,7 +26,7 @@
 #include "ptx.cuh"
 
 #ifndef QC_TC_SPLIT_GROUPS
-#define QC_TC_SPLIT_GROUPS 1
+#define QC_TC_SPLIT_GROUPS 2
 #endif
 
 namespace qc {
