@@ -283,6 +283,11 @@ int qc_encoder_token_block(qc_ctx* ctx, int T, int32_t* token_block);
  * mode 0 = auto (default), 1 = never pack, 2 = always pack.
  */
 int qc_encoder_set_packing(qc_ctx* ctx, int mode);
+/* Host-only test hook (needs no device): the packed-stream plan for `lens` at the given token block, written to
+ * out as [chunk_src | chunk_n | chunk_row] (nchunks entries each, sources relative to a padded [R x T] id matrix)
+ * followed by row_start (R + 1 entries); out_capacity counts int32 slots. */
+int qc_debug_pack_plan(const int32_t* lens, int R, int T, int token_block, int32_t* out, int64_t out_capacity,
+                       int32_t* nchunks, int32_t* nruns);
 int qc_encoder_hint_block_map(qc_ctx* ctx, const int32_t* d_block_map, int nslots);
 
 /* Test/tuning hook: K3 kernel for pools of 9..64 candidates. 0 = auto (tcgen05 kind::tf32 kernel when the

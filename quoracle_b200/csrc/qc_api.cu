@@ -829,6 +829,28 @@ int qc_similarity_batch_dev(qc_ctx* c, const float* d_emb, int B, int N, int D, 
   return QC_OK;
 }
 
+// Host-only: the packed-stream plan exactly as the host entry points build it (no device, no context needed), so the
+// planner that drives K1's gather and K2's row ranges can be checked where there is no GPU.
+int qc_debug_pack_plan(const int32_t* lens, int R, int T, int token_block, int32_t* out, int64_t out_capacity,
+                       int32_t* nchunks_out, int32_t* nruns_out) {
+  if (lens == nullptr || out == nullptr || nchunks_out == nullptr || nruns_out == nullptr || R < 0 || T < 1 ||
+      token_block < 8 || token_block % 8 != 0)
+    return QC_ERR_INVALID_INPUT;
+  const int CH = qc::encoder_chunk_tokens(token_block), nch = token_block / CH;
+  long long chunks = 0;
+  for (int r = 0; r < R; ++r) {
+    if (lens[r] < 0 || lens[r] > T) return QC_ERR_INVALID_INPUT;
+    chunks += (lens[r] + CH - 1) / CH;
+  }
+  const long long nchunks = (chunks + nch - 1) / nch * nch;
+  if (3 * nchunks + R + 1 > out_capacity) return QC_ERR_INVALID_INPUT;
+  const long long runs = fill_pack_plan(lens, R, CH, nch, nchunks, [T](int r) { return static_cast<long long>(r) * T; }, out,
+                                        out + nchunks, out + 2 * nchunks, out + 3 * nchunks);
+  *nchunks_out = static_cast<int32_t>(nchunks);
+  *nruns_out = static_cast<int32_t>(runs);
+  return QC_OK;
+}
+
 int qc_encoder_set_packing(qc_ctx* c, int mode) {
   if (c == nullptr || mode < 0 || mode > 2) return QC_ERR_INVALID_INPUT;
   c->packing = mode;

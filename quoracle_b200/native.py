@@ -34,10 +34,25 @@ ABI_SYMBOLS = (
     "qc_check_status", "qc_last_hang",
     "qc_launch_count", "qc_profile_enable", "qc_profile_reset", "qc_kernel_stats",
     "qc_encoder_info", "qc_encoder_set_cta_group", "qc_encoder_set_variant", "qc_encoder_stall_profile",
-    "qc_similarity_set_path", "qc_encoder_token_block", "qc_encoder_hint_block_map", "qc_encoder_set_packing",
+    "qc_similarity_set_path", "qc_encoder_token_block", "qc_encoder_hint_block_map", "qc_encoder_set_packing", "qc_debug_pack_plan",
     "qc_split_create", "qc_split_export", "qc_split_attach", "qc_decide_split_dev", "qc_split_gathered",
     "qc_split_destroy", "qc_tsplit_create", "qc_embed_tsplit_dev", "qc_decide_tsplit_dev",
 )
+
+
+def debug_pack_plan(lens: np.ndarray, t: int, token_block: int):
+    """Host-only (no GPU): the packed-stream plan the host entry points would build -> dict of int32 arrays."""
+    lib = load_library()
+    lens = np.ascontiguousarray(lens, dtype=np.int32).reshape(-1)
+    r = lens.shape[0]
+    cap = 3 * (int(lens.sum()) // 8 + r + token_block) + r + 1
+    out = np.zeros(cap, np.int32)
+    nchunks, nruns = ctypes.c_int32(), ctypes.c_int32()
+    _check(lib.qc_debug_pack_plan(_ptr(lens), r, int(t), int(token_block), _ptr(out), cap, ctypes.byref(nchunks),
+                                  ctypes.byref(nruns)))
+    n = nchunks.value
+    return {"chunk_src": out[:n], "chunk_n": out[n:2 * n], "chunk_row": out[2 * n:3 * n],
+            "row_start": out[3 * n:3 * n + r + 1], "nruns": nruns.value}
 
 
 class QcError(RuntimeError):
@@ -146,6 +161,8 @@ def load_library() -> ctypes.CDLL:
                                     ctypes.POINTER(ctypes.c_int32)]
     lib.qc_encoder_set_variant.restype = i32
     lib.qc_encoder_set_variant.argtypes = [vp, i32, i32, i32, i32]
+    lib.qc_debug_pack_plan.restype = i32
+    lib.qc_debug_pack_plan.argtypes = [vp, i32, i32, i32, vp, ctypes.c_int64, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.qc_encoder_set_packing.restype = i32
     lib.qc_encoder_set_packing.argtypes = [vp, i32]
     lib.qc_encoder_token_block.restype = i32

@@ -1,6 +1,7 @@
 """CPU tests of the host-side mirror (tokenizer, Embeddings, consensus rule, collector, lesson manager,
 sharding maths) with a fake context whose arithmetic is the oracle's."""
 import numpy as np
+import pytest
 
 from oracle import consensus_rules as orules
 from oracle import embeddings as oemb
@@ -384,3 +385,41 @@ def test_semantic_similarity_mirror_agrees_with_the_oracle():
 def pytest_approx_one(x):
     assert abs(x - 1.0) < 1e-6
     return x
+
+
+def test_packed_stream_plan_invariants():
+    """The host-side planner behind the packed token stream (qc_debug_pack_plan: same code the host entry points run,
+    no device needed).  Checked from first principles for 32-, 16- and 8-token chunks: every valid token is covered
+    exactly once and in order, chunks never mix candidates, a partial row never crosses a block, a candidate's rows
+    are consecutive, padding chunks trail and point nowhere."""
+    from quoracle_b200 import native
+    rng = np.random.default_rng(4)
+    for tb, ch in ((128, 32), (64, 32), (48, 16), (56, 8), (104, 8), (112, 16)):
+        nch = tb // ch
+        for trial in range(30):
+            r, t = int(rng.integers(1, 40)), int(rng.integers(1, 400))
+            lens = rng.integers(0, t + 1, size=r).astype(np.int32)
+            if trial % 5 == 0:
+                lens[rng.integers(0, r)] = 0
+            if trial % 7 == 0:
+                lens[:] = 0
+            plan = native.debug_pack_plan(lens, t, tb)
+            src, cnt, crow, row = plan["chunk_src"], plan["chunk_n"], plan["chunk_row"], plan["row_start"]
+            n = src.shape[0]
+            assert n % nch == 0 and n == -(-int(np.sum(-(-lens // ch))) // nch) * nch
+            k = 0
+            for cand in range(r):
+                nchunks = -(-int(lens[cand]) // ch)
+                assert row[cand + 1] - row[cand] == (0 if nchunks == 0 else len(set(crow[k:k + nchunks].tolist())))
+                for j in range(nchunks):
+                    assert src[k] == cand * t + j * ch and cnt[k] == min(ch, lens[cand] - j * ch)
+                    assert row[cand] <= crow[k] < row[cand + 1]
+                    if j > 0:                                   # same row iff same block, rows ascend by one
+                        same_block = (k // nch) == ((k - 1) // nch)
+                        assert crow[k] == crow[k - 1] + (0 if same_block else 1)
+                    k += 1
+            assert np.all(cnt[k:] == 0) and np.all(crow[k:] == -1)
+            assert row[0] == 0 and row[r] == plan["nruns"] == (int(crow[:k].max()) + 1 if k else 0)
+            assert np.all(np.diff(crow[:k]) >= 0) and np.all(np.diff(crow[:k]) <= 1)
+    with pytest.raises(native.QcError):
+        native.debug_pack_plan(np.array([5], np.int32), 4, 128)          # len > T
