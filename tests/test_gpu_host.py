@@ -114,7 +114,7 @@ def test_http_facade_serves_the_library_embeddings(emb):
     from oracle import encoder as oenc
     from quoracle_b200 import tokenizer
     from quoracle_b200.http_facade import EmbeddingServer
-    srv = EmbeddingServer(emb, max_wait_ms=20.0).start()
+    srv = EmbeddingServer(emb, max_wait_ms=250.0).start()   # generous window: the assertion is about coalescing, not latency
     try:
         texts = [f"agent {i}: restart service {i % 5} after the config change" for i in range(16)]
         out = [None] * len(texts)
