@@ -46,3 +46,8 @@ def calculate_semantic_similarity(emb: Embeddings, text1: Any, text2: Any, cost_
             if r[0] == "ok" and not r[1]["cached"]:
                 acc = acc.add({"cost_type": "llm_embedding", "cost_usd": None, "chunks": r[1]["chunks"]})
     return (sim, acc)
+
+
+def semantic_similarity_with_embeddings(emb: Embeddings, text1: Any, text2: Any, threshold: float) -> bool:
+    """semantic_similarity_with_embeddings/4 (aggregator.ex:352-362): similarity >= threshold."""
+    return calculate_semantic_similarity(emb, text1, text2) >= threshold

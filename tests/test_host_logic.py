@@ -380,6 +380,9 @@ def test_semantic_similarity_mirror_agrees_with_the_oracle():
     assert isinstance(sim, float) and acc2.count() == 2
     sim_b, acc3 = pagg.calculate_semantic_similarity(emb3, "first text", "second text", acc2)
     assert sim_b == sim and acc3.count() == 2                               # both cached: nothing accumulates
+    assert pagg.semantic_similarity_with_embeddings(emb3, "first text", "first text", 0.999999) is True
+    assert pagg.semantic_similarity_with_embeddings(emb3, "first text", "", 0.0) is True     # 0.0 >= 0.0, as in the reference
+    assert pagg.semantic_similarity_with_embeddings(emb3, "first text", "", 0.1) is False
 
 
 def pytest_approx_one(x):
