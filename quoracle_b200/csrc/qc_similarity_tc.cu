@@ -270,9 +270,14 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
     uint32_t ci = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int ch = 0; ch < nchunks; ++ch, ++ci) {
-        if (static_cast<int>(ci % kSplitGroups) != grp) continue;
         const uint32_t s = ci % kStages;
+        // Every group observes EVERY phase of raw_full, its own chunks or not: an mbarrier parity wait cannot tell
+        // phase k from phase k - 2, so a group that skipped the chunks of the other groups could ask for phase k of a
+        // stage whose phase k - 1 (another group's chunk, five chunks earlier) has not landed yet -- TMA completions
+        // are not ordered -- and be let through on stale data.  Observing all phases keeps every waiter within one
+        // phase of the barrier; it cannot fall two behind either, because the ring stalls on its own chunks first.
         w_raw += mbar_wait_parked(&raw_full[s], (ci / kStages) & 1u, dbg, 710);
+        if (static_cast<int>(ci % kSplitGroups) != grp) continue;
         const float4* src = reinterpret_cast<const float4*>(stages + s * 2 * kChunkBytes);
         float4* dl = reinterpret_cast<float4*>(stages + s * 2 * kChunkBytes + kChunkBytes);
         // 1024 16-byte pieces, consecutive per warp; all loads first so their latencies overlap
