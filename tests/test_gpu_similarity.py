@@ -288,3 +288,30 @@ def test_random_shapes_against_the_oracle(ctx):
         assert np.array_equal(med[safe_v], o_med[safe_v])
 
     run()
+
+
+@pytest.mark.parametrize("n,d,b", [(16, 1536, 4096), (32, 384, 4096)])
+def test_tcgen05_ring_survives_long_tiles(ctx, n, d, b):
+    """Regression guard for the splitter / mbarrier phase protocol: many chunks per tile and more tiles than SMs, run
+    back to back (these shapes deadlocked a three-group build in which a group waited only on its own chunks: a
+    parity wait cannot tell phase k from k - 2).  The watchdog must stay silent and verdicts must match the oracle on
+    a sample."""
+    import torch
+    dev = torch.device("cuda:0")
+    host = synth.make_embeddings(256, n, d, seed=n + d)
+    e = torch.from_numpy(host).to(dev).repeat(b // 256, 1, 1).contiguous()
+    thr = torch.full((b,), 0.5, dtype=torch.float32, device=dev)
+    ok = torch.empty(b, dtype=torch.int32, device=dev)
+    med = torch.empty(b, dtype=torch.int32, device=dev)
+    cos = torch.empty((b, n, n), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()                                         # inputs were filled on torch's stream
+    for _ in range(4):
+        ctx.similarity_batch_dev(e.data_ptr(), b, n, d, thr.data_ptr(), ok.data_ptr(), med.data_ptr(), cos.data_ptr())
+    ctx.synchronize()
+    ctx.check_status()                                               # raises on a watchdog record
+    o_ok, o_med, o_cos, margins = numeric.decide_batch(host, np.full(256, 0.5, np.float32))
+    got_cos = cos[:256].cpu().numpy()
+    assert np.max(np.abs(got_cos - o_cos)) < TIGHT
+    assert np.array_equal(cos[-256:].cpu().numpy(), got_cos)          # every repetition of the sample gives the same bits
+    safe = margins["vote"] > MARGIN
+    assert np.array_equal(med[:256].cpu().numpy()[safe], o_med[safe])
