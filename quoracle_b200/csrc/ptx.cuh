@@ -86,6 +86,11 @@ __device__ __forceinline__ bool hang_check(int32_t* dbg, long long t0, int tag) 
   }
   return false;
 }
+// Protocol rule for every barrier in this library: a parity wait only distinguishes "the phase before the current one"
+// from "the current one", so EVERY waiter of a barrier must wait on EVERY phase, in order.  A role that skips phases
+// (e.g. a worker group that only handles every other item) can be let through on phase k - 2's completion while phase
+// k - 1 is still in flight, or block forever if the barrier runs two phases ahead of it (qc_similarity_tc.cu learnt
+// this the hard way; the watchdog below is what turned it into a diagnosable status instead of a hung GPU).
 // Returns the cycles spent in the wait.  try_wait itself suspends the thread for a bounded,
 // implementation-defined time, so the clock brackets the whole call; the watchdog (a global-memory
 // read) is consulted only every 32 timed-out attempts to keep it off the wake-up path.
