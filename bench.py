@@ -9,11 +9,18 @@ A "step" is one pass of the hot path (K1 encode -> K2 finalise -> K3 similarity+
 of 256 decisions per GPU (BASELINE config 2: 8-model pool, 512-token candidates, dim 768).  All inputs
 are synthetic (quoracle_b200/synth.py); the encoder is this build's definition with random weights.
 
-  value  : whole-job decisions/s with token ids already resident in HBM (CUDA events, max over ranks)
-  e2e    : the same metric through the host C-ABI call qc_decide_batch with pinned HOST buffers, the
-           host->device copy of the step's token ids and the device->host read of its verdicts inside
-           the timed region
+  value  : whole-job decisions/s with token ids already resident in HBM (CUDA events, max over ranks);
+           nothing but the library's own launches sits between the two events
+  e2e    : the same metric through the host C-ABI calls qc_decide_batch_submit/_wait with pinned HOST
+           buffers, the host->device copy of the step's token ids and the device->host read of its
+           verdicts inside the timed region
   roofline / cpu_baseline : see DESIGN.md "Measurement"
+
+Extra keys of the same JSON line (none of them changes the headline leg):
+  sustained      3000 more steps of the same workload: the clock / power regime a long job runs in
+  extra.configs  short legs of BASELINE configs 3, 4 and two config-5 corners, each with its own roofline fraction
+                 and its own parity record
+  split_pool, tsplit (N > 1)   the two cross-GPU exchange paths with their bit-equality checks
 """
 from __future__ import annotations
 
@@ -32,35 +39,33 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "consensus decisions/sec (8-model, 512-tok)"
 UNIT = "decisions/s"
-POOL, TOKENS, DIM, VOCAB, AGENTS_PER_GPU = 8, 512, 768, 32768, 256
+VOCAB = 32768
+THRESHOLDS = (0.85, 0.995, 0.9995)      # 0.85 = the most common schema value; the other two make both verdicts occur
+                                        # (cosines between unrelated candidates of this encoder sit near 0.99)
+MARGIN = 2e-5                           # f64 margin below which an fp32 path may flip an index (reported, never dropped)
 # BASELINE.json configs that fit this harness (the default, c2, is the one the metric is quoted on):
 CONFIGS = {
     "c2": dict(pool=8, tokens=512, dim=768, agents=256, name="config 2"),
     "c3": dict(pool=8, tokens=512, dim=768, agents=512, name="config 3 (4096-agent tree over 8 GPUs = 512 agents per GPU)"),
     "c4": dict(pool=16, tokens=2048, dim=1536, agents=128, name="config 4 (1024 agents over 8 GPUs = 128 agents per GPU)"),
 }
-ROTATE = 40                      # distinct input batches per rank: 40 x 4.2 MB = 168 MB > 126 MB L2
-E2E_ROTATE = 8
 E2E_DEPTH = 4                    # batches in flight through qc_decide_batch_submit/_wait (<= QC_PIPELINE_SLOTS)
-WORKLOAD = ""
+L2_BYTES = 126 * 2**20
 
 
-def select_config(name: str) -> None:
-    global POOL, TOKENS, DIM, AGENTS_PER_GPU, WORKLOAD, ROTATE, E2E_ROTATE
-    c = CONFIGS[name]
-    POOL, TOKENS, DIM, AGENTS_PER_GPU = c["pool"], c["tokens"], c["dim"], c["agents"]
-    per_batch = AGENTS_PER_GPU * POOL * TOKENS * 4
-    ROTATE = max(4, -(-(168 * 2**20) // per_batch))          # enough distinct batches to exceed the 126 MB L2
-    E2E_ROTATE = min(8, ROTATE)
-    global METRIC
-    METRIC = f"consensus decisions/sec ({POOL}-model, {TOKENS}-tok)"
-    WORKLOAD = (f"{c['name']}: {POOL}-model pool, {AGENTS_PER_GPU} concurrent agents per GPU, {TOKENS}-token "
-                f"candidates, embedding dim {DIM}, vocab {VOCAB}, threshold 0.85")
+def metric_name(c) -> str:
+    return f"consensus decisions/sec ({c['pool']}-model, {c['tokens']}-tok)"
 
 
-select_config("c2")
+def workload(c) -> str:
+    return (f"{c['name']}: {c['pool']}-model pool, {c['agents']} concurrent agents per GPU, {c['tokens']}-token "
+            f"candidates, embedding dim {c['dim']}, vocab {VOCAB}, thresholds drawn from {list(THRESHOLDS)}")
+
+
+def rotate_for(c) -> int:
+    per_batch = c["agents"] * c["pool"] * c["tokens"] * 4
+    return max(4, -(-(168 * 2**20) // per_batch))            # enough distinct batches to exceed the 126 MB L2
 
 
 def measured_peaks():
@@ -106,7 +111,7 @@ class ClockSampler:
             self.nvml = (nv, nv.nvmlDeviceGetHandleByIndex(self.index))
             self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
             self.thread.start()
-            return
+            return self
         except Exception:
             self.nvml = None
         try:
@@ -115,9 +120,10 @@ class ClockSampler:
                  "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
-            return
+            return self
         self.thread = threading.Thread(target=self._pump, daemon=True)
         self.thread.start()
+        return self
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -159,8 +165,9 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU leg: the oracle's C port of the path (encoder + reference rule + N x N medoid), all host threads.
-# This is the ONLY place bench.py touches oracle/ (cpu_baseline and --impl reference).
+# CPU legs: the oracle's C port of the path (encoder + reference rule + N x N medoid), all host threads, and the
+# oracle's f64 verdict margins.  These four functions are the ONLY place bench.py touches oracle/ (cpu_baseline,
+# the parity records and --impl reference).
 # ---------------------------------------------------------------------------------------------------
 def cpu_path(weights, token_ids, lens, thr, threads):
     from oracle import cport
@@ -179,9 +186,17 @@ def cpu_sim_only(emb, thr, threads, want_full=True, repeat=1):
     from oracle import cport
     t0 = time.perf_counter()
     for _ in range(repeat):
-        cport.similarity_batch(emb, thr.astype(np.float64), want_full=want_full, threads=threads, want_cos=False,
-                               native=True)
-    return (time.perf_counter() - t0) / repeat
+        out = cport.similarity_batch(emb, thr.astype(np.float64), want_full=want_full, threads=threads, want_cos=False,
+                                     native=True)
+    return (time.perf_counter() - t0) / repeat, out
+
+
+def cpu_margins(emb, thr):
+    """f64 oracle verdicts and their margins (|cos - thr| of the row-0 rule, top-2 gap of the vote) for a set of
+    embeddings [B, N, D]: which decisions an fp32 path may legitimately flip."""
+    from oracle import numeric
+    ok, med, _, margins = numeric.decide_batch(emb, np.asarray(thr, np.float64))
+    return ok, med, margins
 
 
 def cpu_threads() -> int:
@@ -195,53 +210,65 @@ def cpu_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def calibrate_cpu_sample(weights, batch, threads, target_s):
-    """Pick the thread count (all logical CPUs, or half of them when SMT oversubscription is slower) and how many
-    decisions of the workload make ~target_s seconds of CPU work.  -> (sample, threads)"""
-    cpu_path(weights, batch.token_ids[:1], batch.lens[:1], batch.thr[:1], threads)   # warms the library
-    probe = min(AGENTS_PER_GPU, max(4, (4 * threads + POOL - 1) // POOL))            # four candidates per thread
-    best = None
-    for th in sorted({threads, max(1, threads // 2)}, reverse=True):
-        per = float("inf")
-        for _ in range(2):
-            t0 = time.perf_counter()
-            cpu_path(weights, batch.token_ids[:probe], batch.lens[:probe], batch.thr[:probe], th)
-            per = min(per, (time.perf_counter() - t0) / probe)
-        if best is None or per < best[0]:
-            best = (per, th)
-    per, th = best
-    return max(1, min(AGENTS_PER_GPU, int(target_s / max(per, 1e-6)))), th
+def parity_record(gpu_ok, gpu_med, emb_cpu, thr, cpu_ok=None, cpu_med=None) -> dict:
+    """GPU verdicts against the f64 oracle on `emb_cpu` [S, N, D]: mismatches over ALL S decisions, mismatches among
+    the margin-safe ones (must be 0), and how many the margin filter set aside -- nothing is dropped silently."""
+    ok, med, margins = cpu_margins(emb_cpu, thr)
+    s = int(ok.shape[0])
+    safe_t, safe_v = margins["thr"] > MARGIN, margins["vote"] > MARGIN
+    rec = {
+        "checked": s,
+        "ref_ok": int((gpu_ok[:s][safe_t] != ok[safe_t]).sum()), "medoid": int((gpu_med[:s][safe_v] != med[safe_v]).sum()),
+        "ref_ok_unfiltered": int((gpu_ok[:s] != ok).sum()), "medoid_unfiltered": int((gpu_med[:s] != med).sum()),
+        "margin_rejected": {"thr": int((~safe_t).sum()), "vote": int((~safe_v).sum()), "margin": MARGIN},
+        "ref_ok_ones": int((ok == 1).sum()), "ref_ok_zeros": int((ok == 0).sum()),
+        "gpu_ref_ok_ones": int((gpu_ok[:s] == 1).sum()), "gpu_ref_ok_zeros": int((gpu_ok[:s] == 0).sum()),
+        "medoid_histogram": np.bincount(med, minlength=emb_cpu.shape[1]).tolist(),
+        "oracle": "numpy f64 reference rule + medoid on the C port's f32 embeddings of the same tokens",
+    }
+    if cpu_ok is not None:
+        rec["c_port_vs_f64_oracle"] = {"ref_ok": int((cpu_ok != ok).sum()), "medoid": int((cpu_med != med).sum())}
+    return rec
 
 
 def run_reference(args):
-    """--impl reference: the CPU port of the reference path on the box's host cores (rank 0 only)."""
+    """--impl reference: the CPU port of the reference path on the box's host cores (rank 0 only).  Every step is the
+    same 256-decision batch shape the GPU arm times (a bounded prefix of it only when the whole run would not finish
+    within a few minutes on this box's cores); all host threads of the affinity mask, no auto-tuning of the count."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from quoracle_b200 import synth
-    weights = synth.make_encoder(DIM, VOCAB, seed=synth.BASE_SEED + 2)
-    batch = synth.make_decisions(AGENTS_PER_GPU, POOL, TOKENS, VOCAB, seed=synth.BASE_SEED + 2)
-    sample, threads = calibrate_cpu_sample(weights, batch, cpu_threads(), target_s=1.0)
+    c = CONFIGS[args.config]
+    b, n, t = c["agents"], c["pool"], c["tokens"]
+    weights = synth.make_encoder(c["dim"], VOCAB, seed=synth.BASE_SEED + 2)
+    batch = synth.make_decisions(b, n, t, VOCAB, seed=synth.BASE_SEED + 2, thresholds=THRESHOLDS)
+    threads = cpu_threads()
     steps, warmup = args.steps, args.warmup
+    cpu_path(weights, batch.token_ids[:1], batch.lens[:1], batch.thr[:1], threads)           # loads the library
+    probe = min(b, max(4, (4 * threads + n - 1) // n))
+    t0 = time.perf_counter()
+    cpu_path(weights, batch.token_ids[:probe], batch.lens[:probe], batch.thr[:probe], threads)
+    per = (time.perf_counter() - t0) / probe
     budget_s = 150.0                                   # keep the whole run within a few minutes
-    est = (steps + warmup) * 1.0                       # each step was sized to ~1 s
-    if est > budget_s:
-        sample = max(1, int(sample * budget_s / est))
+    sample = b if per * b * (steps + warmup) <= budget_s else max(1, int(budget_s / (per * (steps + warmup))))
     for _ in range(warmup):
         cpu_path(weights, batch.token_ids[:sample], batch.lens[:sample], batch.thr[:sample], threads)
     t0 = time.perf_counter()
     for k in range(steps):
-        lo = (k * sample) % max(1, AGENTS_PER_GPU - sample + 1)
+        lo = (k * sample) % max(1, b - sample + 1)
         cpu_path(weights, batch.token_ids[lo:lo + sample], batch.lens[lo:lo + sample], batch.thr[lo:lo + sample], threads)
     dt = time.perf_counter() - t0
     value = sample * steps / dt
-    desc = (f"{sample} decisions per step ({sample * POOL} candidates x {TOKENS} tokens) of the same workload; "
-            f"C port of the path (f32 encoder + f64 reference rule + N x N medoid), OpenMP over candidates")
+    desc = (f"{sample} of the {b} decisions of a step ({sample * n} candidates x {t} tokens) of the same workload; "
+            f"C port of the path (f32 encoder + f64 reference rule + N x N medoid), OpenMP over candidates, "
+            f"{threads} threads (the affinity mask)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "impl": "reference", "metric": metric_name(c), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 encoder / f64 cosine", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "the reference's own Elixir path cannot run here (no BEAM); "
+        "config": {"workload": workload(c), "decisions_per_step": sample,
+                   "note": "the reference's own Elixir path cannot run here (no BEAM); "
                    "its embed step is a remote HTTP call with no local arithmetic, so the CPU arm times this "
                    "build's encoder definition ported to C plus the restated reference rule"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
@@ -252,80 +279,221 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
-# GPU leg
+# GPU legs
 # ---------------------------------------------------------------------------------------------------
+class Env:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{self.local}"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device(f"cuda:{self.local}")
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        tt = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(tt, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in tt]
+
+
+class DecideLeg:
+    """One workload (a CONFIGS entry) resident on this rank's GPU: rotating input batches larger than L2, the
+    device-timed loop, and a separate K1-only timing pass."""
+
+    def __init__(self, env: Env, ctx, c, rotate=None, seed_off=0):
+        from quoracle_b200 import synth
+        torch = env.torch
+        self.env, self.ctx, self.c = env, ctx, c
+        self.b, self.n, self.t, self.dim = c["agents"], c["pool"], c["tokens"], c["dim"]
+        self.rotate = rotate or rotate_for(c)
+        seed = synth.BASE_SEED + 2 + seed_off
+        # Decisions shard by agent: rank r owns its own agents' decisions; no data-path collective.
+        self.batches = [synth.make_decisions(self.b, self.n, self.t, VOCAB, seed=seed + 1000 * env.rank + i,
+                                             thresholds=THRESHOLDS) for i in range(self.rotate)]
+        self.d_tok = [torch.from_numpy(x.token_ids).to(env.dev) for x in self.batches]
+        self.d_len = [torch.from_numpy(x.lens).to(env.dev) for x in self.batches]
+        self.d_thr = [torch.from_numpy(x.thr).to(env.dev) for x in self.batches]
+        self.d_ok = torch.empty(self.b, dtype=torch.int32, device=env.dev)
+        self.d_med = torch.empty(self.b, dtype=torch.int32, device=env.dev)
+        # A dedicated non-default stream: handle 0 (torch's default stream) would mean "context stream" to
+        # the C ABI, and the CUDA events below must sit on the stream the kernels are launched on.
+        self.tstream = torch.cuda.Stream(device=env.dev)
+        self.stream = self.tstream.cuda_stream
+        self.flops = 2.0 * self.b * self.n * self.t * self.dim * self.dim      # algorithmic encoder flops per launch
+
+    def step(self, i):
+        j = i % self.rotate
+        self.ctx.decide_batch_dev(self.d_tok[j].data_ptr(), self.d_len[j].data_ptr(), self.b, self.n, self.t,
+                                  self.d_thr[j].data_ptr(), self.d_ok.data_ptr(), self.d_med.data_ptr(), 0, 0, self.stream)
+
+    def timed(self, steps, warmup):
+        """-> ms for `steps` steps (this rank), launches in the region.  Per-kernel event timing is OFF here."""
+        env, torch = self.env, self.env.torch
+        env.barrier()
+        for i in range(warmup):
+            self.step(i)
+        env.barrier()
+        self.ctx.check_status()
+        self.ctx.profile_enable(False)
+        self.ctx.profile_reset()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        env.barrier()
+        ev0.record(self.tstream)
+        for i in range(steps):
+            self.step(warmup + i)
+        ev1.record(self.tstream)
+        env.barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = self.ctx.launch_count()
+        self.ctx.check_status()
+        return ms, launches
+
+    def kernel_pass(self, steps, first=0):
+        """Same steps again with every launch bracketed by CUDA events on the launching stream (outside any timed
+        region): per-kernel mean durations."""
+        self.ctx.profile_reset()
+        self.ctx.profile_enable(True)
+        for i in range(steps):
+            self.step(first + i)
+        self.env.torch.cuda.synchronize()
+        self.ctx.profile_enable(False)
+        stats = self.ctx.kernel_stats()
+        self.ctx.check_status()
+        return stats
+
+    def roofline(self, stats, step_ms, peaks, long_run, traffic=None, traffic_source=None):
+        k1 = stats["encode"]
+        k1_ms = k1["ms"] / max(1, k1["launches"])
+        achieved = self.flops / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else 0.0
+        peak = peaks["bf16_sustained"] if long_run else peaks["bf16_burst"]
+        return {"bound": "tensor", "kernel": "qc_encode_kernel (K1)", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                "traffic_source": traffic_source,
+                "peak_kind": ("sustained" if long_run else "burst") + ", " + peaks["source"],
+                "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / step_ms if step_ms else None,
+                "k1_timing": "CUDA events around every K1 launch on the launching stream, in a separate pass of the "
+                             "same steps right after the timed region (the timed region itself carries no events)",
+                "flops_per_launch": self.flops}
+
+
+def short_config_leg(env: Env, name: str, ctx, steps: int, peaks, check: int):
+    """extra.configs entry: a few steps of another BASELINE config on this rank's share, with its own roofline
+    fraction and (rank 0) a parity record of `check` decisions against the oracle."""
+    from quoracle_b200 import synth
+    c = CONFIGS[name]
+    leg = DecideLeg(env, ctx, c, rotate=max(4, min(rotate_for(c), 10)), seed_off=100)
+    ms, launches = leg.timed(steps, 3)
+    stats = leg.kernel_pass(steps, first=3)
+    (ms,) = env.max_over_ranks(ms)
+    step_ms = ms / steps
+    rec = {"workload": workload(c), "steps": steps, "warmup": 3, "ms_per_step": step_ms,
+           "value": env.world * leg.b * steps / (ms * 1e-3), "unit": UNIT, "gpu_launches": int(launches),
+           "inputs": f"{leg.rotate} rotating batches of {leg.b * leg.n * leg.t * 4 / 1e6:.1f} MB",
+           "encoder": ctx.encoder_info(),
+           "roofline": leg.roofline(stats, step_ms, peaks, long_run=False),
+           "kernels_ms_per_launch": {k: (v["ms"] / v["launches"] if v["launches"] else None) for k, v in stats.items()}}
+    if env.rank == 0 and check > 0:
+        x = leg.batches[0]
+        r0 = ctx.decide_batch(x.token_ids[:check], x.lens[:check], x.thr[:check], want_cos=False)
+        w = synth.make_encoder(c["dim"], VOCAB, seed=synth.BASE_SEED + 2)
+        cok, cmed, emb = cpu_path(w, x.token_ids[:check], x.lens[:check], x.thr[:check], cpu_threads())
+        rec["index_mismatch_vs_gpu"] = parity_record(r0.ref_ok, r0.medoid, emb.reshape(check, leg.n, -1), x.thr[:check],
+                                                     cok, cmed)
+    return rec
+
+
+def similarity_corner(env: Env, ctx, n: int, d: int, b: int, peaks):
+    """extra.configs.c5_*: K3 alone on embeddings resident in HBM (config 5 corner), L2 flushed between iterations,
+    HBM roofline; parity of a 256-decision sample against the f64 oracle."""
+    from quoracle_b200 import synth
+    torch = env.torch
+    base = synth.make_embeddings(min(b, 2048), n, d, seed=n * d)
+    emb = torch.from_numpy(base).to(env.dev)
+    if b > emb.shape[0]:
+        emb = emb.repeat((b + emb.shape[0] - 1) // emb.shape[0], 1, 1)[:b].contiguous()
+    rng = np.random.default_rng(n + d)
+    thr_h = rng.choice(np.asarray([0.3, 0.5, 0.7], np.float32), size=b)
+    thr = torch.from_numpy(thr_h).to(env.dev)
+    ok = torch.empty(b, dtype=torch.int32, device=env.dev)
+    med = torch.empty(b, dtype=torch.int32, device=env.dev)
+    cos = torch.empty((b, n, n), dtype=torch.float32, device=env.dev)
+    stream = torch.cuda.Stream(device=env.dev)
+    flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=env.dev)
+
+    def run():
+        ctx.similarity_batch_dev(emb.data_ptr(), b, n, d, thr.data_ptr(), ok.data_ptr(), med.data_ptr(), cos.data_ptr(),
+                                 stream.cuda_stream)
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(5):
+        flush.zero_()                                   # evict the inputs from L2 between iterations
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ctx.check_status()
+    ms = float(np.median(times))
+    nbytes = 4 * n * d + 4 * n * n + 8
+    gbs = b * nbytes / (ms * 1e-3) / 1e9
+    s = min(256, b, base.shape[0])
+    rec = {"workload": f"config 5 corner: K3 only, pool {n}, dim {d}, batch {b}, embeddings resident in HBM "
+                       f"({b * n * d * 4 / 1e6:.0f} MB), 256 MB L2 flush between iterations",
+           "ms": ms, "value": b / (ms * 1e-3), "unit": UNIT,
+           "roofline": {"bound": "hbm", "kernel": "qc_sim_small_kernel" if n <= 8 else "qc_sim_tc_kernel",
+                        "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                        "bytes_per_decision": nbytes, "traffic": None, "peak_kind": peaks["source"]}}
+    rec["index_mismatch_vs_gpu"] = parity_record(ok[:s].cpu().numpy(), med[:s].cpu().numpy(), base[:s], thr_h[:s])
+    return rec
+
+
 def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from quoracle_b200 import native, synth
+    from quoracle_b200 import exchange_legs, native, synth
+    env = Env()
+    torch, dist = env.torch, env.dist
+    world, rank, local = env.world, env.rank, env.local
+    c = CONFIGS[args.config]
+    peaks = measured_peaks()
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-
-    weights = synth.make_encoder(DIM, VOCAB, seed=synth.BASE_SEED + 2)
+    weights = synth.make_encoder(c["dim"], VOCAB, seed=synth.BASE_SEED + 2)
     ctx = native.Context(local, weights.table_bf16, weights.w_bf16)
     if args.cta_group:
         ctx.set_cta_group(args.cta_group)
-    b, n, t = AGENTS_PER_GPU, POOL, TOKENS
+    leg = DecideLeg(env, ctx, c)
+    b, n, t = leg.b, leg.n, leg.t
 
-    # Decisions shard by agent: rank r owns its own agents' decisions; no data-path collective.
-    batches = [synth.make_decisions(b, n, t, VOCAB, seed=synth.BASE_SEED + 2 + 1000 * rank + i) for i in range(ROTATE)]
-    d_tok = [torch.from_numpy(x.token_ids).to(dev) for x in batches]
-    d_len = [torch.from_numpy(x.lens).to(dev) for x in batches]
-    d_thr = [torch.from_numpy(x.thr).to(dev) for x in batches]
-    d_ok = torch.empty(b, dtype=torch.int32, device=dev)
-    d_med = torch.empty(b, dtype=torch.int32, device=dev)
-    # A dedicated non-default stream: handle 0 (torch's default stream) would mean "context stream" to
-    # the C ABI, and the CUDA events below must sit on the stream the kernels are launched on.
-    tstream = torch.cuda.Stream(device=dev)
-    stream = tstream.cuda_stream
+    # ---- headline: device-resident inputs, nothing but the library's launches between the events -----------
+    sampler = ClockSampler(local).start()
+    ms, launches = leg.timed(args.steps, args.warmup)
+    # ---- K1 timing: the same steps again, per-kernel events, outside the timed region ---------------------
+    stats = leg.kernel_pass(args.steps, first=args.warmup)
 
-    def step(i):
-        j = i % ROTATE
-        ctx.decide_batch_dev(d_tok[j].data_ptr(), d_len[j].data_ptr(), b, n, t, d_thr[j].data_ptr(),
-                             d_ok.data_ptr(), d_med.data_ptr(), 0, 0, stream)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    barrier()
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    ctx.check_status()
-    ctx.profile_reset()
-    ctx.profile_enable(True)
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(tstream)
-    for i in range(args.steps):
-        step(args.warmup + i)
-    ev1.record(tstream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count()
-    ctx.profile_enable(False)
-    stats = ctx.kernel_stats()
-    ctx.check_status()
-
-    # ---- e2e: host buffers through the C-ABI host entry point --------------------------------------
-    pinned_tok = [native.PinnedArray((b, n, t), np.int32) for _ in range(E2E_ROTATE)]
-    for k, pa in enumerate(pinned_tok):
-        pa.array[...] = batches[k].token_ids
-    pin_len = native.PinnedArray((b, n), np.int32)
-    pin_len.array[...] = batches[0].lens
-    pin_thr = native.PinnedArray((b,), np.float32)
-    pin_thr.array[...] = batches[0].thr
+    # ---- e2e: host buffers through the C-ABI host entry point --------------------------------------------
+    e2e_rotate = min(8, leg.rotate)
+    pinned_tok = [native.PinnedArray((b, n, t), np.int32) for _ in range(e2e_rotate)]
+    pin_len = [native.PinnedArray((b, n), np.int32) for _ in range(e2e_rotate)]
+    pin_thr = [native.PinnedArray((b,), np.float32) for _ in range(e2e_rotate)]
+    for k in range(e2e_rotate):
+        pinned_tok[k].array[...] = leg.batches[k].token_ids
+        pin_len[k].array[...] = leg.batches[k].lens
+        pin_thr[k].array[...] = leg.batches[k].thr
     # Pipelined host API (qc_decide_batch_submit / _wait), E2E_DEPTH batches in flight: the H2D copy of one step
     # overlaps the GPU work of another and an encoder launch is always queued while the host turns a finished
     # slot around; every step still copies its own inputs from pinned host memory and reads its own verdicts
@@ -340,51 +508,85 @@ def run_ours(args):
             k = i % E2E_DEPTH
             if i >= E2E_DEPTH:
                 ctx.decide_batch_wait(k)
-            ctx.decide_batch_submit(k, pinned_tok[i % E2E_ROTATE].array, pin_len.array, pin_thr.array, outs[k])
+            j = i % e2e_rotate
+            ctx.decide_batch_submit(k, pinned_tok[j].array, pin_len[j].array, pin_thr[j].array, outs[k])
         for i in range(max(0, nsteps - E2E_DEPTH), nsteps):
             ctx.decide_batch_wait(i % E2E_DEPTH)
 
     e2e_run(max(3, min(6, args.warmup)))
-    barrier()
+    env.barrier()
     t0 = time.perf_counter()
     e2e_run(e2e_steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    barrier()
+    env.barrier()
     clocks = sampler.stop()
     gpu_ok0, gpu_med0 = None, None
     if rank == 0:
-        r0 = ctx.decide_batch(batches[0].token_ids, batches[0].lens, batches[0].thr, want_cos=False)
+        r0 = ctx.decide_batch(leg.batches[0].token_ids, leg.batches[0].lens, leg.batches[0].thr, want_cos=False)
         gpu_ok0, gpu_med0 = r0.ref_ok.copy(), r0.medoid.copy()
 
-    # ---- max over ranks ---------------------------------------------------------------------------
-    if world > 1:
-        tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(tt[0]), float(tt[1])
+    ms, e2e_s = env.max_over_ranks(ms, e2e_s)
     value = world * b * args.steps / (ms * 1e-3)
     e2e_value = world * b * e2e_steps / e2e_s
+    step_ms = ms / args.steps
+
+    # ---- sustained: the regime a long job runs in (clocks under power cap), same workload ------------------
+    sustained = None
+    if args.sustained_steps > 0:
+        s2 = ClockSampler(local).start()
+        sms, _ = leg.timed(args.sustained_steps, 3)
+        sstats = leg.kernel_pass(min(200, args.sustained_steps), first=3)
+        sclk = s2.stop()
+        (sms,) = env.max_over_ranks(sms)
+        k1s = sstats["encode"]["ms"] / max(1, sstats["encode"]["launches"])
+        tfl = leg.flops / (k1s * 1e-3) / 1e12
+        sustained = {"steps": args.sustained_steps, "seconds": sms * 1e-3,
+                     "value": world * b * args.sustained_steps / (sms * 1e-3), "unit": UNIT,
+                     "ms_per_step": sms / args.sustained_steps, "sm_mhz": sclk.get("sm_mhz"),
+                     "reasons": sclk.get("reasons"), "k1_tflops": tfl,
+                     "frac_of_bf16_sustained": tfl / peaks["bf16_sustained"] if peaks["bf16_sustained"] else None,
+                     "frac_of_bf16_burst": tfl / peaks["bf16_burst"] if peaks["bf16_burst"] else None,
+                     "k1_note": "K1 mean over an event-bracketed pass of 200 steps right after the sustained run"}
+
+    # ---- other BASELINE configs, short legs ---------------------------------------------------------------
+    extra = {}
+    if not args.no_extra:
+        if args.config == "c2":
+            extra["c3"] = short_config_leg(env, "c3", ctx, steps=max(5, min(10, args.steps)), peaks=peaks, check=32)
+        w4 = synth.make_encoder(CONFIGS["c4"]["dim"], VOCAB, seed=synth.BASE_SEED + 2)
+        ctx4 = native.Context(local, w4.table_bf16, w4.w_bf16)
+        extra["c4"] = short_config_leg(env, "c4", ctx4, steps=5, peaks=peaks, check=2)
+        if world == 1:
+            extra["c5_pool8_dim768"] = similarity_corner(env, ctx, 8, 768, 65536, peaks)
+            extra["c5_pool32_dim768"] = similarity_corner(env, ctx, 32, 768, 16384, peaks)
+    else:
+        ctx4 = None
+
+    # ---- cross-GPU exchange paths (N > 1 only): driver-visible bit-equality + timing ----------------------
+    split_rec = tsplit_rec = None
+    if world > 1 and not args.no_exchange:
+        split_rec = exchange_legs.split_pool_leg(ctx, env.dev, decisions=256, pool=8, tokens=512, iters=10)
+        if ctx4 is None:
+            w4 = synth.make_encoder(CONFIGS["c4"]["dim"], VOCAB, seed=synth.BASE_SEED + 2)
+            ctx4 = native.Context(local, w4.table_bf16, w4.w_bf16)
+        tsplit_rec = exchange_legs.tsplit_leg(ctx4, env.dev, decisions=32, pool=16, tokens=2048, iters=5)
 
     if rank == 0:
-        peaks = measured_peaks()
-        k1 = stats["encode"]
-        k1_ms = k1["ms"] / max(1, k1["launches"])
-        flops = 2.0 * b * n * t * DIM * DIM                      # algorithmic encoder flops per launch
-        achieved = flops / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else 0.0
-        long_run = ms > 2000.0
-        peak = peaks["bf16_sustained"] if long_run else peaks["bf16_burst"]
-        traffic = None
+        traffic, traffic_source = None, None
         tp = ROOT / "profiles" / "k1_traffic.json"
         if tp.exists() and args.config == "c2":
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
-        step_ms = ms / args.steps
+            tj = json.loads(tp.read_text())
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_source = ("static: " + tj.get("source", "profiles/k1_traffic.json") +
+                              " (one `ncu --set full` capture of this kernel on this workload; NOT measured in this run)")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(c), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16 (fp32 accumulate; fp32 similarity)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "decisions_per_gpu_per_step": b,
-                       "l2": f"inputs rotate over {ROTATE} batches per rank ({ROTATE * b * n * t * 4 / 1e6:.0f} MB "
-                             f"> 126 MB L2); encoder table+weights ({(VOCAB * DIM + DIM * DIM) * 2 / 1e6:.0f} MB) are "
+            "config": {"workload": workload(c), "decisions_per_gpu_per_step": b,
+                       "l2": f"inputs rotate over {leg.rotate} batches per rank ({leg.rotate * b * n * t * 4 / 1e6:.0f} MB "
+                             f"> 126 MB L2); encoder table+weights ({(VOCAB * c['dim'] + c['dim'] ** 2) * 2 / 1e6:.0f} MB) are "
                              "persistent state",
                        "parallelism": f"agents sharded over {world} GPU(s), no data-path collective",
                        "encoder": ctx.encoder_info(), "seed": synth.BASE_SEED + 2},
@@ -393,23 +595,33 @@ def run_ours(args):
                     "api": f"qc_decide_batch_submit/_wait (host C ABI, {E2E_DEPTH} batches in flight), pinned host buffers, wall clock"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "qc_encode_kernel (K1)", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "peak_kind": ("sustained" if long_run else "burst") + ", " + peaks["source"],
-                         "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / step_ms if step_ms else None,
-                         "flops_per_launch": flops},
+            "roofline": leg.roofline(stats, step_ms, peaks, long_run=ms > 2000.0, traffic=traffic,
+                                     traffic_source=traffic_source),
             "kernels_ms_per_launch": {k: (v["ms"] / v["launches"] if v["launches"] else None) for k, v in stats.items()},
         }
+        if sustained is not None:
+            line["sustained"] = sustained
+        if extra:
+            line["extra"] = {"configs": extra}
+        if split_rec is not None:
+            line["split_pool"] = split_rec
+            line["tsplit"] = tsplit_rec
         if world == 1 and not args.no_cpu_baseline:
-            sample, threads = calibrate_cpu_sample(weights, batches[0], cpu_threads(), target_s=args.cpu_seconds)
+            threads = cpu_threads()
+            x = leg.batches[0]
+            cpu_path(weights, x.token_ids[:1], x.lens[:1], x.thr[:1], threads)          # loads the library
+            probe = min(b, max(4, (4 * threads + n - 1) // n))
             t0 = time.perf_counter()
-            ok, med, emb = cpu_path(weights, batches[0].token_ids[:sample], batches[0].lens[:sample],
-                                    batches[0].thr[:sample], threads)
+            cpu_path(weights, x.token_ids[:probe], x.lens[:probe], x.thr[:probe], threads)
+            per = (time.perf_counter() - t0) / probe
+            sample = max(1, min(b, int(args.cpu_seconds / max(per, 1e-6))))
+            t0 = time.perf_counter()
+            ok, med, emb = cpu_path(weights, x.token_ids[:sample], x.lens[:sample], x.thr[:sample], threads)
             dt = time.perf_counter() - t0
             e3 = emb.reshape(sample, n, -1)
-            sim_dt = cpu_sim_only(e3, batches[0].thr[:sample], 1)
-            rule_dt = cpu_sim_only(e3, batches[0].thr[:sample], 1, want_full=False)
-            sim_all_dt = cpu_sim_only(e3, batches[0].thr[:sample], threads, repeat=20)
+            sim_dt, _ = cpu_sim_only(e3, x.thr[:sample], 1)
+            rule_dt, _ = cpu_sim_only(e3, x.thr[:sample], 1, want_full=False)
+            sim_all_dt, _ = cpu_sim_only(e3, x.thr[:sample], threads, repeat=20)
             line["cpu_baseline"] = {
                 "value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
                 "sample": f"first {sample} decisions of batch 0 ({sample * n} candidates x {t} tokens), C port of the "
@@ -417,10 +629,11 @@ def run_ours(args):
                 "similarity_only_1thread_decisions_per_s": sample / sim_dt if sim_dt > 0 else None,
                 "reference_rule_only_1thread_decisions_per_s": sample / rule_dt if rule_dt > 0 else None,
                 f"similarity_only_{threads}threads_decisions_per_s": sample / sim_all_dt if sim_all_dt > 0 else None,
-                "index_mismatch_vs_gpu": {"ref_ok": int((ok != gpu_ok0[:sample]).sum()),
-                                          "medoid": int((med != gpu_med0[:sample]).sum()), "checked": int(sample)},
+                "index_mismatch_vs_gpu": parity_record(gpu_ok0, gpu_med0, e3, x.thr[:sample], ok, med),
             }
         print(json.dumps(line), flush=True)
+    if ctx4 is not None:
+        ctx4.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -435,12 +648,14 @@ def main():
     ap.add_argument("--cta-group", type=int, default=0, help="force the K1 variant (1 or 2); 0 = library default")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="size of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra.configs legs (c3, c4, c5 corners)")
+    ap.add_argument("--no-exchange", action="store_true", help="skip the split_pool / tsplit legs at N > 1")
+    ap.add_argument("--sustained-steps", type=int, default=3000, help="extra sustained leg (0 = off)")
     ap.add_argument("--e2e-depth", type=int, default=E2E_DEPTH, choices=[1, 2, 3, 4],
                     help="batches in flight in the e2e leg (host C ABI submit/wait slots)")
     ap.add_argument("--config", choices=sorted(CONFIGS), default="c2",
                     help="BASELINE config (c2 = the headline; c3/c4 are the 8-GPU configs, per-GPU share)")
     args = ap.parse_args()
-    select_config(args.config)
     globals()["E2E_DEPTH"] = args.e2e_depth
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":

@@ -300,6 +300,12 @@ int qc_encoder_set_cta_group(qc_ctx* ctx, int cta_group);
  * gather mode 0 = cp.async / 1 = TMA gather4).  token_block 0 returns to the default: the tiling is
  * chosen per call from T (fastest measured tiling weighted by the fraction of non-padding token slots). */
 int qc_encoder_set_variant(qc_ctx* ctx, int token_block, int cta_group, int w_bk, int gather_mode);
+/* W^T multicast degree of K1: `pairs` CTA pairs of one thread-block cluster (2 -> cluster of 4 SMs, 4 -> cluster of 8)
+ * walk the weight tiles in lock step, each tile read from L2 once and delivered to all of them by TMA multicast.
+ * 0 = the tiling's own default, 1 = off.  Applied to every later launch whose tiling has such an instantiation
+ * (CTA-pair tilings with TMA gather); other tilings ignore it.  qc_encoder_multicast reports the degree in effect. */
+int qc_encoder_set_multicast(qc_ctx* ctx, int pairs);
+int qc_encoder_multicast(const qc_ctx* ctx, int32_t* pairs);
 
 #ifdef __cplusplus
 }

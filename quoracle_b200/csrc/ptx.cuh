@@ -56,6 +56,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// Arm (arrive + expect_tx) the barrier at the same offset in CTA `cta` of this cluster.
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint64_t* bar, uint32_t bytes, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(remote), "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -194,9 +201,9 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
 // CTA-pair variant: data lands in THIS CTA's shared memory, the transaction bytes are
 // credited to the barrier at the same offset in the pair's leader (even) CTA.
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, uint64_t* bar_in_leader,
-                                                 int32_t c0, int32_t c1) {
+                                                 int32_t c0, int32_t c1, uint32_t leader_cta = 0) {
   uint32_t leader_bar;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(leader_bar) : "r"(smem_u32(bar_in_leader)), "r"(0));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(leader_bar) : "r"(smem_u32(bar_in_leader)), "r"(leader_cta));
   uint32_t dst;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(smem_u32(smem_dst)), "r"(cluster_ctarank()));
   asm volatile(
@@ -205,12 +212,25 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tma
       : "memory");
 }
 
+// CTA-pair multicast: the tile lands at the same offset in every CTA of `cta_mask` (the same-parity CTA of several
+// pairs of one cluster), and each destination's bytes are credited to the barrier at the same offset in the EVEN CTA
+// of that destination's pair (the peer bit, bit 24 of a shared::cluster address, is cleared in the barrier operand).
+// One L2 read feeds popcount(cta_mask) SMs.
+__device__ __forceinline__ void tma_load_2d_pair_mcast(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0,
+                                                       int32_t c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%4, %5}], [%2], %3;" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 // TMA gather4: four rows (row indices r0..r3) x one box width of a 2D tensor land as four consecutive
 // 128-byte rows at smem_dst; out-of-range row indices are zero-filled.  CG == 2: the transaction
 // bytes are credited to the barrier at the same offset in the pair's leader CTA.
 template <int CG>
 __device__ __forceinline__ void tma_gather4(uint32_t smem_dst, const void* tmap, uint64_t* bar, int32_t col,
-                                            int32_t r0, int32_t r1, int32_t r2, int32_t r3) {
+                                            int32_t r0, int32_t r1, int32_t r2, int32_t r3, uint32_t leader_cta = 0) {
   if constexpr (CG == 1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes "
@@ -219,7 +239,7 @@ __device__ __forceinline__ void tma_gather4(uint32_t smem_dst, const void* tmap,
         : "memory");
   } else {
     uint32_t leader_bar, dst;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(leader_bar) : "r"(smem_u32(bar)), "r"(0));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(leader_bar) : "r"(smem_u32(bar)), "r"(leader_cta));
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(smem_dst), "r"(cluster_ctarank()));
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::2 "

@@ -115,7 +115,8 @@ struct qc_ctx {
   // encoder
   bool has_encoder = false;
   int dim = 0, vocab = 0;
-  qc::EncoderVariant variant{0, 0, 0, 0};
+  qc::EncoderVariant variant{0, 0, 0, 0, 1};
+  int mcast = 0;                 // W multicast degree forced by qc_encoder_set_multicast (0 = the variant's own)
   EncodePlan plan;               // one-shot plan of the next encoder launch (see EncodePlan)
   DevBuf map, packed;
   HostBuf h_map;
@@ -128,7 +129,10 @@ struct qc_ctx {
   uint16_t* d_table = nullptr;
   uint16_t* d_wt = nullptr;  // W^T [dim(out) x dim(in)] bf16
   CUtensorMap w_tmap64, w_tmap32, e_tmap;
-  int32_t* d_err = nullptr;   // int32[8] device status words
+  // Device status words, 8 per block: block 0 for the synchronous and _dev entry points, block 1 + k for pipeline
+  // slot k.  Every in-flight batch reads and clears only its own block, so a flag raised by one slot's kernels can
+  // neither fail a neighbouring slot's valid batch nor be cleared by it before its owner has looked.
+  int32_t* d_err = nullptr;
   int32_t hang[4] = {};
   // workspaces
   DevBuf part, emb, tok, lens, thr, cosm, refok, medoid, q, rows, idx, stall;
@@ -331,6 +335,10 @@ long long fill_pack_plan(const int32_t* lens, int R, int CH, int nch, long long 
   return runs;
 }
 
+constexpr int kErrWords = 8;
+constexpr int kErrBlocks = 1 + QC_PIPELINE_SLOTS;
+inline int32_t* err_block(qc_ctx* c, int slot /* -1: synchronous and _dev calls */) { return c->d_err + (slot + 1) * kErrWords; }
+
 StreamWs* ws_for(qc_ctx* c, cudaStream_t s) {
   for (StreamWs& w : c->ws)
     if (w.used && w.s == s) {
@@ -425,7 +433,7 @@ struct HintGuard {
 
 int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, int T, float* d_emb, cudaStream_t s,
                DevBuf* part_buf = nullptr, const qc::FinalizeDst* scatter = nullptr,
-               const qc::TsplitDst* tsplit = nullptr) {
+               const qc::TsplitDst* tsplit = nullptr, int32_t* err = nullptr) {
   DevBuf& part = part_buf ? *part_buf : ws_for(c, s)->part;
   const EncodePlan plan = c->plan;                             // consumed: the next launch starts from a clean plan
   c->plan.clear();
@@ -475,11 +483,16 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
       a.nslots = nslots;
     }
     a.part = static_cast<float*>(part.p);
-    a.err_flag = c->d_err;
+    a.err_flag = err != nullptr ? err : err_block(c, -1);
     a.stall = c->stall_on ? static_cast<unsigned long long*>(c->stall.p) : nullptr;
     a.dim = c->dim;
     a.vocab = c->vocab;
     a.variant = c->variant;
+    if (c->mcast > 0) {                                       // forced multicast degree, where the tiling has it
+      qc::EncoderVariant vm = c->variant;
+      vm.mcast = c->mcast;
+      if (qc::encoder_variant_supported(c->dim, vm)) a.variant = vm;
+    }
     a.num_sms = c->num_sms;
     a.stream = s;
     QC_CUDA(qc::launch_encode(a));
@@ -499,11 +512,11 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
 // Synchronises the context stream and reads the device status words written by K1:
 // [0..3] barrier watchdog record (a protocol bug ended the kernel early), [4] token id out of range.
 int check_token_flag(qc_ctx* c) {
-  int32_t flags[8] = {};
-  QC_CUDA(cudaMemcpyAsync(flags, c->d_err, sizeof(flags), cudaMemcpyDeviceToHost, c->stream));
+  int32_t flags[kErrWords] = {};
+  QC_CUDA(cudaMemcpyAsync(flags, err_block(c, -1), sizeof(flags), cudaMemcpyDeviceToHost, c->stream));
   QC_CUDA(cudaStreamSynchronize(c->stream));
   if (flags[0] != 0 || flags[4] != 0) {
-    QC_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(flags), c->stream));
+    QC_CUDA(cudaMemsetAsync(err_block(c, -1), 0, sizeof(flags), c->stream));
     QC_CUDA(cudaStreamSynchronize(c->stream));
   }
   if (flags[0] != 0) {
@@ -590,9 +603,13 @@ int qc_ctx_create(qc_ctx** out, int device_id, const qc_encoder_cfg* enc) {
   int st = QC_OK;
   do {
     if ((st = cuda_status(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking))) != QC_OK) break;
-    if ((st = cuda_status(cudaMalloc(&c->d_err, 8 * sizeof(int32_t)))) != QC_OK) break;
-    if ((st = cuda_status(cudaMemset(c->d_err, 0, 8 * sizeof(int32_t)))) != QC_OK) break;
+    if ((st = cuda_status(cudaMalloc(&c->d_err, kErrBlocks * kErrWords * sizeof(int32_t)))) != QC_OK) break;
+    if ((st = cuda_status(cudaMemset(c->d_err, 0, kErrBlocks * kErrWords * sizeof(int32_t)))) != QC_OK) break;
     if ((st = resolve_encode_tiled(c)) != QC_OK) break;
+    // per-device function attributes (shared-memory opt-ins) of every kernel this context can launch
+    if ((st = cuda_status(qc::similarity_prepare_device())) != QC_OK) break;
+    if ((st = cuda_status(qc::similarity_tc_prepare_device())) != QC_OK) break;
+    if (enc != nullptr && (st = cuda_status(qc::encoder_prepare_device(enc->dim))) != QC_OK) break;
     if (enc != nullptr) {
       c->dim = enc->dim;
       c->vocab = enc->vocab;
@@ -722,6 +739,15 @@ int qc_encoder_info(const qc_ctx* c, int32_t* cta_group, int32_t* token_block, i
   return QC_OK;
 }
 
+int qc_encoder_multicast(const qc_ctx* c, int32_t* pairs) {
+  if (c == nullptr || pairs == nullptr) return QC_ERR_INVALID_INPUT;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  qc::EncoderVariant vm = c->variant;
+  if (c->mcast > 0) vm.mcast = c->mcast;
+  *pairs = qc::encoder_variant_supported(c->dim, vm) ? (vm.mcast < 1 ? 1 : vm.mcast) : (c->variant.mcast < 1 ? 1 : c->variant.mcast);
+  return QC_OK;
+}
+
 int qc_encoder_stall_profile(qc_ctx* c, int enable, double out[16]) {
   if (c == nullptr) return QC_ERR_INVALID_INPUT;
   DeviceGuard g(c->device);
@@ -758,7 +784,7 @@ int qc_encoder_set_cta_group(qc_ctx* c, int cta_group) {
   qc::EncoderVariant v = c->variant;
   v.cta_group = cta_group;
   if (!qc::encoder_variant_supported(c->dim, v)) {
-    v = qc::EncoderVariant{c->dim == 1536 ? 64 : 128, cta_group, 64, 0};
+    v = qc::EncoderVariant{c->dim == 1536 ? 64 : 128, cta_group, 64, 0, 1};
     if (!qc::encoder_variant_supported(c->dim, v)) return QC_ERR_UNSUPPORTED;
   }
   c->variant = v;
@@ -774,10 +800,17 @@ int qc_encoder_set_variant(qc_ctx* c, int token_block, int cta_group, int w_bk, 
     c->variant = qc::encoder_default_variant(c->dim);
     return QC_OK;
   }
-  const qc::EncoderVariant v{token_block, cta_group, w_bk, gather_mode};
+  const qc::EncoderVariant v{token_block, cta_group, w_bk, gather_mode, 1};
   if (!qc::encoder_variant_supported(c->dim, v)) return QC_ERR_UNSUPPORTED;
   c->variant = v;
   c->variant_forced = true;
+  return QC_OK;
+}
+
+int qc_encoder_set_multicast(qc_ctx* c, int pairs) {
+  if (c == nullptr || (pairs != 0 && pairs != 1 && pairs != 2 && pairs != 4)) return QC_ERR_INVALID_INPUT;
+  if (!c->has_encoder) return QC_ERR_NOT_CONFIGURED;
+  c->mcast = pairs;
   return QC_OK;
 }
 
@@ -795,8 +828,12 @@ int qc_embed_batch_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, i
   return encode_dev(c, d_tok, d_lens, R, T, d_emb, s);
 }
 
-int qc_similarity_batch_dev(qc_ctx* c, const float* d_emb, int B, int N, int D, const float* d_thr,
-                            int32_t* d_ref_ok, int32_t* d_medoid, float* d_cos, void* stream) {
+}  // extern "C"
+
+namespace {
+// K3 on a caller-chosen status block (the public _dev entry point uses block 0, pipeline slots their own).
+int similarity_dev(qc_ctx* c, const float* d_emb, int B, int N, int D, const float* d_thr, int32_t* d_ref_ok,
+                   int32_t* d_medoid, float* d_cos, void* stream, int32_t* err) {
   if (c == nullptr || d_emb == nullptr || d_thr == nullptr || B < 0 || D < 1) return QC_ERR_INVALID_INPUT;
   if (N < 1 || N > QC_MAX_POOL) return QC_ERR_UNSUPPORTED;
   if (B == 0) return QC_OK;
@@ -821,12 +858,21 @@ int qc_similarity_batch_dev(qc_ctx* c, const float* d_emb, int B, int N, int D, 
         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return QC_ERR_CUDA;
-    QC_CUDA(qc::launch_similarity_tc(&xm, B, N, D, d_thr, d_ref_ok, d_medoid, d_cos, c->d_err,
+    QC_CUDA(qc::launch_similarity_tc(&xm, B, N, D, d_thr, d_ref_ok, d_medoid, d_cos, err,
                                      c->stall_on ? static_cast<unsigned long long*>(c->stall.p) : nullptr, c->num_sms, s));
     return QC_OK;
   }
   QC_CUDA(qc::launch_similarity(d_emb, B, N, D, d_thr, d_ref_ok, d_medoid, d_cos, c->num_sms, s));
   return QC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int qc_similarity_batch_dev(qc_ctx* c, const float* d_emb, int B, int N, int D, const float* d_thr,
+                            int32_t* d_ref_ok, int32_t* d_medoid, float* d_cos, void* stream) {
+  if (c == nullptr) return QC_ERR_INVALID_INPUT;
+  return similarity_dev(c, d_emb, B, N, D, d_thr, d_ref_ok, d_medoid, d_cos, stream, err_block(c, -1));
 }
 
 // Host-only: the packed-stream plan exactly as the host entry points build it (no device, no context needed), so the
@@ -951,7 +997,7 @@ struct RaggedBufs {           // the context's own buffers (synchronous calls) o
 };
 
 static int ragged_common(qc_ctx* c, const RaggedBufs& wb, const int32_t* tokens, const int32_t* offsets, int R,
-                         float* d_emb, cudaStream_t s) {
+                         float* d_emb, cudaStream_t s, int32_t* err = nullptr) {
   const long long total = offsets[R];
   const size_t tokb = static_cast<size_t>(total > 0 ? total : 1) * 4, lenb = static_cast<size_t>(R) * 4;
   QC_CUDA(wb.tok->ensure(tokb));
@@ -1005,7 +1051,7 @@ static int ragged_common(qc_ctx* c, const RaggedBufs& wb, const int32_t* tokens,
   c->plan.packed_buf = wb.packed;
   // T only sizes the dense walk, which the pack hint replaces
   return encode_dev(c, static_cast<int32_t*>(wb.tok->p), static_cast<int32_t*>(wb.lens->p), R, vp.token_block, d_emb, s,
-                    wb.part);
+                    wb.part, nullptr, nullptr, err);
 }
 
 static RaggedBufs ctx_ragged_bufs(qc_ctx* c) {
@@ -1191,7 +1237,7 @@ int qc_decide_split_dev(qc_ctx* c, qc_split* sp, const int32_t* d_tok, const int
   if (st != QC_OK) return st;
   c->launches += 2;
   QC_CUDA(qc::launch_peer_signal(pf, epoch, s));
-  QC_CUDA(qc::launch_peer_wait(pf, epoch, c->d_err, s));
+  QC_CUDA(qc::launch_peer_wait(pf, epoch, err_block(c, -1), s));
   sp->last_buf = buf;
   sp->last_B = B;
   return qc_similarity_batch_dev(c, reinterpret_cast<const float*>(sp->local + static_cast<size_t>(buf) * sp->buf_bytes), B,
@@ -1261,7 +1307,7 @@ int qc_embed_tsplit_dev(qc_ctx* c, qc_split* sp, const int32_t* d_tok, const int
   if (st != QC_OK) return st;
   c->launches += 3;
   QC_CUDA(qc::launch_peer_signal(pf, epoch, s));
-  QC_CUDA(qc::launch_peer_wait(pf, epoch, c->d_err, s));
+  QC_CUDA(qc::launch_peer_wait(pf, epoch, err_block(c, -1), s));
   QC_CUDA(qc::launch_tsplit_reduce(reinterpret_cast<const float*>(sp->local + off),
                                    reinterpret_cast<const int32_t*>(sp->local + off + sp->psum_bytes), d_emb, R, sp->world,
                                    sp->max_rows, c->dim, s));
@@ -1413,11 +1459,11 @@ int qc_decide_batch_submit(qc_ctx* c, int slot, const int32_t* token_ids, const 
   HintGuard hg(c);
   if ((st = stage_block_map(c, lens, R, T, &sl.map, &sl.h_map, &sl.packed, sl.stream)) != QC_OK) return st;
   st = encode_dev(c, static_cast<int32_t*>(sl.tok.p), static_cast<int32_t*>(sl.lens.p), R, T,
-                  static_cast<float*>(sl.emb.p), sl.stream, &sl.part);
+                  static_cast<float*>(sl.emb.p), sl.stream, &sl.part, nullptr, nullptr, err_block(c, slot));
   if (st != QC_OK) return st;
-  st = qc_similarity_batch_dev(c, static_cast<float*>(sl.emb.p), B, N, c->dim, static_cast<float*>(sl.thr.p),
-                               static_cast<int32_t*>(sl.refok.p), static_cast<int32_t*>(sl.medoid.p),
-                               out_cos ? static_cast<float*>(sl.cosm.p) : nullptr, sl.stream);
+  st = similarity_dev(c, static_cast<float*>(sl.emb.p), B, N, c->dim, static_cast<float*>(sl.thr.p),
+                      static_cast<int32_t*>(sl.refok.p), static_cast<int32_t*>(sl.medoid.p),
+                      out_cos ? static_cast<float*>(sl.cosm.p) : nullptr, sl.stream, err_block(c, slot));
   if (st != QC_OK) return st;
   sl.pend.clear();
   size_t ooff = 0;
@@ -1436,7 +1482,7 @@ int qc_decide_batch_submit(qc_ctx* c, int slot, const int32_t* token_ids, const 
   if ((st = outc(out_ref_ok, sl.refok.p, ib)) != QC_OK) return st;
   if ((st = outc(out_medoid, sl.medoid.p, ib)) != QC_OK) return st;
   if ((st = outc(out_cos, sl.cosm.p, cosb)) != QC_OK) return st;
-  QC_CUDA(cudaMemcpyAsync(sl.h_flags.p, c->d_err, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+  QC_CUDA(cudaMemcpyAsync(sl.h_flags.p, err_block(c, slot), kErrWords * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
   sl.busy = true;
   return QC_OK;
 }
@@ -1463,7 +1509,7 @@ int qc_decide_ragged_submit(qc_ctx* c, int slot, const int32_t* tokens, const in
   QC_CUDA(sl.h_out.ensure(2 * pad256(ib) + pad256(cosb) + pad256(thrb)));
   QC_CUDA(sl.h_flags.ensure(8 * sizeof(int32_t)));
   const RaggedBufs wb{&sl.tok, &sl.lens, &sl.map, &sl.packed, &sl.part, &sl.h_in, &sl.h_map};
-  int st = ragged_common(c, wb, tokens, offsets, R, static_cast<float*>(sl.emb.p), sl.stream);
+  int st = ragged_common(c, wb, tokens, offsets, R, static_cast<float*>(sl.emb.p), sl.stream, err_block(c, slot));
   if (st != QC_OK) return st;
   {  // thresholds: staged at the tail of the slot's pinned output area unless the caller's buffer is pinned
     const void* src = thr;
@@ -1474,9 +1520,9 @@ int qc_decide_ragged_submit(qc_ctx* c, int slot, const int32_t* tokens, const in
     }
     QC_CUDA(cudaMemcpyAsync(sl.thr.p, src, thrb, cudaMemcpyHostToDevice, sl.stream));
   }
-  st = qc_similarity_batch_dev(c, static_cast<float*>(sl.emb.p), B, N, c->dim, static_cast<float*>(sl.thr.p),
-                               static_cast<int32_t*>(sl.refok.p), static_cast<int32_t*>(sl.medoid.p),
-                               out_cos ? static_cast<float*>(sl.cosm.p) : nullptr, sl.stream);
+  st = similarity_dev(c, static_cast<float*>(sl.emb.p), B, N, c->dim, static_cast<float*>(sl.thr.p),
+                      static_cast<int32_t*>(sl.refok.p), static_cast<int32_t*>(sl.medoid.p),
+                      out_cos ? static_cast<float*>(sl.cosm.p) : nullptr, sl.stream, err_block(c, slot));
   if (st != QC_OK) return st;
   sl.pend.clear();
   size_t ooff = 0;
@@ -1495,7 +1541,7 @@ int qc_decide_ragged_submit(qc_ctx* c, int slot, const int32_t* tokens, const in
   if ((st = outc(out_ref_ok, sl.refok.p, ib)) != QC_OK) return st;
   if ((st = outc(out_medoid, sl.medoid.p, ib)) != QC_OK) return st;
   if ((st = outc(out_cos, sl.cosm.p, cosb)) != QC_OK) return st;
-  QC_CUDA(cudaMemcpyAsync(sl.h_flags.p, c->d_err, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+  QC_CUDA(cudaMemcpyAsync(sl.h_flags.p, err_block(c, slot), kErrWords * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
   sl.busy = true;
   return QC_OK;
 }
@@ -1511,7 +1557,7 @@ int qc_decide_batch_wait(qc_ctx* c, int slot) {
   if (flags[0] != 0 || flags[4] != 0) {
     const bool hang = flags[0] != 0;
     if (hang) for (int i = 0; i < 4; ++i) c->hang[i] = flags[i];
-    QC_CUDA(cudaMemsetAsync(c->d_err, 0, 8 * sizeof(int32_t), sl.stream));
+    QC_CUDA(cudaMemsetAsync(err_block(c, slot), 0, kErrWords * sizeof(int32_t), sl.stream));
     QC_CUDA(cudaStreamSynchronize(sl.stream));
     return hang ? QC_ERR_KERNEL_TIMEOUT : QC_ERR_TOKEN_RANGE;
   }

@@ -12,6 +12,7 @@ struct EncoderVariant {
   int cta_group;
   int w_bk;
   int gather;   // 0 = cp.async (LDGSTS) gather, 1 = TMA gather4
+  int mcast;    // CTA pairs per cluster sharing each W^T tile through TMA multicast: 1 (none), 2 or 4
 };
 
 struct EncoderLaunch {
@@ -29,9 +30,16 @@ struct EncoderLaunch {
   int chunked;                 // 1: packed token stream; part rows are addressed through chunk_row
   const int32_t* chunk_row;    // device [R x bpc x (TB/CH)]: partial-row id of every CH-token chunk, -1 for padding
   int R, T, dim, vocab, num_sms;
+  int max_clusters;            // co-resident clusters of this variant (0 = ask the occupancy API at launch)
   EncoderVariant variant;
   cudaStream_t stream;
 };
+
+// Per-device function attributes (dynamic shared-memory opt-ins); qc_ctx_create calls these with the context's
+// device current -- there is no process-wide "already set" state anywhere in the library.
+cudaError_t encoder_prepare_device(int dim);
+cudaError_t similarity_prepare_device();
+cudaError_t similarity_tc_prepare_device();
 
 // K1
 cudaError_t launch_encode(const EncoderLaunch& a);

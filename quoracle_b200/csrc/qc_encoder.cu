@@ -35,11 +35,13 @@ namespace qc {
 
 using namespace ptx;
 
-template <int D_, int TB_, int CG_, int WBK_, int GM_>
+template <int D_, int TB_, int CG_, int WBK_, int GM_, int MC_ = 1>
 struct EncTraits {
   static constexpr int D = D_;
   static constexpr int TB = TB_;
   static constexpr int CG = CG_;
+  static constexpr int MC = MC_;                  // CTA pairs per cluster sharing every W^T tile through TMA multicast
+  static constexpr int CLUSTER = CG_ * MC_;       // CTAs per cluster
   static constexpr int WBK = WBK_;                // k elements per streamed W stage
   static constexpr int GM = GM_;                  // gather mode: 0 = cp.async (LDGSTS), 1 = TMA gather4
   static constexpr int BK = 64;                   // bf16 elements per 128-byte swizzle row (token tiles)
@@ -61,6 +63,9 @@ struct EncTraits {
   static constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;   // 128 / 256 / 512: powers of two >= 32
   static constexpr int SMEM_BYTES = 1024 + TOK_BYTES_PAD + W_STAGES * W_STAGE_BYTES + BAR_BYTES;
   static constexpr int GATHER_GROUP = (KB % 4 == 0) ? 4 : 3;   // k-blocks per cp.async group / proxy fence
+  static constexpr int GATHER_LANES = TB > 128 ? 16 : 8;      // gather4 issuing lanes per gather warp (4 rows each)
+  static_assert(MC == 1 || (CG == 2 && (MC == 2 || MC == 4)), "W multicast needs CTA pairs; cluster of 4 or 8");
+  static_assert(4 * GATHER_LANES * 4 >= TB, "gather lanes must cover the token block");
   static_assert(WBK == 64 || WBK == 32, "W stage width is 64 (SW128) or 32 (SW64)");
   static_assert(D % MT == 0, "feature tiles must cover D");
   static_assert(D % BK == 0, "k-blocks must cover D");
@@ -197,12 +202,29 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = (CG == 2) ? (blockIdx.x & 1u) : 0u;    // position in the CTA pair (cluster dim x = 2)
+  constexpr int MC = Tr::MC, CL = Tr::CLUSTER;
+  const uint32_t crank = (CL > 1) ? (blockIdx.x % CL) : 0u;    // rank in the cluster (cluster dim x = CL, 1-D grid)
+  const uint32_t rank = (CG == 2) ? (crank & 1u) : 0u;         // position in the CTA pair
+  const uint32_t lcta = crank & ~1u;                            // cluster rank of this pair's leader (even) CTA
+  const uint32_t pair = crank >> 1;                             // which pair of the cluster (0 when MC == 1)
   const bool leader = (rank == 0);
-  const int group = blockIdx.x / CG;                           // CTA (pair) index
-  const int ngroups = gridDim.x / CG;
+  const uint16_t pair_mask = static_cast<uint16_t>(0x3u << lcta);   // commit targets: both CTAs of this pair
+  // Work: a cluster item is MC pair items (CG token blocks each).  The MC pairs of a cluster walk the same W^T
+  // tiles in lock step (every tile is loaded from L2 once and multicast to all of them), so every role of every
+  // CTA of the cluster takes part in a cluster item as soon as ANY of its MC * CG blocks is non-empty; a pair whose
+  // own blocks are empty then multiplies zero rows and stores nothing.
+  const int cl = blockIdx.x / CL;
+  const int ncl = gridDim.x / CL;
   const int nblocks = R * bpc;
-  const int nitems = (nslots + CG - 1) / CG;                   // work items: CG slots (blocks) each
+  const int nitems = (nslots + CG - 1) / CG;                   // pair items: CG slots (blocks) each
+  const int ncitems = (nitems + MC - 1) / MC;                  // cluster items
+  auto item_any = [&](int citem) -> bool {
+    bool any = false;
+#pragma unroll
+    for (int s = 0; s < MC * CG; ++s)
+      any |= block_valid(lens, slot_block(block_map, citem * MC * CG + s, nslots, nblocks), nblocks, bpc, TB) > 0;
+    return any;
+  };
 
   // ---- one-time setup -----------------------------------------------------------------
   if (warp == 8 && lane == 0) {
@@ -210,7 +232,8 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
     if (Tr::GM == 1) tma_prefetch_desc(&e_tmap);
     for (int s = 0; s < WS; ++s) {
       mbar_init(&w_full[s], 1);   // leader's producer arrive.expect_tx (TMA bytes of the whole group)
-      mbar_init(&w_empty[s], 1);  // tcgen05.commit
+      // tcgen05.commit of every pair that reads the stage; with multicast only pair 0's CTAs produce and wait here
+      mbar_init(&w_empty[s], MC);
     }
     for (int k = 0; k < KB; ++k) {
       // cp.async gather: one arrival per gather warp of each CTA; TMA gather: the leader's expect_tx
@@ -228,7 +251,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
     tmem_alloc<CG>(tmem_slot, Tr::TMEM_COLS);
   }
   tcgen05_fence_before();
-  if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+  if constexpr (CL > 1) cluster_sync(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -239,15 +262,13 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
     uint32_t acc_iter = 0;
     long long st_wait = 0;
     const long long st_t0 = clock64();
-    for (int item = group; item < nitems; item += ngroups) {
+    for (int citem = cl; citem < ncitems; citem += ncl) {
+      if (!item_any(citem)) continue;
+      const int item = citem * MC + static_cast<int>(pair);
       int valid[CG];
-      bool any = false;
 #pragma unroll
-      for (int s = 0; s < CG; ++s) {
+      for (int s = 0; s < CG; ++s)
         valid[s] = block_valid(lens, slot_block(block_map, item * CG + s, nslots, nblocks), nblocks, bpc, TB);
-        any |= valid[s] > 0;
-      }
-      if (!any) continue;
       for (int ft = 0; ft < NFT; ++ft, ++acc_iter) {
         const uint32_t as = acc_iter & 1u;
         st_wait += mbar_wait(&acc_full[as], (acc_iter >> 1) & 1u, dbg, 100 + ft);
@@ -261,7 +282,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if constexpr (CG == 2) mbar_arrive_cluster(&acc_empty[as], 0); else mbar_arrive(&acc_empty[as]);
+            if constexpr (CG == 2) mbar_arrive_cluster(&acc_empty[as], lcta); else mbar_arrive(&acc_empty[as]);
           }
           // consecutive chunks of one candidate inside a block share a partial row (chunk_row, warp-uniform)
 #pragma unroll
@@ -295,7 +316,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (CG == 2) mbar_arrive_cluster(&acc_empty[as], 0); else mbar_arrive(&acc_empty[as]);
+          if constexpr (CG == 2) mbar_arrive_cluster(&acc_empty[as], lcta); else mbar_arrive(&acc_empty[as]);
         }
 #pragma unroll
         for (int s = 0; s < CG; ++s) {
@@ -316,17 +337,16 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
     // gather4 issues per warp per k-block (the per-lane operands force the compiler's one-lane-at-a-time
     // issue loop, so the work is spread over the four gather warps).
     {
-      const int rg = (warp - 4) * 8 + lane;
-      const bool active = lane < 8 && rg * 4 < TB;
+      constexpr int GL = Tr::GATHER_LANES;
+      const int rg = (warp - 4) * GL + lane;
+      const bool active = lane < GL && rg * 4 < TB;
       const uint32_t tok_base = smem_u32(tok_smem);
       uint32_t it = 0;
       long long st_wait = 0;
       const long long st_t0 = clock64();
-      for (int item = group; item < nitems; item += ngroups) {
-        bool any = false;
-#pragma unroll
-        for (int s = 0; s < CG; ++s) any |= block_valid(lens, slot_block(block_map, item * CG + s, nslots, nblocks), nblocks, bpc, TB) > 0;
-        if (!any) continue;
+      for (int citem = cl; citem < ncitems; citem += ncl) {
+        if (!item_any(citem)) continue;
+        const int item = citem * MC + static_cast<int>(pair);
         const int blk = slot_block(block_map, item * CG + static_cast<int>(rank), nslots, nblocks);
         const int valid = block_valid(lens, blk, nblocks, bpc, TB);
         const int cand = blk < nblocks ? blk / bpc : 0;
@@ -354,7 +374,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
           __syncwarp();
           if (active)
             tma_gather4<CG>(tok_base + kb * Tr::TOK_KB_BYTES + rg * 512, &e_tmap, &tok_full[kb], kb * 64, rid[0], rid[1],
-                            rid[2], rid[3]);
+                            rid[2], rid[3], lcta);
         }
         ++it;
       }
@@ -374,11 +394,9 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
     uint32_t it = 0;
     long long st_wait = 0, st_ld = 0, st_fence = 0;
     const long long st_t0 = clock64();
-    for (int item = group; item < nitems; item += ngroups) {
-      bool any = false;
-#pragma unroll
-      for (int s = 0; s < CG; ++s) any |= block_valid(lens, slot_block(block_map, item * CG + s, nslots, nblocks), nblocks, bpc, TB) > 0;
-      if (!any) continue;
+    for (int citem = cl; citem < ncitems; citem += ncl) {
+      if (!item_any(citem)) continue;
+      const int item = citem * MC + static_cast<int>(pair);
       const int blk = slot_block(block_map, item * CG + static_cast<int>(rank), nslots, nblocks);
       const int valid = block_valid(lens, blk, nblocks, bpc, TB);
       const int cand = blk < nblocks ? blk / bpc : 0;
@@ -430,7 +448,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
 #pragma unroll
             for (int kk = 0; kk < GG; ++kk) {
               const int kb = (g - 1) * GG + kk;
-              if constexpr (CG == 2) mbar_arrive_cluster(&tok_full[kb], 0); else mbar_arrive(&tok_full[kb]);
+              if constexpr (CG == 2) mbar_arrive_cluster(&tok_full[kb], lcta); else mbar_arrive(&tok_full[kb]);
             }
           }
         }
@@ -448,7 +466,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
 #pragma unroll
         for (int kk = 0; kk < GG; ++kk) {
           const int kb = (NG - 1) * GG + kk;
-          if constexpr (CG == 2) mbar_arrive_cluster(&tok_full[kb], 0); else mbar_arrive(&tok_full[kb]);
+          if constexpr (CG == 2) mbar_arrive_cluster(&tok_full[kb], lcta); else mbar_arrive(&tok_full[kb]);
         }
       }
       ++it;
@@ -465,19 +483,28 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
       uint32_t wi = 0;
       long long st_wait = 0;
       const long long st_t0 = clock64();
-      for (int item = group; item < nitems; item += ngroups) {
-        bool any = false;
-#pragma unroll
-        for (int s = 0; s < CG; ++s) any |= block_valid(lens, slot_block(block_map, item * CG + s, nslots, nblocks), nblocks, bpc, TB) > 0;
-        if (!__any_sync(0xffffffffu, any)) continue;
+      // With multicast (MC > 1) only pair 0 produces: CTA 0 arms w_full[s] in the leader of every pair, then CTA 0 /
+      // CTA 1 each load their 128-feature half of the tile ONCE and multicast it to the same-parity CTA of all pairs.
+      // w_empty[s] here counts one tcgen05.commit per pair, so a stage is refilled only when every pair is done with it.
+      for (int citem = cl; citem < ncitems && (MC == 1 || pair == 0); citem += ncl) {
+        if (!__any_sync(0xffffffffu, item_any(citem))) continue;
         for (int ft = 0; ft < NFT; ++ft) {
           for (int ws = 0; ws < NWS; ++ws, ++wi) {
             const uint32_t s = wi % WS;
             const uint32_t ph = (wi / WS) & 1u;
-            st_wait += mbar_wait(&w_empty[s], ph ^ 1u, dbg, 300 + static_cast<int>(s));
+            if constexpr (MC > 1) st_wait += mbar_wait_cluster(&w_empty[s], ph ^ 1u, dbg, 300 + static_cast<int>(s));
+            else st_wait += mbar_wait(&w_empty[s], ph ^ 1u, dbg, 300 + static_cast<int>(s));
             void* dst = w_smem + s * Tr::W_STAGE_BYTES;
             if (elect_one()) {
-              if constexpr (CG == 2) {
+              if constexpr (MC > 1) {
+                constexpr uint16_t even_mask = MC == 2 ? 0x5 : 0x55;
+                if (leader) {
+#pragma unroll
+                  for (int pp = 0; pp < MC; ++pp) mbar_expect_tx_cluster(&w_full[s], 2 * Tr::W_STAGE_BYTES, 2 * pp);
+                }
+                tma_load_2d_pair_mcast(dst, &w_tmap, &w_full[s], ws * WBK, ft * Tr::MT + static_cast<int>(rank) * 128,
+                                       static_cast<uint16_t>(even_mask << rank));
+              } else if constexpr (CG == 2) {
                 if (leader) mbar_expect_tx(&w_full[s], 2 * Tr::W_STAGE_BYTES);
                 tma_load_2d_pair(dst, &w_tmap, &w_full[s], ws * WBK, ft * Tr::MT + static_cast<int>(rank) * 128);
               } else {
@@ -509,11 +536,8 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
       uint32_t wi = 0, acc_iter = 0, it = 0;
       long long st_w = 0, st_tok = 0, st_acc = 0;
       const long long st_t0 = clock64();
-      for (int item = group; item < nitems; item += ngroups) {
-        bool any = false;
-#pragma unroll
-        for (int s = 0; s < CG; ++s) any |= block_valid(lens, slot_block(block_map, item * CG + s, nslots, nblocks), nblocks, bpc, TB) > 0;
-        if (!__any_sync(0xffffffffu, any)) continue;
+      for (int citem = cl; citem < ncitems; citem += ncl) {
+        if (!__any_sync(0xffffffffu, item_any(citem))) continue;
         for (int ft = 0; ft < NFT; ++ft, ++acc_iter) {
           const uint32_t as = acc_iter & 1u;
           if constexpr (CG == 2) st_acc += mbar_wait_cluster(&acc_empty[as], ((acc_iter >> 1) & 1u) ^ 1u, dbg, 400 + ft);
@@ -528,7 +552,8 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
               else st_tok += mbar_wait(&tok_full[kb], it & 1u, dbg, 500 + kb);
             }
             const uint32_t s = wi % WS;
-            st_w += mbar_wait(&w_full[s], (wi / WS) & 1u, dbg, 600 + static_cast<int>(s));
+            if constexpr (MC > 1) st_w += mbar_wait_cluster(&w_full[s], (wi / WS) & 1u, dbg, 600 + static_cast<int>(s));
+            else st_w += mbar_wait(&w_full[s], (wi / WS) & 1u, dbg, 600 + static_cast<int>(s));
             tcgen05_fence_after();
             const uint64_t adesc = (WBK == 64) ? make_kmajor_sw128_desc(w_base + s * Tr::W_STAGE_BYTES)
                                                : make_kmajor_sw64_desc(w_base + s * Tr::W_STAGE_BYTES);
@@ -540,9 +565,11 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
                 // +32 bytes per 16-element k step inside the swizzle row (descriptor units of 16 B => +2)
                 umma_bf16<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ws | k) != 0 ? 1u : 0u);
               }
-              umma_commit<CG>(&w_empty[s]);                         // W stage reusable once these MMAs retire
-              if (ft == NFT - 1 && sub == WPK - 1) umma_commit<CG>(&tok_empty[kb]);   // token k-block free
-              if (ws == NWS - 1) umma_commit<CG>(&acc_full[as]);
+              // W stage reusable once these MMAs retire: the arrival goes to the producing CTAs (cluster ranks 0 and 1;
+              // with MC == 1 that is this pair itself)
+              umma_commit<CG>(&w_empty[s], MC > 1 ? uint16_t(0x3) : pair_mask);
+              if (ft == NFT - 1 && sub == WPK - 1) umma_commit<CG>(&tok_empty[kb], pair_mask);   // token k-block free
+              if (ws == NWS - 1) umma_commit<CG>(&acc_full[as], pair_mask);
             }
             __syncwarp();
           }
@@ -561,7 +588,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
   // ---- teardown -----------------------------------------------------------------------
   __syncwarp();  // single-lane roles (TMA producer, MMA issuer) rejoin their warp before the aligned barriers
   tcgen05_fence_before();
-  if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+  if constexpr (CL > 1) cluster_sync(); else __syncthreads();
   if (warp == 9) {
     tcgen05_fence_after();
     tmem_dealloc<CG>(tmem_base, Tr::TMEM_COLS);
@@ -574,27 +601,19 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
 
 template <class Tr>
 static cudaError_t launch_encode_t(const EncoderLaunch& a) {
-  auto kern = qc_encode_kernel<Tr>;
-  static bool attr_set[16] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 16 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tr::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set[dev] = true;
-  }
+  auto kern = qc_encode_kernel<Tr>;   // its shared-memory opt-in was set for this device by encoder_prepare_device()
   const int bpc = (a.T + Tr::TB - 1) / Tr::TB;
-  int grid = a.num_sms;
-  if (Tr::CG == 2) grid &= ~1;
+  constexpr int CL = Tr::CLUSTER;
+  int grid = a.num_sms / CL * CL;
   if (a.chunked && a.chunk_row == nullptr) return cudaErrorInvalidValue;
   const long long nblocks = static_cast<long long>(a.R) * bpc;
   if (nblocks > 0x7fffffffLL) return cudaErrorInvalidValue;
   const int nslots = a.block_map != nullptr ? a.nslots : static_cast<int>(nblocks);
   if (nslots < 0 || nslots > nblocks) return cudaErrorInvalidValue;
   if (nslots == 0) return cudaSuccess;                         // every candidate is empty: K2 writes zero rows
-  const long long nitems = (static_cast<long long>(nslots) + Tr::CG - 1) / Tr::CG;
-  if (nitems * Tr::CG < grid) grid = static_cast<int>(nitems * Tr::CG);
-  if (grid < Tr::CG) grid = Tr::CG;
+  const long long ncitems = (static_cast<long long>(nslots) + CL - 1) / CL;   // cluster items: CL token blocks each
+  if (ncitems * CL < grid) grid = static_cast<int>(ncitems * CL);
+  if (grid < CL) grid = CL;
 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -603,37 +622,68 @@ static cudaError_t launch_encode_t(const EncoderLaunch& a) {
   cfg.stream = a.stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = Tr::CG;
+  attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if constexpr (CL > 2) {
+    // Clusters of 4 / 8 SMs must sit inside one GPC: the persistent grid is as many clusters as can be co-resident
+    // (a wave that does not fit would serialise behind the first).  a.max_clusters caches the occupancy query.
+    int fit = a.max_clusters;
+    if (fit <= 0) {
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&fit, kern, &cfg);
+      if (e != cudaSuccess) return e;
+    }
+    if (fit < 1) return cudaErrorInvalidConfiguration;
+    if (grid > fit * CL) cfg.gridDim = dim3(fit * CL);
+  }
   const CUtensorMap* tm = Tr::WBK == 64 ? a.w_tmap64 : a.w_tmap32;
   return cudaLaunchKernelEx(&cfg, kern, *tm, *a.e_tmap, a.table, a.token_ids, a.lens, a.part, a.err_flag, a.stall,
                             a.block_map, nslots, a.chunk_row, a.chunked, a.R, a.T, bpc, a.vocab);
 }
 
-// The instantiated variants.  {dim, token block, cta group, W stage width, gather mode}
+// The instantiated variants.  {dim, token block, cta group, W stage width, gather mode, pairs per cluster (W multicast)}
 #define QC_ENC_VARIANTS(X)                                                                                   \
-  X(384, 128, 1, 64, 0)  X(384, 128, 1, 32, 0)  X(384, 128, 1, 64, 1)                                         \
-  X(768, 128, 1, 64, 0)  X(768, 128, 1, 32, 0)  X(768, 128, 2, 64, 0)  X(768, 128, 2, 32, 0)                   \
-  X(768, 112, 2, 64, 0)  X(768, 104, 2, 64, 0)  X(768, 96, 2, 64, 0)                                           \
-  X(768, 128, 1, 64, 1)  X(768, 128, 2, 64, 1)  X(768, 128, 2, 32, 1)  X(768, 112, 2, 64, 1)  X(768, 104, 2, 64, 1)  X(768, 96, 2, 64, 1) \
-  X(1536, 64, 1, 64, 0)  X(1536, 64, 2, 64, 0)  X(1536, 48, 2, 64, 0)                                          \
-  X(1536, 64, 1, 64, 1)  X(1536, 64, 2, 64, 1)  X(1536, 56, 2, 64, 1)  X(1536, 48, 2, 64, 1)
+  X(384, 128, 1, 64, 0, 1)  X(384, 128, 1, 32, 0, 1)  X(384, 128, 1, 64, 1, 1)  X(384, 256, 1, 64, 1, 1)         \
+  X(768, 128, 1, 64, 0, 1)  X(768, 128, 1, 32, 0, 1)  X(768, 128, 2, 64, 0, 1)  X(768, 128, 2, 32, 0, 1)         \
+  X(768, 112, 2, 64, 0, 1)  X(768, 104, 2, 64, 0, 1)  X(768, 96, 2, 64, 0, 1)                                   \
+  X(768, 128, 1, 64, 1, 1)  X(768, 128, 2, 64, 1, 1)  X(768, 128, 2, 32, 1, 1)  X(768, 112, 2, 64, 1, 1)         \
+  X(768, 104, 2, 64, 1, 1)  X(768, 96, 2, 64, 1, 1)                                                            \
+  X(768, 128, 2, 64, 1, 2)  X(768, 112, 2, 64, 1, 2)  X(768, 104, 2, 64, 1, 2)  X(768, 128, 2, 64, 1, 4)         \
+  X(1536, 64, 1, 64, 0, 1)  X(1536, 64, 2, 64, 0, 1)  X(1536, 48, 2, 64, 0, 1)                                  \
+  X(1536, 64, 1, 64, 1, 1)  X(1536, 64, 2, 64, 1, 1)  X(1536, 56, 2, 64, 1, 1)  X(1536, 48, 2, 64, 1, 1)         \
+  X(1536, 64, 2, 64, 1, 2)  X(1536, 56, 2, 64, 1, 2)  X(1536, 48, 2, 64, 1, 2)                                  \
+  X(1536, 64, 2, 64, 1, 4)  X(1536, 56, 2, 64, 1, 4)
 
-#define QC_MATCH(D, TB, CG, WBK, GM) \
-  (dim == D && v.token_block == TB && v.cta_group == CG && v.w_bk == WBK && v.gather == GM)
+#define QC_MATCH(D, TB, CG, WBK, GM, MC) \
+  (dim == D && v.token_block == TB && v.cta_group == CG && v.w_bk == WBK && v.gather == GM && (v.mcast < 1 ? 1 : v.mcast) == MC)
+
+// Per-device (= per CUDA context) function state: the > 48 KB dynamic shared-memory opt-in of every tiling of
+// `dim`.  qc_ctx_create calls this with the context's device current, so no launch path keeps process-wide
+// "already set" flags (a second context on another GPU of the same process would otherwise launch without it).
+cudaError_t encoder_prepare_device(int dim) {
+#define X(D, TB, CG, WBK, GM, MC)                                                                          \
+  if (dim == D) {                                                                                          \
+    cudaError_t e = cudaFuncSetAttribute(qc_encode_kernel<EncTraits<D, TB, CG, WBK, GM, MC>>,              \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,                      \
+                                         EncTraits<D, TB, CG, WBK, GM, MC>::SMEM_BYTES);                    \
+    if (e != cudaSuccess) return e;                                                                        \
+  }
+  QC_ENC_VARIANTS(X)
+#undef X
+  return cudaSuccess;
+}
 
 bool encoder_variant_supported(int dim, const EncoderVariant& v) {
-#define X(D, TB, CG, WBK, GM) if (QC_MATCH(D, TB, CG, WBK, GM)) return true;
+#define X(D, TB, CG, WBK, GM, MC) if (QC_MATCH(D, TB, CG, WBK, GM, MC)) return true;
   QC_ENC_VARIANTS(X)
 #undef X
   return false;
 }
 
 int encoder_variant_w_stages(int dim, const EncoderVariant& v) {
-#define X(D, TB, CG, WBK, GM) if (QC_MATCH(D, TB, CG, WBK, GM)) return EncTraits<D, TB, CG, WBK, GM>::W_STAGES;
+#define X(D, TB, CG, WBK, GM, MC) if (QC_MATCH(D, TB, CG, WBK, GM, MC)) return EncTraits<D, TB, CG, WBK, GM, MC>::W_STAGES;
   QC_ENC_VARIANTS(X)
 #undef X
   return 0;
@@ -642,10 +692,10 @@ int encoder_variant_w_stages(int dim, const EncoderVariant& v) {
 EncoderVariant encoder_default_variant(int dim) {
   switch (dim) {
     // fastest measured on B200 (tools/gpu_tune.py, profiles/k1_variants_r1.md)
-    case 384: return EncoderVariant{128, 1, 64, 0};
-    case 768: return EncoderVariant{128, 2, 64, 1};
-    case 1536: return EncoderVariant{56, 2, 64, 1};
-    default: return EncoderVariant{0, 0, 0, 0};
+    case 384: return EncoderVariant{128, 1, 64, 0, 1};
+    case 768: return EncoderVariant{128, 2, 64, 1, 1};
+    case 1536: return EncoderVariant{56, 2, 64, 1, 1};
+    default: return EncoderVariant{0, 0, 0, 0, 1};
   }
 }
 
@@ -655,8 +705,8 @@ EncoderVariant encoder_default_variant(int dim) {
 // over TB = 128 (3 blocks, 22 % padding).
 EncoderVariant encoder_auto_variant(int dim, int T) {
   struct Cand { EncoderVariant v; float tput; };
-  static const Cand c768[] = {{{128, 2, 64, 1}, 1.00f}, {{112, 2, 64, 1}, 0.955f}, {{104, 2, 64, 1}, 0.965f}, {{96, 2, 64, 1}, 0.80f}};
-  static const Cand c1536[] = {{{56, 2, 64, 1}, 1.00f}, {{64, 2, 64, 1}, 0.91f}, {{48, 2, 64, 1}, 0.84f}};
+  static const Cand c768[] = {{{128, 2, 64, 1, 1}, 1.00f}, {{112, 2, 64, 1, 1}, 0.955f}, {{104, 2, 64, 1, 1}, 0.965f}, {{96, 2, 64, 1, 1}, 0.80f}};
+  static const Cand c1536[] = {{{56, 2, 64, 1, 1}, 1.00f}, {{64, 2, 64, 1, 1}, 0.91f}, {{48, 2, 64, 1, 1}, 0.84f}};
   const Cand* cs = nullptr;
   int n = 0;
   if (dim == 768) { cs = c768; n = 4; }
@@ -676,7 +726,7 @@ EncoderVariant encoder_auto_variant(int dim, int T) {
 cudaError_t launch_encode(const EncoderLaunch& a) {
   const int dim = a.dim;
   const EncoderVariant& v = a.variant;
-#define X(D, TB, CG, WBK, GM) if (QC_MATCH(D, TB, CG, WBK, GM)) return launch_encode_t<EncTraits<D, TB, CG, WBK, GM>>(a);
+#define X(D, TB, CG, WBK, GM, MC) if (QC_MATCH(D, TB, CG, WBK, GM, MC)) return launch_encode_t<EncTraits<D, TB, CG, WBK, GM, MC>>(a);
   QC_ENC_VARIANTS(X)
 #undef X
   return cudaErrorInvalidValue;

@@ -584,6 +584,13 @@ static cudaError_t launch_small(const float* emb, int B, int D, const float* thr
   return cudaGetLastError();
 }
 
+// Shared-memory opt-in (51 KB) of the mma.sync kernel on the current device (called by qc_ctx_create).
+cudaError_t similarity_prepare_device() {
+  cudaError_t e = cudaFuncSetAttribute(qc_sim_large_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSimLargeSmem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(qc_sim_large_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSimLargeSmem);
+}
+
 cudaError_t launch_similarity(const float* emb, int B, int N, int D, const float* thr, int32_t* ref_ok,
                               int32_t* medoid, float* cos, int num_sms, cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
@@ -599,16 +606,6 @@ cudaError_t launch_similarity(const float* emb, int B, int N, int D, const float
     case 7: return launch_small<7>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
     case 8: return launch_small<8>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
     default: break;
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(qc_sim_large_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kSimLargeSmem);
-    cudaError_t e2 = cudaFuncSetAttribute(qc_sim_large_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kSimLargeSmem);
-    if (e1 != cudaSuccess) return e1;
-    if (e2 != cudaSuccess) return e2;
-    attr_set = true;
   }
   int grid = B < num_sms * 4 ? B : num_sms * 4;  // four resident CTAs per SM (51 KB each)
   if (vec) qc_sim_large_kernel<true><<<grid, kSimThreads, kSimLargeSmem, stream>>>(emb, B, N, D, thr, ref_ok, medoid, cos);

@@ -374,19 +374,20 @@ static cudaError_t launch_tc(const CUtensorMap* x_tmap, int B, int N, int D, con
                              cudaStream_t stream) {
   constexpr int smem = tc_smem_bytes(kStages, kWin, kTail);
   static_assert(smem <= 232448, "tcgen05 K3: shared-memory carve-up exceeds the 227 KB opt-in limit");
-  static bool attr_set[16] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 16 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(qc_sim_tc_kernel<kStages, kWin, kTail>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    attr_set[dev] = true;
-  }
   const int q = 128 / N;
   const int ntiles = (B + q - 1) / q;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   qc_sim_tc_kernel<kStages, kWin, kTail><<<grid, kTcThreads, smem, stream>>>(*x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall);
   return cudaGetLastError();
+}
+
+// Shared-memory opt-in of the three instantiations on the current device (called by qc_ctx_create).
+cudaError_t similarity_tc_prepare_device() {
+  cudaError_t e = cudaFuncSetAttribute(qc_sim_tc_kernel<5, 33, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(5, 33, 7));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(qc_sim_tc_kernel<5, 49, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(5, 49, 7));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(qc_sim_tc_kernel<5, 65, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(5, 65, 0));
 }
 
 cudaError_t launch_similarity_tc(const CUtensorMap* x_tmap, int B, int N, int D, const float* thr, int32_t* ref_ok,

@@ -34,7 +34,7 @@ ABI_SYMBOLS = (
     "qc_check_status", "qc_last_hang",
     "qc_launch_count", "qc_profile_enable", "qc_profile_reset", "qc_kernel_stats",
     "qc_encoder_info", "qc_encoder_set_cta_group", "qc_encoder_set_variant", "qc_encoder_stall_profile",
-    "qc_similarity_set_path", "qc_encoder_token_block", "qc_encoder_hint_block_map", "qc_encoder_set_packing", "qc_debug_pack_plan",
+    "qc_similarity_set_path", "qc_encoder_set_multicast", "qc_encoder_multicast", "qc_encoder_token_block", "qc_encoder_hint_block_map", "qc_encoder_set_packing", "qc_debug_pack_plan",
     "qc_split_create", "qc_split_export", "qc_split_attach", "qc_decide_split_dev", "qc_split_gathered",
     "qc_split_destroy", "qc_tsplit_create", "qc_embed_tsplit_dev", "qc_decide_tsplit_dev",
 )
@@ -161,6 +161,10 @@ def load_library() -> ctypes.CDLL:
                                     ctypes.POINTER(ctypes.c_int32)]
     lib.qc_encoder_set_variant.restype = i32
     lib.qc_encoder_set_variant.argtypes = [vp, i32, i32, i32, i32]
+    lib.qc_encoder_set_multicast.restype = i32
+    lib.qc_encoder_set_multicast.argtypes = [vp, i32]
+    lib.qc_encoder_multicast.restype = i32
+    lib.qc_encoder_multicast.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
     lib.qc_debug_pack_plan.restype = i32
     lib.qc_debug_pack_plan.argtypes = [vp, i32, i32, i32, vp, ctypes.c_int64, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.qc_encoder_set_packing.restype = i32
@@ -426,7 +430,7 @@ class Context:
     def encoder_info(self) -> dict:
         cg, tb, ws = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         _check(self._lib.qc_encoder_info(self._h, ctypes.byref(cg), ctypes.byref(tb), ctypes.byref(ws)))
-        return {"cta_group": cg.value, "token_block": tb.value, "w_stages": ws.value}
+        return {"cta_group": cg.value, "token_block": tb.value, "w_stages": ws.value, "w_multicast_pairs": self.multicast()}
 
     STALL_FIELDS = ("mma_total", "mma_wait_w", "mma_wait_tokens", "mma_wait_acc", "epi_total", "epi_wait_acc",
                     "gather_total", "gather_wait_free", "wprod_total", "wprod_wait_free", "gather_wait_loads", "mma_issue", "mma_commit", "gather_fence")
@@ -459,6 +463,15 @@ class Context:
 
     def set_variant(self, token_block: int, cta_group: int, w_bk: int = 64, gather: int = 0) -> None:
         _check(self._lib.qc_encoder_set_variant(self._h, int(token_block), int(cta_group), int(w_bk), int(gather)))
+
+    def set_multicast(self, pairs: int) -> None:
+        """K1 W-tile multicast degree: 0 default, 1 off, 2 / 4 CTA pairs per cluster (see the header)."""
+        _check(self._lib.qc_encoder_set_multicast(self._h, int(pairs)))
+
+    def multicast(self) -> int:
+        v = ctypes.c_int32()
+        _check(self._lib.qc_encoder_multicast(self._h, ctypes.byref(v)))
+        return v.value
 
     def set_cta_group(self, cta_group: int) -> None:
         _check(self._lib.qc_encoder_set_cta_group(self._h, int(cta_group)))

@@ -28,11 +28,13 @@ def cta_groups(dim):
     return [1] if dim == 384 else [1, 2]
 
 
-VARIANTS = {384: [(128, 1, 64, 0), (128, 1, 32, 0), (128, 1, 64, 1)],
+# (token block, cta group, W stage k-width, gather mode[, CTA pairs per cluster sharing each W tile by TMA multicast])
+VARIANTS = {384: [(128, 1, 64, 0), (128, 1, 32, 0), (128, 1, 64, 1), (256, 1, 64, 1)],
             768: [(128, 1, 64, 0), (128, 1, 32, 0), (128, 2, 64, 0), (128, 2, 32, 0), (112, 2, 64, 0), (104, 2, 64, 0),
-                  (96, 2, 64, 0), (128, 1, 64, 1), (128, 2, 64, 1), (128, 2, 32, 1), (112, 2, 64, 1), (104, 2, 64, 1), (96, 2, 64, 1)],
+                  (96, 2, 64, 0), (128, 1, 64, 1), (128, 2, 64, 1), (128, 2, 32, 1), (112, 2, 64, 1), (104, 2, 64, 1), (96, 2, 64, 1),
+                  (128, 2, 64, 1, 2), (112, 2, 64, 1, 2), (104, 2, 64, 1, 2), (128, 2, 64, 1, 4)],
             1536: [(64, 1, 64, 0), (64, 2, 64, 0), (48, 2, 64, 0), (64, 1, 64, 1), (64, 2, 64, 1), (56, 2, 64, 1),
-                   (48, 2, 64, 1)]}
+                   (48, 2, 64, 1), (64, 2, 64, 1, 2), (56, 2, 64, 1, 2), (48, 2, 64, 1, 2), (64, 2, 64, 1, 4), (56, 2, 64, 1, 4)]}
 
 
 @pytest.mark.parametrize("dim", [384, 768, 1536])
@@ -46,10 +48,20 @@ def test_every_tiling_variant_matches_oracle(dim):
     tok[np.arange(t)[None, :] >= lens[:, None]] = -1
     want = oenc.encode(w.table_bf16, w.w_bf16, tok, lens)
     with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
-        for (tb, cg, wbk, gm) in VARIANTS[dim]:
+        first = None
+        for var in VARIANTS[dim]:
+            tb, cg, wbk, gm = var[:4]
+            mc = var[4] if len(var) > 4 else 1
             ctx.set_variant(tb, cg, wbk, gm)
+            ctx.set_multicast(mc)
+            assert ctx.multicast() == mc, var
             got = ctx.embed_batch(tok, lens)
-            assert np.max(np.abs(got - want)) < EMB_TOL, (dim, tb, cg, wbk, gm)
+            assert np.max(np.abs(got - want)) < EMB_TOL, (dim, var)
+            # W multicast changes who loads the weight tiles, not a single flop: same bits as the unicast tiling
+            if mc == 1 and gm == 1:
+                first = (tb, cg, wbk, got)
+            elif mc > 1 and first is not None and first[:3] == (tb, cg, wbk):
+                assert np.array_equal(got, first[3]), (dim, var)
 
 
 @pytest.mark.parametrize("dim", [384, 768, 1536])
@@ -533,3 +545,50 @@ def test_block_map_hint_for_device_callers():
         assert torch.equal(dense, listed) and torch.equal(dense, after)
         want = oenc.encode(w.table_bf16, w.w_bf16, batch.token_ids.reshape(b * n, t), lens)
         assert np.max(np.abs(listed.cpu().numpy() - want)) < EMB_TOL
+
+
+def test_pipeline_slots_keep_their_own_status_words():
+    """A token id out of range in slot 1 fails slot 1 only: the batches in flight around it (slots 0, 2, 3) and a
+    synchronous call made while they are in flight return their own, valid results; the failing slot is usable again
+    afterwards (its status block is cleared by its own wait, nobody else's)."""
+    w = weights(768, vocab=8192)
+    good = [synth.make_decisions(16, 8, 256, vocab=8192, seed=synth.BASE_SEED + 900 + i) for i in range(4)]
+    bad = good[1].token_ids.copy()
+    bad[3, 2, 17] = 8192                                # == vocab
+    with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+        want = [ctx.decide_batch(x.token_ids, x.lens, x.thr, want_cos=False) for x in good]
+        outs = [native.DecideResult(np.empty(16, np.int32), np.empty(16, np.int32), None, None) for _ in range(4)]
+        for k in range(4):
+            ctx.decide_batch_submit(k, bad if k == 1 else good[k].token_ids, good[k].lens, good[k].thr, outs[k])
+        sync = ctx.decide_batch(good[0].token_ids, good[0].lens, good[0].thr, want_cos=False)   # while slots are in flight
+        assert np.array_equal(sync.medoid, want[0].medoid)
+        for k in (0, 2, 3):
+            ctx.decide_batch_wait(k)
+            assert np.array_equal(outs[k].ref_ok, want[k].ref_ok) and np.array_equal(outs[k].medoid, want[k].medoid)
+        with pytest.raises(native.QcError) as e:
+            ctx.decide_batch_wait(1)
+        assert e.value.atom == "invalid_input"
+        ctx.decide_batch_submit(1, good[1].token_ids, good[1].lens, good[1].thr, outs[1])
+        ctx.decide_batch_wait(1)
+        assert np.array_equal(outs[1].medoid, want[1].medoid)
+        ctx.check_status()                               # block 0 never saw the flag
+
+
+def test_two_devices_in_one_process():
+    """Function attributes (dynamic shared-memory opt-ins) are per device: a context created on a second GPU of the
+    same process must be able to launch every kernel, including the 51 KB mma.sync K3 (N = 20, D = 5: not
+    TMA-addressable) and the encoder."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    w = weights(384)
+    emb = synth.make_embeddings(12, 20, 5, seed=3)
+    thr = np.full(12, 0.5, np.float32)
+    batch = synth.make_decisions(4, 3, 64, vocab=4096, seed=synth.BASE_SEED + 1)
+    res = []
+    for dev in (0, 1):
+        with native.Context(dev, w.table_bf16, w.w_bf16) as ctx:
+            res.append((ctx.similarity_batch(emb, thr), ctx.decide_batch(batch.token_ids, batch.lens, batch.thr)))
+    (s0, d0), (s1, d1) = res
+    assert all(np.array_equal(a, b) for a, b in zip(s0, s1))
+    assert np.array_equal(d0.cos, d1.cos) and np.array_equal(d0.medoid, d1.medoid)

@@ -22,15 +22,15 @@ def main():
     dev = torch.device("cuda:0")
     if args.dim == 768:
         b, n, t = 256, 8, 512
-        variants = [(128, 1, 64, 0), (128, 2, 64, 0), (112, 2, 64, 0), (104, 2, 64, 0), (96, 2, 64, 0),
-                    (128, 1, 64, 1), (128, 2, 64, 1), (112, 2, 64, 1), (104, 2, 64, 1), (96, 2, 64, 1)]
+        variants = [(128, 1, 64, 1), (128, 2, 64, 1), (112, 2, 64, 1), (104, 2, 64, 1),
+                    (128, 2, 64, 1, 2), (112, 2, 64, 1, 2), (104, 2, 64, 1, 2), (128, 2, 64, 1, 4)]
     elif args.dim == 1536:
         b, n, t = 32, 16, 2048
-        variants = [(64, 1, 64, 0), (64, 2, 64, 0), (48, 2, 64, 0), (64, 1, 64, 1), (64, 2, 64, 1), (56, 2, 64, 1),
-                    (48, 2, 64, 1)]
+        variants = [(64, 2, 64, 1), (56, 2, 64, 1), (48, 2, 64, 1), (64, 2, 64, 1, 2), (56, 2, 64, 1, 2),
+                    (48, 2, 64, 1, 2), (64, 2, 64, 1, 4), (56, 2, 64, 1, 4)]
     else:
         b, n, t = 512, 8, 512
-        variants = [(128, 1, 64, 0), (128, 1, 64, 1)]
+        variants = [(128, 1, 64, 0), (128, 1, 64, 1), (256, 1, 64, 1)]
     if args.variants:
         variants = [tuple(int(x) for x in v.split(",")) for v in args.variants.split(";")]
     w = synth.make_encoder(args.dim, seed=synth.BASE_SEED + 2)
@@ -44,11 +44,16 @@ def main():
     flops = 2.0 * float(np.mean([x.lens.sum() for x in batches])) * args.dim * args.dim   # valid tokens only
     ref = None
     print(f"dim={args.dim} B={b} N={n} T={t}  flops/launch={flops:.3e}")
-    for (tb, cg, wbk, gm) in variants:
+    for var in variants:
+        tb, cg, wbk, gm = var[:4]
+        mc = var[4] if len(var) > 4 else 1
         try:
             ctx.set_variant(tb, cg, wbk, gm)
+            ctx.set_multicast(mc)
+            if ctx.multicast() != mc:
+                raise native.QcError(-7, "no such multicast instantiation", "bad_request")
         except native.QcError as e:
-            print(f"variant tb={tb} cg={cg} wbk={wbk} gm={gm}: unsupported ({e})")
+            print(f"variant tb={tb} cg={cg} wbk={wbk} gm={gm} mc={mc}: unsupported ({e})")
             continue
         info = ctx.encoder_info()
         for i in range(3):
@@ -58,7 +63,7 @@ def main():
         try:
             ctx.check_status()
         except native.QcError as e:
-            print(f"variant tb={tb} cg={cg} wbk={wbk} gm={gm}: {e} hang={ctx.last_hang()}")
+            print(f"variant tb={tb} cg={cg} wbk={wbk} gm={gm} mc={mc}: {e} hang={ctx.last_hang()}")
             continue
         ctx.profile_reset()
         ctx.profile_enable(True)
@@ -79,7 +84,7 @@ def main():
             ref = emb
         diff = float(np.max(np.abs(emb - ref)))
         mt = max(sp["mma_total"], 1.0)
-        print(f"tb={tb:3d} cg={cg} wbk={wbk:2d} gm={gm} stages={info['w_stages']}: {ms:7.4f} ms  {flops / ms / 1e9:7.1f} TFLOP/s"
+        print(f"tb={tb:3d} cg={cg} wbk={wbk:2d} gm={gm} mc={mc} stages={info['w_stages']}: {ms:7.4f} ms  {flops / ms / 1e9:7.1f} TFLOP/s"
               f"  | MMA wait W {100 * sp['mma_wait_w'] / mt:4.1f}% tok {100 * sp['mma_wait_tokens'] / mt:4.1f}%"
               f" acc {100 * sp['mma_wait_acc'] / mt:4.1f}%  | epi wait {100 * sp['epi_wait_acc'] / max(sp['epi_total'], 1):4.1f}%"
               f"  gather wait free {100 * sp['gather_wait_free'] / max(sp['gather_total'], 1):4.1f}% loads {100 * sp['gather_wait_loads'] / max(sp['gather_total'], 1):4.1f}% fence {100 * sp['gather_fence'] / max(sp['gather_total'], 1):4.1f}%"
