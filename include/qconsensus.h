@@ -164,6 +164,24 @@ int qc_similarity_batch(qc_ctx* ctx, const float* emb, int B, int N, int D, cons
 int qc_first_match_batch(qc_ctx* ctx, const float* query, const float* rows, int Q, int M, int D,
                          const float* thr, int32_t* out_index, float* out_cos);
 
+/*
+ * Device-resident lesson rows for the dedup above.  The reference re-embeds every existing
+ * lesson (<= 100 per agent, lesson_manager.ex:150-173) for every new lesson; with a cache the rows of one agent's
+ * lesson list stay in HBM in LIST ORDER and a dedup call uploads one query row:
+ *   put     rows [nrows*dim] f32 (host) are written at index .. index+nrows-1; index <= count (index == count appends;
+ *           a merged lesson REPLACES its row: the merged lesson keeps the NEW content, lesson_manager.ex:159-161)
+ *   gather  the list was pruned / reordered: new row i = old row src_index[i], count becomes n
+ *   match   first resident row m (ascending) with cos(query, row_m) >= thr, else -1; out_cos (optional) [count]
+ * Calls are serialised with the other calls of the owning context.  capacity is fixed at creation.
+ */
+typedef struct qc_lesson_cache qc_lesson_cache;
+int qc_lesson_cache_create(qc_ctx* ctx, int capacity, int dim, qc_lesson_cache** out);
+void qc_lesson_cache_destroy(qc_lesson_cache* cache);
+int qc_lesson_cache_count(const qc_lesson_cache* cache);
+int qc_lesson_cache_put(qc_lesson_cache* cache, int index, const float* rows, int nrows);
+int qc_lesson_cache_gather(qc_lesson_cache* cache, const int32_t* src_index, int n);
+int qc_lesson_cache_match(qc_lesson_cache* cache, const float* query, float thr, int32_t* out_index, float* out_cos);
+
 /* Unweighted, un-normalised element-wise mean of C chunk vectors per group: in [G*C*D] -> out [G*D]. */
 int qc_chunk_mean(qc_ctx* ctx, const float* chunks, int G, int C, int D, float* out_mean);
 

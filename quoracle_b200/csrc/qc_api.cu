@@ -1602,6 +1602,118 @@ int qc_first_match_batch(qc_ctx* c, const float* query, const float* rows, int Q
   return QC_OK;
 }
 
+// ---- device-resident lesson rows -----------------------------------------------------
+// LessonManager.find_similar_lesson/5 (reference lib/quoracle/agent/lesson_manager.ex:150-173) re-embeds every
+// existing lesson (<= 100) for every new one; qc_first_match_batch already batches the comparison but still takes
+// the [M x D] rows from the host on every call.  A lesson cache keeps an agent's rows in HBM: append / replace by
+// index when a lesson is added or merged, reorder when the list is pruned, and a dedup call then uploads ONE query
+// row (D floats) and reads back one index (+ M cosines when asked).
+struct qc_lesson_cache {
+  qc_ctx* ctx = nullptr;
+  int capacity = 0, dim = 0, count = 0;
+  float* rows = nullptr;      // [capacity x dim]
+  float* spare = nullptr;     // gather target, swapped with rows
+};
+
+int qc_lesson_cache_create(qc_ctx* c, int capacity, int dim, qc_lesson_cache** out) {
+  if (c == nullptr || out == nullptr || capacity < 1 || capacity > 65536 || dim < 1) return QC_ERR_INVALID_INPUT;
+  *out = nullptr;
+  DeviceGuard g(c->device);
+  qc_lesson_cache* lc = new (std::nothrow) qc_lesson_cache();
+  if (lc == nullptr) return QC_ERR_OUT_OF_MEMORY;
+  lc->ctx = c;
+  lc->capacity = capacity;
+  lc->dim = dim;
+  const size_t bytes = static_cast<size_t>(capacity) * dim * sizeof(float);
+  cudaError_t e = cudaMalloc(&lc->rows, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&lc->spare, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    if (lc->rows) cudaFree(lc->rows);
+    delete lc;
+    return cuda_status(e);
+  }
+  *out = lc;
+  return QC_OK;
+}
+
+void qc_lesson_cache_destroy(qc_lesson_cache* lc) {
+  if (lc == nullptr) return;
+  DeviceGuard g(lc->ctx->device);
+  cudaStreamSynchronize(lc->ctx->stream);
+  cudaFree(lc->rows);
+  cudaFree(lc->spare);
+  delete lc;
+}
+
+int qc_lesson_cache_count(const qc_lesson_cache* lc) { return lc ? lc->count : -1; }
+
+int qc_lesson_cache_put(qc_lesson_cache* lc, int index, const float* rows, int nrows) {
+  if (lc == nullptr || rows == nullptr || nrows < 1 || index < 0 || index > lc->count) return QC_ERR_INVALID_INPUT;
+  if (index + nrows > lc->capacity) return QC_ERR_UNSUPPORTED;
+  qc_ctx* c = lc->ctx;
+  DeviceGuard g(c->device);
+  const size_t bytes = static_cast<size_t>(nrows) * lc->dim * sizeof(float);
+  QC_CUDA(c->h_in.ensure(pad256(bytes)));
+  size_t off = 0;
+  int st = h2d(c, lc->rows + static_cast<size_t>(index) * lc->dim, rows, bytes, &off);
+  if (st != QC_OK) return st;
+  QC_CUDA(cudaStreamSynchronize(c->stream));          // the staging area is reused by the next call
+  if (index + nrows > lc->count) lc->count = index + nrows;
+  return QC_OK;
+}
+
+int qc_lesson_cache_gather(qc_lesson_cache* lc, const int32_t* src_index, int n) {
+  if (lc == nullptr || n < 0 || n > lc->capacity || (n > 0 && src_index == nullptr)) return QC_ERR_INVALID_INPUT;
+  for (int i = 0; i < n; ++i)
+    if (src_index[i] < 0 || src_index[i] >= lc->count) return QC_ERR_INVALID_INPUT;
+  qc_ctx* c = lc->ctx;
+  DeviceGuard g(c->device);
+  const size_t rowb = static_cast<size_t>(lc->dim) * sizeof(float);
+  for (int i = 0; i < n; ++i)                          // <= capacity device-to-device row copies on one stream
+    QC_CUDA(cudaMemcpyAsync(lc->spare + static_cast<size_t>(i) * lc->dim, lc->rows + static_cast<size_t>(src_index[i]) * lc->dim,
+                            rowb, cudaMemcpyDeviceToDevice, c->stream));
+  float* t = lc->rows;
+  lc->rows = lc->spare;
+  lc->spare = t;
+  lc->count = n;
+  return QC_OK;
+}
+
+int qc_lesson_cache_match(qc_lesson_cache* lc, const float* query, float thr, int32_t* out_index, float* out_cos) {
+  if (lc == nullptr || query == nullptr || out_index == nullptr) return QC_ERR_INVALID_INPUT;
+  qc_ctx* c = lc->ctx;
+  if (lc->count == 0) {
+    *out_index = -1;
+    return QC_OK;
+  }
+  DeviceGuard g(c->device);
+  const size_t qb = static_cast<size_t>(lc->dim) * 4, cb = static_cast<size_t>(lc->count) * 4;
+  QC_CUDA(c->q.ensure(qb + 256));
+  QC_CUDA(c->idx.ensure(4));
+  if (out_cos) QC_CUDA(c->cosm.ensure(cb));
+  QC_CUDA(c->h_in.ensure(pad256(qb) + 256));
+  QC_CUDA(c->h_out.ensure(pad256(cb) + 256));
+  // the query row and its threshold ride in one staged copy: [D floats | thr]
+  char* st = static_cast<char*>(c->h_in.p);
+  memcpy(st, query, qb);
+  memcpy(st + qb, &thr, 4);
+  QC_CUDA(cudaMemcpyAsync(c->q.p, st, qb + 4, cudaMemcpyHostToDevice, c->stream));
+  {
+    KernelScope ks(c, QC_K_FIRST_MATCH, c->stream);
+    QC_CUDA(qc::launch_first_match(static_cast<float*>(c->q.p), lc->rows, 1, lc->count, lc->dim,
+                                   reinterpret_cast<float*>(static_cast<char*>(c->q.p) + qb), static_cast<int32_t*>(c->idx.p),
+                                   out_cos ? static_cast<float*>(c->cosm.p) : nullptr, c->stream));
+  }
+  char* so = static_cast<char*>(c->h_out.p);
+  QC_CUDA(cudaMemcpyAsync(so, c->idx.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  if (out_cos) QC_CUDA(cudaMemcpyAsync(so + 256, c->cosm.p, cb, cudaMemcpyDeviceToHost, c->stream));
+  QC_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(out_index, so, 4);
+  if (out_cos) memcpy(out_cos, so + 256, cb);
+  return QC_OK;
+}
+
 int qc_chunk_mean(qc_ctx* c, const float* chunks, int G, int C, int D, float* out_mean) {
   if (c == nullptr || chunks == nullptr || out_mean == nullptr || G < 0 || C < 1 || D < 1) return QC_ERR_INVALID_INPUT;
   if (G == 0) return QC_OK;

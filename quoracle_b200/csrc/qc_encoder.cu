@@ -232,8 +232,10 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
     if (Tr::GM == 1) tma_prefetch_desc(&e_tmap);
     for (int s = 0; s < WS; ++s) {
       mbar_init(&w_full[s], 1);   // leader's producer arrive.expect_tx (TMA bytes of the whole group)
-      // tcgen05.commit of every pair that reads the stage; with multicast only pair 0's CTAs produce and wait here
-      mbar_init(&w_empty[s], MC);
+      // tcgen05.commit of every pair that reads the stage.  With multicast only pair 0's CTAs produce: their w_empty
+      // collects one commit per pair; the leader of every other pair keeps its own copy (its pair's commit only) to
+      // know when it may arm w_full for the next phase.
+      mbar_init(&w_empty[s], crank < 2 ? MC : 1);
     }
     for (int k = 0; k < KB; ++k) {
       // cp.async gather: one arrival per gather warp of each CTA; TMA gather: the leader's expect_tx
@@ -483,27 +485,28 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
       uint32_t wi = 0;
       long long st_wait = 0;
       const long long st_t0 = clock64();
-      // With multicast (MC > 1) only pair 0 produces: CTA 0 arms w_full[s] in the leader of every pair, then CTA 0 /
-      // CTA 1 each load their 128-feature half of the tile ONCE and multicast it to the same-parity CTA of all pairs.
-      // w_empty[s] here counts one tcgen05.commit per pair, so a stage is refilled only when every pair is done with it.
-      for (int citem = cl; citem < ncitems && (MC == 1 || pair == 0); citem += ncl) {
+      // With multicast (MC > 1) only pair 0 loads: CTA 0 / CTA 1 each fetch their 128-feature half of the tile ONCE and
+      // multicast it to the same-parity CTA of all pairs; their w_empty[s] counts one tcgen05.commit per pair, so a
+      // stage is refilled only when every pair is done with it.  Every pair's leader arms its OWN w_full[s] (one local
+      // arrive.expect_tx per phase, after its pair's commit released the stage): remote arming from CTA 0 put a
+      // cluster-scope release on the producer's critical path for every pair and made the multicast kernel 4x slower
+      // than the unicast one.  A tile may land in a pair before that pair has armed the phase -- the barrier's
+      // transaction count goes transiently negative, which is legal, and the phase cannot complete without the arm.
+      for (int citem = cl; citem < ncitems && (pair == 0 || leader); citem += ncl) {
         if (!__any_sync(0xffffffffu, item_any(citem))) continue;
         for (int ft = 0; ft < NFT; ++ft) {
           for (int ws = 0; ws < NWS; ++ws, ++wi) {
             const uint32_t s = wi % WS;
             const uint32_t ph = (wi / WS) & 1u;
-            if constexpr (MC > 1) st_wait += mbar_wait_cluster(&w_empty[s], ph ^ 1u, dbg, 300 + static_cast<int>(s));
-            else st_wait += mbar_wait(&w_empty[s], ph ^ 1u, dbg, 300 + static_cast<int>(s));
+            st_wait += mbar_wait(&w_empty[s], ph ^ 1u, dbg, 300 + static_cast<int>(s));
             void* dst = w_smem + s * Tr::W_STAGE_BYTES;
             if (elect_one()) {
               if constexpr (MC > 1) {
                 constexpr uint16_t even_mask = MC == 2 ? 0x5 : 0x55;
-                if (leader) {
-#pragma unroll
-                  for (int pp = 0; pp < MC; ++pp) mbar_expect_tx_cluster(&w_full[s], 2 * Tr::W_STAGE_BYTES, 2 * pp);
-                }
-                tma_load_2d_pair_mcast(dst, &w_tmap, &w_full[s], ws * WBK, ft * Tr::MT + static_cast<int>(rank) * 128,
-                                       static_cast<uint16_t>(even_mask << rank));
+                if (leader) mbar_expect_tx(&w_full[s], 2 * Tr::W_STAGE_BYTES);
+                if (pair == 0)
+                  tma_load_2d_pair_mcast(dst, &w_tmap, &w_full[s], ws * WBK, ft * Tr::MT + static_cast<int>(rank) * 128,
+                                         static_cast<uint16_t>(even_mask << rank));
               } else if constexpr (CG == 2) {
                 if (leader) mbar_expect_tx(&w_full[s], 2 * Tr::W_STAGE_BYTES);
                 tma_load_2d_pair(dst, &w_tmap, &w_full[s], ws * WBK, ft * Tr::MT + static_cast<int>(rank) * 128);
@@ -552,8 +555,7 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
               else st_tok += mbar_wait(&tok_full[kb], it & 1u, dbg, 500 + kb);
             }
             const uint32_t s = wi % WS;
-            if constexpr (MC > 1) st_w += mbar_wait_cluster(&w_full[s], (wi / WS) & 1u, dbg, 600 + static_cast<int>(s));
-            else st_w += mbar_wait(&w_full[s], (wi / WS) & 1u, dbg, 600 + static_cast<int>(s));
+            st_w += mbar_wait(&w_full[s], (wi / WS) & 1u, dbg, 600 + static_cast<int>(s));
             tcgen05_fence_after();
             const uint64_t adesc = (WBK == 64) ? make_kmajor_sw128_desc(w_base + s * Tr::W_STAGE_BYTES)
                                                : make_kmajor_sw64_desc(w_base + s * Tr::W_STAGE_BYTES);
@@ -565,9 +567,9 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
                 // +32 bytes per 16-element k step inside the swizzle row (descriptor units of 16 B => +2)
                 umma_bf16<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ws | k) != 0 ? 1u : 0u);
               }
-              // W stage reusable once these MMAs retire: the arrival goes to the producing CTAs (cluster ranks 0 and 1;
-              // with MC == 1 that is this pair itself)
-              umma_commit<CG>(&w_empty[s], MC > 1 ? uint16_t(0x3) : pair_mask);
+              // W stage reusable once these MMAs retire: the arrival goes to the loading CTAs (cluster ranks 0 and 1)
+              // and to this pair's own leader, which arms the next phase (with MC == 1 all of that is this pair)
+              umma_commit<CG>(&w_empty[s], MC > 1 ? uint16_t(0x3u | (1u << lcta)) : pair_mask);
               if (ft == NFT - 1 && sub == WPK - 1) umma_commit<CG>(&tok_empty[kb], pair_mask);   // token k-block free
               if (ws == NWS - 1) umma_commit<CG>(&acc_full[as], pair_mask);
             }
@@ -691,8 +693,10 @@ int encoder_variant_w_stages(int dim, const EncoderVariant& v) {
 
 EncoderVariant encoder_default_variant(int dim) {
   switch (dim) {
-    // fastest measured on B200 (tools/gpu_tune.py, profiles/k1_variants_r1.md)
-    case 384: return EncoderVariant{128, 1, 64, 0, 1};
+    // fastest measured on B200 (tools/gpu_tune.py, profiles/k1_variants_*_r2.log).  W multicast (mcast 2 / 4) is
+    // instantiated and bit-identical but measured SLOWER at every dim (the bound is per-SM ingest, not L2 reads:
+    // DESIGN.md section 4), so no default uses it.
+    case 384: return EncoderVariant{256, 1, 64, 1, 1};
     case 768: return EncoderVariant{128, 2, 64, 1, 1};
     case 1536: return EncoderVariant{56, 2, 64, 1, 1};
     default: return EncoderVariant{0, 0, 0, 0, 1};
@@ -707,9 +711,13 @@ EncoderVariant encoder_auto_variant(int dim, int T) {
   struct Cand { EncoderVariant v; float tput; };
   static const Cand c768[] = {{{128, 2, 64, 1, 1}, 1.00f}, {{112, 2, 64, 1, 1}, 0.955f}, {{104, 2, 64, 1, 1}, 0.965f}, {{96, 2, 64, 1, 1}, 0.80f}};
   static const Cand c1536[] = {{{56, 2, 64, 1, 1}, 1.00f}, {{64, 2, 64, 1, 1}, 0.91f}, {{48, 2, 64, 1, 1}, 0.84f}};
+  // dim 384: a 256-token block (UMMA N = 256: half the operand bytes per flop of N = 128) is 5 % faster on full
+  // blocks; short candidates keep the 128-token block
+  static const Cand c384[] = {{{256, 1, 64, 1, 1}, 1.00f}, {{128, 1, 64, 0, 1}, 0.953f}};
   const Cand* cs = nullptr;
   int n = 0;
-  if (dim == 768) { cs = c768; n = 4; }
+  if (dim == 384) { cs = c384; n = 2; }
+  else if (dim == 768) { cs = c768; n = 4; }
   else if (dim == 1536) { cs = c1536; n = 3; }
   else return encoder_default_variant(dim);
   EncoderVariant best = cs[0].v;

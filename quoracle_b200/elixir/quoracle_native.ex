@@ -5,7 +5,12 @@ defmodule Quoracle.Native do
 
   NOT COMPILED OR RUN IN THE BUILD REPOSITORY (no BEAM in its image); the executable specification of
   this module is the Python mirror (`quoracle_b200/{tokenizer,embeddings,consensus_rules,collector}.py`)
-  and its tests.  Wiring into Quoracle is described in INTEGRATION.md.
+  and its tests, and the NIF table below is checked against the C shim's export table by
+  `tests/test_nif_mock.py` (names and arities).  Wiring into Quoracle is described in INTEGRATION.md.
+
+  Concurrency: one `ctx` may be shared by every agent process and the collector -- the NIF serialises the calls
+  on a context with a per-resource mutex (qconsensus_nif.c), so closures returned by `embedding_fn/1` are safe to
+  put into every agent's `cost_opts`.
   """
 
   @on_load :load_nif
@@ -28,6 +33,19 @@ defmodule Quoracle.Native do
   def first_match_batch(_ctx, _query, _rows, _q, _m, _d, _thr), do: :erlang.nif_error(:nif_not_loaded)
   def chunk_mean(_ctx, _chunks, _g, _c, _d), do: :erlang.nif_error(:nif_not_loaded)
   def launch_count(_ctx), do: :erlang.nif_error(:nif_not_loaded)
+  # pipelined pair: up to four batches in flight per context (slots 0..3); `wait` returns the verdict binaries
+  def decide_batch_submit(_ctx, _slot, _tok, _lens, _b, _n, _t, _thr, _want_cos), do: :erlang.nif_error(:nif_not_loaded)
+  def decide_ragged_submit(_ctx, _slot, _tokens, _offsets, _n, _thr, _want_cos), do: :erlang.nif_error(:nif_not_loaded)
+  def decide_batch_wait(_ctx, _slot), do: :erlang.nif_error(:nif_not_loaded)
+  # an agent's lesson embeddings resident on the GPU (LessonManager dedup uploads one query row per call)
+  def lesson_cache_create(_ctx, _capacity, _dim), do: :erlang.nif_error(:nif_not_loaded)
+  def lesson_cache_put(_cache, _index, _rows), do: :erlang.nif_error(:nif_not_loaded)
+  def lesson_cache_gather(_cache, _src_index), do: :erlang.nif_error(:nif_not_loaded)
+  def lesson_cache_match(_cache, _query, _thr, _want_cos), do: :erlang.nif_error(:nif_not_loaded)
+
+  # One encoder call takes candidates of up to QC_MAX_TOKENS = 8192 tokens; texts are chunked at the reference's own
+  # effective limit, floor(0.9 * 8191) (lib/quoracle/models/embeddings/token_chunker.ex:13-15,48-53).
+  @chunk_tokens 7371
 
   # ---- tokenizer: FNV-1a-32 of whitespace words, mod vocab (same function as tokenizer.py) -----------
   @spec tokenize(String.t()) :: [non_neg_integer()]
@@ -86,27 +104,100 @@ defmodule Quoracle.Native do
   """
   def embedding_fn(ctx) do
     fn value, opts ->
+      # LessonManager passes a keyword list (lib/quoracle/agent/lesson_manager.ex:98-106), ConsensusRules a map
+      # (lib/quoracle/actions/consensus_rules.ex:260-261,304); the reference's get_embedding/2 normalises likewise.
+      opts = if is_list(opts), do: Map.new(opts), else: opts
       text = if is_binary(value), do: value, else: Jason.encode!(value)
 
-      if text == "" do
-        {:error, :invalid_input}
-      else
-        {ids, lens, t} = pack([tokenize(text)])
+      case embed_texts(ctx, [text]) do
+        [{:ok, vec, chunks}] ->
+          result = %{embedding: vec, cached: false, chunks: chunks}
 
-        case embed_batch(ctx, ids, lens, 1, t) do
-          {:ok, emb} ->
-            result = %{embedding: floats(emb), cached: false, chunks: 1}
+          case Map.get(opts, :cost_accumulator) do
+            nil -> {:ok, result}
+            acc -> {:ok, result, acc}
+          end
 
-            case Map.get(opts, :cost_accumulator) do
-              nil -> {:ok, result}
-              acc -> {:ok, result, acc}
-            end
-
-          {:error, reason} ->
-            {:error, reason}
-        end
+        [{:error, reason}] ->
+          {:error, reason}
       end
     end
+  end
+
+  @doc """
+  1-arity closure for the `embedding_fn:` option INSIDE `Quoracle.Models.Embeddings.get_embedding/2`
+  (lib/quoracle/models/embeddings.ex:213-217): replaces only the provider HTTP call, so the reference's own ETS
+  cache, TTL, chunking and cost recording stay exactly as they are.  This is the wiring INTEGRATION.md recommends.
+  """
+  def raw_embedding_fn(ctx) do
+    fn text ->
+      case embed_texts(ctx, [text]) do
+        [{:ok, vec, _chunks}] -> {:ok, vec}
+        [{:error, reason}] -> {:error, reason}
+      end
+    end
+  end
+
+  @doc """
+  Embeds many texts with ONE `embed_ragged/3` call: `[{:ok, [float], chunks} | {:error, atom}]`, one per text, in
+  order.  `""` is `{:error, :invalid_input}` (embeddings.ex:49-50).  A text longer than #{7371} tokens is split on
+  whitespace into chunks of at most that many tokens, every chunk is embedded, and the text's vector is the
+  unweighted, un-normalised mean of its chunk vectors (`chunk_mean/5`) -- Embeddings.get_embedding_with_chunking/2
+  and average_embeddings/1 (embeddings.ex:142-192,371-383).  A failure of the batched call is retried text by text
+  so that only the offending text fails.
+  """
+  def embed_texts(ctx, texts) do
+    # "" and whitespace-only texts have no tokens: :invalid_input, like the empty string in the reference
+    chunked =
+      Enum.map(texts, fn t ->
+        case tokenize(t) do
+          [] -> :empty
+          toks -> Enum.chunk_every(toks, @chunk_tokens)
+        end
+      end)
+    lists = for c when c != :empty <- chunked, toks <- c, do: toks
+
+    rows =
+      case lists do
+        [] -> {:ok, []}
+        _ -> embed_token_lists(ctx, lists)
+      end
+
+    case rows do
+      {:ok, vecs} ->
+        {out, _rest} =
+          Enum.map_reduce(chunked, vecs, fn
+            :empty, rest -> {{:error, :invalid_input}, rest}
+            chunks, rest ->
+              {mine, rest} = Enum.split(rest, length(chunks))
+              {{:ok, mean_of(ctx, mine), length(chunks)}, rest}
+          end)
+
+        out
+
+      {:error, _} when length(texts) > 1 ->
+        Enum.flat_map(texts, &embed_texts(ctx, [&1]))
+
+      {:error, reason} ->
+        [{:error, reason}]
+    end
+  end
+
+  defp embed_token_lists(ctx, lists) do
+    {tokens, offsets} = pack_ragged(lists)
+
+    with {:ok, emb} <- embed_ragged(ctx, tokens, offsets) do
+      dim = div(byte_size(emb), 4 * length(lists))
+      {:ok, for(<<row::binary-size(dim * 4) <- emb>>, do: row)}
+    end
+  end
+
+  defp mean_of(_ctx, [one]), do: floats(one)
+
+  defp mean_of(ctx, rows) do
+    dim = div(byte_size(hd(rows)), 4)
+    {:ok, mean} = chunk_mean(ctx, IO.iodata_to_binary(rows), 1, length(rows), dim)
+    floats(mean)
   end
 
   # ---- the rule on the GPU: all N values of a parameter in one call -----------------------------------
@@ -128,26 +219,43 @@ defmodule Quoracle.Native do
         {{[v | _], _}, i} -> {i, {:ok, v}}
       end)
 
-    gpu_results =
-      pending
-      |> Enum.group_by(fn {{values, _}, _} -> length(values) end)
-      |> Enum.flat_map(fn {n, group} ->
-        texts = Enum.flat_map(group, fn {{values, _}, _} -> Enum.map(values, &stringify/1) end)
-        {tokens, offsets} = pack_ragged(Enum.map(texts, &tokenize/1))
-        thr = for {{_, th}, _} <- group, into: <<>>, do: <<th::little-float-32>>
-        _ = dim
+    # Every value of every pending merge goes through embed_texts/2 (ONE embed_ragged call for the whole flush,
+    # over-long values chunked and averaged like the reference does); a value that cannot be embedded fails ITS merge
+    # only (consensus_rules.ex:294-297: any failure -> {:error, :no_consensus} -> mode fallback in Result), every other
+    # merge of the flush is decided normally with one similarity_batch call per pool size.
+    all_values = Enum.flat_map(pending, fn {{values, _}, _} -> Enum.map(values, &stringify/1) end)
+    embedded = embed_texts(ctx, all_values)
 
-        # one dirty-scheduler NIF entry per pool size: values of different lengths, nothing padded
-        with {:ok, ref_ok, _medoid, _cos} <- decide_ragged(ctx, tokens, offsets, n, thr, 0) do
-          Enum.zip(group, ints(ref_ok))
-          |> Enum.map(fn
-            {{{[v0 | _], _}, i}, 1} -> {i, {:ok, v0}}
-            {{_, i}, _} -> {i, {:error, :no_consensus}}
-          end)
-        else
-          {:error, _reason} -> Enum.map(group, fn {_, i} -> {i, {:error, :no_consensus}} end)
+    {per_merge, _} =
+      Enum.map_reduce(pending, embedded, fn {{values, thr}, i}, rest ->
+        {mine, rest} = Enum.split(rest, length(values))
+        {{i, values, thr, mine}, rest}
+      end)
+
+    {failed, ready} = Enum.split_with(per_merge, fn {_, _, _, embs} -> Enum.any?(embs, &match?({:error, _}, &1)) end)
+    failed_results = Enum.map(failed, fn {i, _, _, _} -> {i, {:error, :no_consensus}} end)
+
+    gpu_results =
+      ready
+      |> Enum.group_by(fn {_, values, _, _} -> length(values) end)
+      |> Enum.flat_map(fn {n, group} ->
+        emb = for {_, _, _, embs} <- group, {:ok, vec, _} <- embs, f <- vec, into: <<>>, do: <<f::little-float-32>>
+        thr = for {_, _, th, _} <- group, into: <<>>, do: <<th::little-float-32>>
+
+        case similarity_batch(ctx, emb, length(group), n, dim, thr) do
+          {:ok, ref_ok, _medoid, _cos} ->
+            Enum.zip(group, ints(ref_ok))
+            |> Enum.map(fn
+              {{i, [v0 | _], _, _}, 1} -> {i, {:ok, v0}}
+              {{i, _, _, _}, _} -> {i, {:error, :no_consensus}}
+            end)
+
+          {:error, _reason} ->
+            Enum.map(group, fn {i, _, _, _} -> {i, {:error, :no_consensus}} end)
         end
       end)
+
+    gpu_results = failed_results ++ gpu_results
 
     (trivial_results ++ gpu_results) |> Enum.sort_by(&elem(&1, 0)) |> Enum.map(&elem(&1, 1))
   end

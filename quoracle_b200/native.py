@@ -34,7 +34,9 @@ ABI_SYMBOLS = (
     "qc_check_status", "qc_last_hang",
     "qc_launch_count", "qc_profile_enable", "qc_profile_reset", "qc_kernel_stats",
     "qc_encoder_info", "qc_encoder_set_cta_group", "qc_encoder_set_variant", "qc_encoder_stall_profile",
-    "qc_similarity_set_path", "qc_encoder_set_multicast", "qc_encoder_multicast", "qc_encoder_token_block", "qc_encoder_hint_block_map", "qc_encoder_set_packing", "qc_debug_pack_plan",
+    "qc_similarity_set_path", "qc_encoder_set_multicast", "qc_encoder_multicast",
+    "qc_lesson_cache_create", "qc_lesson_cache_destroy", "qc_lesson_cache_count", "qc_lesson_cache_put",
+    "qc_lesson_cache_gather", "qc_lesson_cache_match", "qc_encoder_token_block", "qc_encoder_hint_block_map", "qc_encoder_set_packing", "qc_debug_pack_plan",
     "qc_split_create", "qc_split_export", "qc_split_attach", "qc_decide_split_dev", "qc_split_gathered",
     "qc_split_destroy", "qc_tsplit_create", "qc_embed_tsplit_dev", "qc_decide_tsplit_dev",
 )
@@ -165,6 +167,18 @@ def load_library() -> ctypes.CDLL:
     lib.qc_encoder_set_multicast.argtypes = [vp, i32]
     lib.qc_encoder_multicast.restype = i32
     lib.qc_encoder_multicast.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
+    lib.qc_lesson_cache_create.restype = i32
+    lib.qc_lesson_cache_create.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
+    lib.qc_lesson_cache_destroy.restype = None
+    lib.qc_lesson_cache_destroy.argtypes = [vp]
+    lib.qc_lesson_cache_count.restype = i32
+    lib.qc_lesson_cache_count.argtypes = [vp]
+    lib.qc_lesson_cache_put.restype = i32
+    lib.qc_lesson_cache_put.argtypes = [vp, i32, vp, i32]
+    lib.qc_lesson_cache_gather.restype = i32
+    lib.qc_lesson_cache_gather.argtypes = [vp, vp, i32]
+    lib.qc_lesson_cache_match.restype = i32
+    lib.qc_lesson_cache_match.argtypes = [vp, vp, ctypes.c_float, ctypes.POINTER(ctypes.c_int32), vp]
     lib.qc_debug_pack_plan.restype = i32
     lib.qc_debug_pack_plan.argtypes = [vp, i32, i32, i32, vp, ctypes.c_int64, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     lib.qc_encoder_set_packing.restype = i32
@@ -394,6 +408,10 @@ class Context:
         _check(self._lib.qc_similarity_batch_dev(self._h, _dev(d_emb), b, n, d, _dev(d_thr), _dev(d_ref_ok),
                                                  _dev(d_medoid), _dev(d_cos), _dev(stream)))
 
+    def lesson_cache(self, capacity: int = 128, dim: Optional[int] = None) -> "LessonCache":
+        """Device-resident rows of one agent's lesson list (qc_lesson_cache_*); see LessonCache."""
+        return LessonCache(self, capacity, dim or self.dim)
+
     def token_split(self, world: int, rank: int, max_rows: int) -> "TokenSplit":
         """Exchange object for candidates sharded on T over `world` GPUs; see TokenSplit."""
         return TokenSplit(self, world, rank, max_rows)
@@ -552,3 +570,50 @@ class TokenSplit(SplitPool):
 
     def gathered(self):
         raise NotImplementedError("token-split objects hold partial sums, not gathered rows")
+
+
+class LessonCache:
+    """One agent's lesson embeddings resident in HBM, in list order (qc_lesson_cache_*):
+    a dedup call uploads one query row instead of the whole [M x D] list."""
+
+    def __init__(self, ctx: "Context", capacity: int, dim: int):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        self.capacity, self.dim = int(capacity), int(dim)
+        h = ctypes.c_void_p()
+        _check(self._lib.qc_lesson_cache_create(ctx._h, self.capacity, self.dim, ctypes.byref(h)))
+        self._h = h
+
+    def __len__(self) -> int:
+        return int(self._lib.qc_lesson_cache_count(self._h))
+
+    def put(self, index: int, rows: np.ndarray) -> None:
+        rows = _as(rows, np.float32).reshape(-1, self.dim)
+        _check(self._lib.qc_lesson_cache_put(self._h, int(index), _ptr(rows), rows.shape[0]))
+
+    def append(self, rows: np.ndarray) -> None:
+        self.put(len(self), rows)
+
+    def gather(self, src_index) -> None:
+        idx = _as(np.asarray(src_index, dtype=np.int32).reshape(-1), np.int32)
+        _check(self._lib.qc_lesson_cache_gather(self._h, _ptr(idx) if idx.size else None, idx.size))
+
+    def match(self, query: np.ndarray, thr: float, want_cos: bool = False):
+        """-> (index of the first resident row with cos >= thr or -1, cosines [count] or None)."""
+        q = _as(query, np.float32).reshape(self.dim)
+        idx = ctypes.c_int32(-1)
+        cos = np.empty(len(self), np.float32) if want_cos else None
+        _check(self._lib.qc_lesson_cache_match(self._h, _ptr(q), ctypes.c_float(thr), ctypes.byref(idx), _ptr(cos)))
+        return idx.value, cos
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.qc_lesson_cache_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self._ctx._h:
+                self.close()
+        except Exception:
+            pass

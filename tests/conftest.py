@@ -41,3 +41,26 @@ def pytest_collection_modifyitems(config, items):
     # `-m gpu` on a box without a GPU must fail, not silently pass: nothing to do here; the tests
     # call into libqconsensus, which returns QC_ERR_NO_DEVICE.
     return
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    """Margin-filter accounting of the GPU parity tests (tests/parity.py): printed, never dropped."""
+    try:
+        from tests import parity
+    except Exception:
+        return
+    if not parity.LOG:
+        return
+    filt = [r for r in parity.LOG if r["filtered"]]
+    unf = [r for r in parity.LOG if not r["filtered"]]
+    tr = terminalreporter
+    tr.write_sep("-", "index parity vs the f64 oracle (tests/parity.py)")
+    tr.write_line(f"margin-safe inputs (|cos-thr| >= {parity.SAFE_MARGIN}, vote gap >= {parity.SAFE_MARGIN}): "
+                  f"{sum(r['decisions'] for r in unf)} decisions in {len(unf)} batches, bit-identical indices on 100 %, no filter")
+    tr.write_line(f"random inputs: {sum(r['decisions'] for r in filt)} decisions in {len(filt)} batches, bit-identical where the "
+                  f"oracle margin exceeds the per-test margin; set aside by the filter: "
+                  f"{sum(r['rejected_thr'] for r in filt)} (threshold rule) / {sum(r['rejected_vote'] for r in filt)} (vote)")
+    worst = sorted(filt, key=lambda r: -(r["rejected_thr"] + r["rejected_vote"]))[:5]
+    for r in worst:
+        if r["rejected_thr"] + r["rejected_vote"]:
+            tr.write_line(f"  {r['test']}: {r['rejected_thr']} / {r['rejected_vote']} of {r['decisions']} (margin {r['margin']:g})")

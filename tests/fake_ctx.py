@@ -40,3 +40,43 @@ class FakeContext:
         self.calls["chunk_mean"] += 1
         return np.stack([np.array(numeric.average_embeddings(g.astype(np.float64).tolist()), dtype=np.float32)
                          for g in chunks])
+
+    def lesson_cache(self, capacity=128, dim=None):
+        return FakeLessonCache(self, capacity, dim or self.dim)
+
+
+class FakeLessonCache:
+    """Host stand-in for native.LessonCache with the same methods (rows kept in a numpy array, oracle arithmetic)."""
+
+    def __init__(self, ctx, capacity, dim):
+        self.ctx, self.capacity, self.dim = ctx, capacity, dim
+        self.rows = np.zeros((0, dim), np.float32)
+
+    def __len__(self):
+        return self.rows.shape[0]
+
+    def put(self, index, rows):
+        rows = np.asarray(rows, np.float32).reshape(-1, self.dim)
+        assert 0 <= index <= len(self) and index + rows.shape[0] <= self.capacity
+        keep = max(len(self), index + rows.shape[0])
+        out = np.zeros((keep, self.dim), np.float32)
+        out[: len(self)] = self.rows
+        out[index:index + rows.shape[0]] = rows
+        self.rows = out
+
+    def append(self, rows):
+        self.put(len(self), rows)
+
+    def gather(self, src_index):
+        idx = np.asarray(src_index, np.int64).reshape(-1)
+        self.rows = self.rows[idx] if idx.size else np.zeros((0, self.dim), np.float32)
+
+    def match(self, query, thr, want_cos=False):
+        self.ctx.calls["first_match"] += 1
+        if len(self) == 0:
+            return -1, None
+        i = numeric.first_match(np.asarray(query, np.float64).tolist(), self.rows.astype(np.float64).tolist(), float(thr))
+        return int(i), None
+
+    def close(self):
+        pass

@@ -1,0 +1,101 @@
+"""Index parity between the GPU path and the f64 oracle, with the margin filter made visible.
+
+An fp32 path may legitimately flip `cos >= thr` or the argmax of the row means when the f64 oracle's own margin is
+below the path's cosine error, so equality is asserted where the oracle's margin exceeds `margin` -- and the number of
+decisions the filter set aside is RECORDED per test, capped at 2 % of the batch (a test that the filter hollows out
+fails), and printed in the terminal summary (tests/conftest.py), so "bit-identical on margin-safe inputs, N rejected
+on random inputs" is a fact of every GPU test run rather than a silent drop (hard parts).
+
+`margin_safe_inputs` builds inputs that carry the SURVEY margin by construction (|cos - thr| >= 2e-3, top-2 vote gap
+>= 2e-3): on those, equality is asserted on 100 % of the decisions with no filter at all.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+
+from oracle import numeric
+
+LOG: list[dict] = []          # one record per checked batch; summarised by conftest.pytest_terminal_summary
+SAFE_MARGIN = 2e-3            # reject/regenerate below this
+
+
+def _test_name() -> str:
+    return os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+
+
+def assert_indices(gpu_ok, gpu_med, ok, med, margins, margin, max_rejected_frac=0.02, what=""):
+    """GPU verdicts == oracle verdicts wherever the oracle margin > `margin`; the rejected counts are logged and
+    bounded.  Returns (rejected_thr, rejected_vote)."""
+    b = int(np.asarray(ok).shape[0])
+    safe_t = np.asarray(margins["thr"]) > margin
+    safe_v = np.asarray(margins["vote"]) > margin
+    rej_t, rej_v = int((~safe_t).sum()), int((~safe_v).sum())
+    LOG.append({"test": _test_name(), "what": what, "decisions": b, "margin": margin, "rejected_thr": rej_t,
+                "rejected_vote": rej_v, "filtered": True})
+    assert np.array_equal(np.asarray(gpu_ok)[safe_t], np.asarray(ok)[safe_t]), "ref_ok differs on margin-safe decisions"
+    assert np.array_equal(np.asarray(gpu_med)[safe_v], np.asarray(med)[safe_v]), "medoid differs on margin-safe decisions"
+    cap = max(1, math.ceil(max_rejected_frac * b))       # tiny batches: one borderline decision is still reported
+    assert rej_t <= cap and rej_v <= cap, f"margin filter set aside {rej_t} / {rej_v} of {b} decisions (cap {cap})"
+    return rej_t, rej_v
+
+
+def assert_indices_unfiltered(gpu_ok, gpu_med, ok, med, what=""):
+    """100 % equality, no filter (inputs built by margin_safe_inputs)."""
+    b = int(np.asarray(ok).shape[0])
+    LOG.append({"test": _test_name(), "what": what, "decisions": b, "margin": SAFE_MARGIN, "rejected_thr": 0,
+                "rejected_vote": 0, "filtered": False})
+    assert np.array_equal(np.asarray(gpu_ok), np.asarray(ok)), "ref_ok differs"
+    assert np.array_equal(np.asarray(gpu_med), np.asarray(med)), "medoid differs"
+
+
+def planted_embeddings(count: int, n: int, d: int, seed: int) -> np.ndarray:
+    """Decisions with a clear medoid: rows mix a private direction with a per-decision shared one (weights U[0, 0.8]),
+    one random row per decision leans on the shared direction with weight 0.95, so the top-2 gap of the row means is
+    large for every pool size (random mixes alone leave pools of 64 with gaps below 2e-3 almost always)."""
+    rng = np.random.default_rng(seed)
+    own = rng.standard_normal((count, n, d), dtype=np.float32)
+    shared = rng.standard_normal((count, 1, d), dtype=np.float32)
+    mix = (0.8 * rng.random((count, n, 1), dtype=np.float32)).astype(np.float32)
+    mix[np.arange(count), rng.integers(0, n, count), 0] = 0.95
+    x = (1.0 - mix) * own + mix * shared
+    x /= np.linalg.norm(x, axis=2, keepdims=True)
+    return np.ascontiguousarray(x.astype(np.float32))
+
+
+def margin_safe_inputs(make_emb, b: int, seed: int, safe: float = SAFE_MARGIN, thr_choices=(-0.3, 0.6, 0.05, 0.3, 0.85)):
+    """-> (emb [b, N, D] f32, thr [b] f32, regenerated).  `make_emb(count, seed)` draws candidate decisions; a decision is
+    kept when its oracle vote gap >= safe, and gets the first threshold of `thr_choices` (rotated per decision, so
+    both verdicts occur) that is >= safe away from every row-0 cosine.  `regenerated` counts the draws thrown away."""
+    kept, thrs, thrown, rnd = [], [], 0, 0
+    while len(kept) < b:
+        emb = make_emb(2 * b, seed + 7919 * rnd)
+        rnd += 1
+        cos = numeric.cosine_matrix_batch(emb)
+        n = cos.shape[1]
+        means = cos.sum(axis=2) / n
+        srt = np.sort(means, axis=1)
+        gap = srt[:, -1] - srt[:, -2] if n > 1 else np.full(emb.shape[0], np.inf)
+        for i in range(emb.shape[0]):
+            if len(kept) >= b:
+                break
+            if gap[i] < safe:
+                thrown += 1
+                continue
+            row0 = cos[i, 0, 1:]
+            k0 = len(kept) % len(thr_choices)
+            pick = None
+            for k in range(len(thr_choices)):
+                t = thr_choices[(k0 + k) % len(thr_choices)]
+                if row0.size == 0 or np.min(np.abs(row0 - np.float64(np.float32(t)))) >= safe:
+                    pick = t
+                    break
+            if pick is None:
+                thrown += 1
+                continue
+            kept.append(emb[i])
+            thrs.append(pick)
+        assert rnd < 50, "margin-safe generator does not converge"
+    return np.ascontiguousarray(np.stack(kept), np.float32), np.asarray(thrs, np.float32), thrown

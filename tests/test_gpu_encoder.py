@@ -8,6 +8,7 @@ import pytest
 from oracle import encoder as oenc
 from oracle import numeric
 from quoracle_b200 import native, synth
+from tests import parity
 
 pytestmark = pytest.mark.gpu
 EMB_TOL = 2e-4      # abs, on unit-norm rows (fp32 accumulate + tanh.approx vs f64 libm)
@@ -115,10 +116,7 @@ def test_config1_plumbing():
     emb = oenc.encode(w.table_bf16, w.w_bf16, batch.token_ids.reshape(3, 64), batch.lens.reshape(3))
     ok, med, cos, margins = numeric.decide_batch(emb.reshape(1, 3, -1), batch.thr)
     assert np.max(np.abs(res.cos - cos)) < COS_TOL
-    if margins["thr"][0] > MARGIN:
-        assert res.ref_ok[0] == ok[0]
-    if margins["vote"][0] > MARGIN:
-        assert res.medoid[0] == med[0]
+    parity.assert_indices(res.ref_ok, res.medoid, ok, med, margins, MARGIN, what="config 1")
 
 
 @pytest.mark.parametrize("cg", [1, 2])
@@ -135,10 +133,9 @@ def test_decide_mid_batch(cg, ragged):
     assert np.max(np.abs(res.emb.reshape(-1, 768) - emb)) < EMB_TOL
     ok, med, cos, margins = numeric.decide_batch(emb.reshape(24, 8, 768), batch.thr.astype(np.float64))
     assert np.max(np.abs(res.cos - cos)) < COS_TOL
-    safe_t, safe_v = margins["thr"] > MARGIN, margins["vote"] > MARGIN
-    assert np.array_equal(res.ref_ok[safe_t], ok[safe_t])
-    assert np.array_equal(res.medoid[safe_v], med[safe_v])
-    assert safe_t.sum() >= 12 and safe_v.sum() >= 12   # the margin filter must not hollow out the test
+    # thresholds 0.995 / 0.9995 sit inside this encoder's cosine cloud, so a few decisions of 24
+    # may be decided by less than the margin: counted, capped at half the batch so the test cannot be hollowed out
+    parity.assert_indices(res.ref_ok, res.medoid, ok, med, margins, MARGIN, max_rejected_frac=0.5, what="config 2 shape")
     assert len(set(res.ref_ok.tolist())) == 2          # both verdicts occur
 
 
@@ -206,8 +203,7 @@ def test_shape_edges():
             assert np.max(np.abs(res.emb.reshape(b * n, -1) - emb)) < EMB_TOL, (b, n, t)
             ok, med, cos, margins = numeric.decide_batch(emb.reshape(b, n, -1), thr.astype(np.float64))
             assert np.max(np.abs(res.cos - cos)) < COS_TOL
-            st, sv = margins["thr"] > MARGIN, margins["vote"] > MARGIN
-            assert np.array_equal(res.ref_ok[st], ok[st]) and np.array_equal(res.medoid[sv], med[sv])
+            parity.assert_indices(res.ref_ok, res.medoid, ok, med, margins, MARGIN, what=f"shape {b}x{n}x{t}")
 
 
 def test_workspace_growth_and_context_reuse():
@@ -318,8 +314,8 @@ def test_packed_token_stream_matches_unpacked(dim, t):
         assert np.max(np.abs(packed.emb.reshape(b * n, dim) - want)) < EMB_TOL
         assert np.all(packed.emb.reshape(b * n, dim)[flat == 0] == 0.0)
         o_ok, o_med, o_cos, margins = numeric.decide_batch(want.reshape(b, n, dim), batch.thr)
-        safe_t, safe_v = margins["thr"] > MARGIN, margins["vote"] > MARGIN
-        assert np.array_equal(packed.ref_ok[safe_t], o_ok[safe_t]) and np.array_equal(packed.medoid[safe_v], o_med[safe_v])
+        parity.assert_indices(packed.ref_ok, packed.medoid, o_ok, o_med, margins, MARGIN, max_rejected_frac=0.25,
+                              what="packed token stream")
         # the pipelined host path packs too; auto mode picks packing for this batch (much more than 5 % saved)
         ctx.set_packing(0)
         out = native.DecideResult(np.empty(b, np.int32), np.empty(b, np.int32), np.empty((b, n, n), np.float32), None)
@@ -367,8 +363,8 @@ def test_ragged_csr_entry_points(dim):
         ctx.set_packing(0)
         assert np.max(np.abs(res.emb - ref.emb)) < 1e-6 and np.max(np.abs(res.cos - ref.cos)) < 1e-5
         o_ok, o_med, _, margins = numeric.decide_batch(want.reshape(b, n, dim), thr)
-        safe_t, safe_v = margins["thr"] > MARGIN, margins["vote"] > MARGIN
-        assert np.array_equal(res.ref_ok[safe_t], o_ok[safe_t]) and np.array_equal(res.medoid[safe_v], o_med[safe_v])
+        parity.assert_indices(res.ref_ok, res.medoid, o_ok, o_med, margins, MARGIN, max_rejected_frac=0.25,
+                              what="CSR entry points")
         # pipelined CSR form over all four slots
         outs = [native.DecideResult(np.empty(b, np.int32), np.empty(b, np.int32), np.empty((b, n, n), np.float32), None)
                 for _ in range(6)]

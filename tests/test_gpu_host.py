@@ -85,7 +85,11 @@ def test_lesson_dedup_matches_oracle(emb):
 
 
 def test_decide_tree_on_gpu_matches_oracle(emb):
-    """The batched decide step over a small tree on the real GPU path vs oracle format_result."""
+    """The batched decide step over a small tree on the real GPU path vs oracle format_result.
+
+    Scope: the oracle's `:embedding_fn` here returns the GPU's OWN embeddings (oracle_fn(emb)), so this checks the host
+    logic and K3 (cosine + rule on those vectors) -- NOT K1.  K1's values are checked against the numpy f64 encoder in
+    tests/test_gpu_encoder.py."""
     from oracle import aggregator as oagg
     from oracle import result as ores
     from quoracle_b200 import consensus
@@ -159,3 +163,40 @@ def test_semantic_similarity_pairs_on_gpu(emb):
         want = oagg.cosine_similarity(ea.astype(np.float64).tolist(), eb.astype(np.float64).tolist())
         assert abs(g - want) < 1e-6
     assert abs(got[2] - 1.0) < 1e-6
+
+
+def test_lesson_store_on_gpu_matches_oracle(emb):
+    """LessonStore: lesson rows resident in a device-side cache (qc_lesson_cache_*), one query row uploaded per dedup,
+    against the oracle's accumulate_lessons fed the same embeddings; and against the uncached mirror."""
+    fn1 = lambda t: oracle_fn(emb)(t, {})                                 # noqa: E731
+    rng = np.random.default_rng(8)
+    store = lesson_manager.LessonStore(emb, threshold=0.97, max_lessons=6)
+    want, plain = [], []
+    for step in range(10):
+        news = [{"type": "factual", "content": " ".join(rng.choice(SENTENCES, int(rng.integers(1, 3)))) if rng.random() > 0.1 else "",
+                 "confidence": int(rng.integers(1, 4))} for _ in range(int(rng.integers(1, 4)))]
+        _, want = olm.accumulate_lessons(want, news, {"embedding_fn": fn1, "similarity_threshold": 0.97, "max_lessons": 6})
+        _, plain = lesson_manager.accumulate_lessons(emb, plain, news, threshold=0.97, max_lessons=6)
+        _, got = store.accumulate(news)
+        assert got == want == plain, step
+    store.close()
+
+
+def test_lesson_cache_equals_first_match_batch(emb):
+    ctx = emb.ctx
+    rng = np.random.default_rng(4)
+    rows = rng.standard_normal((100, ctx.dim)).astype(np.float32)
+    cache = ctx.lesson_cache(128)
+    cache.append(rows[:60])
+    cache.append(rows[60:])
+    assert len(cache) == 100
+    for k in (0, 17, 99):
+        q = (2.0 * rows[k] + 0.02 * rows[(k + 1) % 100]).astype(np.float32)
+        idx, cos = cache.match(q, 0.95, want_cos=True)
+        w_idx, w_cos = ctx.first_match_batch(q[None], rows[None], np.array([0.95], np.float32))
+        assert idx == int(w_idx[0]) == k and np.array_equal(cos, w_cos[0])
+    perm = rng.permutation(100)[:40]
+    cache.gather(perm)
+    idx, _ = cache.match(rows[perm[5]], 0.99)
+    assert idx == 5 and len(cache) == 40
+    cache.close()

@@ -8,6 +8,7 @@ import pytest
 
 from oracle import numeric
 from quoracle_b200 import native, synth
+from tests import parity
 
 pytestmark = pytest.mark.gpu
 GOLD = json.loads((Path(__file__).parent / "golden" / "reference_vectors.json").read_text())
@@ -23,16 +24,20 @@ def ctx():
     c.close()
 
 
-def _check(ctx, emb, thr):
+def _check(ctx, emb, thr, max_rejected_frac=0.02):
     ref_ok, medoid, cos = ctx.similarity_batch(emb, thr)
     o_ok, o_med, o_cos, margins = numeric.decide_batch(emb, thr)
     assert np.all(np.isfinite(cos))
     assert np.max(np.abs(cos - o_cos)) < TIGHT
-    safe_thr = margins["thr"] > MARGIN
-    safe_vote = margins["vote"] > MARGIN
-    assert np.array_equal(ref_ok[safe_thr], o_ok[safe_thr])
-    assert np.array_equal(medoid[safe_vote], o_med[safe_vote])
-    return int((~safe_thr).sum()), int((~safe_vote).sum())
+    # equality wherever the oracle margin allows; the set-aside counts are logged, capped at 2 % and printed at the
+    # end of the run (tests/parity.py)
+    if emb.shape[1] == 2:
+        # a pool of two has equal row means by symmetry ((1 + c) / 2 twice): the vote margin is 0 for every decision and
+        # only the lowest-index tie-break is left to check -- which an fp32 ulp on the diagonal may flip either way
+        margins = dict(margins, vote=np.full(emb.shape[0], np.inf))
+        assert np.all((medoid == 0) | (medoid == 1))
+        o_med = medoid
+    return parity.assert_indices(ref_ok, medoid, o_ok, o_med, margins, MARGIN, max_rejected_frac=max_rejected_frac)
 
 
 def test_reference_cosine_vectors(ctx):
@@ -145,8 +150,8 @@ def test_tcgen05_split_keeps_the_low_mantissa_bits(ctx):
         ctx.set_similarity_path(0)
     o_ok, o_med, o_cos, margins = numeric.decide_batch(emb, thr)
     assert np.max(np.abs(cos - o_cos)) < 2e-6
-    safe = margins["vote"] > 1e-5
-    assert np.array_equal(medoid[safe], o_med[safe])
+    # thresholds are far from every cosine here; the vote is decided by structure below the TF32 resolution
+    parity.assert_indices(ref_ok, medoid, o_ok, o_med, margins, 1e-5, max_rejected_frac=0.1, what="tf32 low bits")
 
 
 def test_tcgen05_path_refuses_unaddressable_layout(ctx):
@@ -175,9 +180,8 @@ def test_config5_sweep_large_batch(ctx):
     emb = synth.make_embeddings(65536, 8, 384, seed=synth.BASE_SEED + 5)
     thr = np.resize(np.array([0.3, 0.5, 0.7], np.float32), 65536)
     bad_thr, bad_vote = _check(ctx, emb, thr)
-    # margin rejections (verdict decided by < 1e-4) are a property of the inputs: reported, and rare
+    # margin rejections (verdict decided by < 1e-4) are a property of the inputs: reported, capped at 2 %
     print(f"margin-rejected: thr {bad_thr}, vote {bad_vote} of 65536")
-    assert bad_thr < 0.05 * 65536 and bad_vote < 0.05 * 65536
 
 
 def test_batch_independence(ctx):
@@ -283,9 +287,9 @@ def test_random_shapes_against_the_oracle(ctx):
         assert np.max(np.abs(cos - o_cos)) < TIGHT
         if n >= 4:
             assert np.all(cos[::4, 3, :] == 0.0)
-        safe_t, safe_v = margins["thr"] > MARGIN, margins["vote"] > MARGIN
-        assert np.array_equal(ok[safe_t], o_ok[safe_t])
-        assert np.array_equal(med[safe_v], o_med[safe_v])
+        # adversarial rows (exact duplicates, opposites, thresholds of exactly +-1 / 0) sit ON the decision boundary by
+        # construction, so the filter is allowed to set aside whole batches here -- and every one is counted
+        parity.assert_indices(ok, med, o_ok, o_med, margins, MARGIN, max_rejected_frac=1.0, what="adversarial rows")
 
     run()
 
@@ -313,5 +317,42 @@ def test_tcgen05_ring_survives_long_tiles(ctx, n, d, b):
     got_cos = cos[:256].cpu().numpy()
     assert np.max(np.abs(got_cos - o_cos)) < TIGHT
     assert np.array_equal(cos[-256:].cpu().numpy(), got_cos)          # every repetition of the sample gives the same bits
-    safe = margins["vote"] > MARGIN
-    assert np.array_equal(med[:256].cpu().numpy()[safe], o_med[safe])
+    parity.assert_indices(ok[:256].cpu().numpy(), med[:256].cpu().numpy(), o_ok, o_med, margins, MARGIN)
+
+
+# ---- margin-safe inputs: 100 % index equality, no filter -----------------------------------
+def _safe_case(ctx, n, d, b, path):
+    def draw(count, seed):
+        return parity.planted_embeddings(count, n, d, seed)
+    emb, thr, thrown = parity.margin_safe_inputs(draw, b, seed=synth.BASE_SEED + 31 * n + d)
+    ctx.set_similarity_path(path)
+    try:
+        ok, med, cos = ctx.similarity_batch(emb, thr)
+    finally:
+        ctx.set_similarity_path(0)
+    o_ok, o_med, o_cos, margins = numeric.decide_batch(emb, thr)
+    assert margins["thr"].min() >= parity.SAFE_MARGIN * 0.999 and margins["vote"].min() >= parity.SAFE_MARGIN * 0.999
+    assert np.max(np.abs(cos - o_cos)) < TIGHT
+    parity.assert_indices_unfiltered(ok, med, o_ok, o_med, what=f"N={n} D={d} path={path} regenerated={thrown}")
+    assert len(set(o_ok.tolist())) == 2, "both verdicts must occur"
+    print(f"margin-safe N={n} D={d} B={b}: {thrown} draws regenerated, indices equal on 100 %")
+
+
+@pytest.mark.parametrize("n,d", [(3, 384), (4, 768), (5, 130), (8, 768), (8, 1536)])     # N = 2: the vote is a tie by symmetry
+def test_margin_safe_small_pool_kernel(ctx, n, d):
+    """qc_sim_small_kernel (N <= 8), both the one-warp and the four-warp layouts: bit-identical indices on every
+    decision of inputs that carry the SURVEY margin."""
+    _safe_case(ctx, n, d, 3000, 0)      # B >= 16 * SMs: one warp per decision
+    _safe_case(ctx, n, d, 400, 0)       # small batch: four warps per decision
+
+
+@pytest.mark.parametrize("n,d", [(9, 384), (16, 768), (32, 768), (48, 384), (64, 1536)])
+def test_margin_safe_tcgen05_kernel(ctx, n, d):
+    """qc_sim_tc_kernel (pools 9..64 on tcgen05 kind::tf32, 3xTF32 split)."""
+    _safe_case(ctx, n, d, 1200 if n <= 32 else 500, 2)
+
+
+@pytest.mark.parametrize("n,d", [(12, 100), (20, 5), (33, 200), (64, 384)])
+def test_margin_safe_mma_sync_kernel(ctx, n, d):
+    """qc_sim_large_kernel (the mma.sync fallback for layouts TMA cannot address, forced here for every shape)."""
+    _safe_case(ctx, n, d, 600, 1)

@@ -426,3 +426,35 @@ def test_packed_stream_plan_invariants():
             assert np.all(np.diff(crow[:k]) >= 0) and np.all(np.diff(crow[:k]) <= 1)
     with pytest.raises(native.QcError):
         native.debug_pack_plan(np.array([5], np.int32), 4, 128)          # len > T
+
+
+def test_lesson_store_equals_the_oracle_over_random_histories():
+    """LessonStore (rows resident in a lesson cache, one query row per dedup) against the oracle's
+    accumulate_lessons over random sequences of calls: merges (incl. duplicate contents), new lessons, lessons whose
+    embedding fails (empty content), and pruning."""
+    from oracle import lesson_manager as olm
+    emb, ctx = make_emb()
+    words = ["alpha", "beta", "gamma", "delta", "epsilon", "zeta", "eta", "theta", "iota", "kappa"]
+    rng = np.random.default_rng(12)
+
+    def ofn(text):
+        r = emb.get_embedding(text)
+        return ("ok", {"embedding": r[1]["embedding"].astype(np.float64).tolist()}) if r[0] == "ok" else r
+
+    for trial in range(6):
+        thr = float(rng.choice([0.9, 0.97, 0.999]))
+        max_lessons = int(rng.choice([5, 8, 100]))
+        store = lesson_manager.LessonStore(emb, threshold=thr, max_lessons=max_lessons)
+        want = []
+        for _ in range(12):
+            news = []
+            for _ in range(int(rng.integers(1, 4))):
+                k = int(rng.integers(1, 4))
+                content = " ".join(rng.choice(words, k)) if rng.random() > 0.08 else ""
+                news.append({"type": "factual", "content": content, "confidence": int(rng.integers(1, 4))})
+            _, want = olm.accumulate_lessons(want, news, {"embedding_fn": ofn, "similarity_threshold": thr,
+                                                           "max_lessons": max_lessons})
+            _, got = store.accumulate(news)
+            assert got == want, (trial, news)
+            assert len(store.cache) == sum(1 for r in store.row_of if r >= 0)
+        store.close()
