@@ -292,11 +292,17 @@ def decide_tree(collector: DecisionCollector, pending: Sequence[dict], round_num
     Pass 1 (host): cluster, find the winner, merge every non-semantic parameter, enqueue every semantic one.
     One collector flush (GPU).  Pass 2 (host): fill the semantic parameters, mode fallback on error."""
     plans = []
+    default_round, default_max = round_num, max_refinement_rounds
     for d in pending:
         responses = d["responses"]
         clusters = cluster(responses)
-        total = len(responses)
-        if find_majority(clusters, total, round_num) is None and round_num <= max_refinement_rounds:
+        # per-decision overrides (consensus_driver.run_consensus_rounds): the reference counts majorities against the
+        # POOL size (consensus.ex:297), agents of one sweep sit at different rounds, and a dead refinement formats the
+        # answers in hand whatever the majority says ("force")
+        total = d.get("total", len(responses))
+        round_num = d.get("round", default_round)
+        max_refinement_rounds = d.get("max_refinement_rounds", default_max)
+        if not d.get("force") and find_majority(clusters, total, round_num) is None and round_num <= max_refinement_rounds:
             plans.append({"agent_id": d["agent_id"], "kind": "no_majority", "clusters": clusters})
             continue
         kind, win = pick_winner(clusters, total)
@@ -321,7 +327,8 @@ def decide_tree(collector: DecisionCollector, pending: Sequence[dict], round_num
                     r = host_rule(rule, vals)
                     merged[p] = r[1] if r[0] == "ok" else mode_value(vals)
         plans.append({"agent_id": d["agent_id"], "kind": kind, "win": win, "schema": schema, "merged": merged,
-                      "waiting": waiting, "batch": batch, "total": total})
+                      "waiting": waiting, "batch": batch, "total": total, "round": round_num,
+                      "max_rounds": max_refinement_rounds})
     results = collector.flush()
     out = []
     for pl in plans:
@@ -361,5 +368,5 @@ def decide_tree(collector: DecisionCollector, pending: Sequence[dict], round_num
                       "reasoning": next((a.get("reasoning") for a in win["actions"] if a.get("reasoning") != ""), ""),
                       "wait": wait_rule(waits) if waits else False}
         out.append({"agent_id": pl["agent_id"], "kind": pl["kind"], "action": action,
-                    "confidence": confidence(win["count"], pl["total"], round_num, max_refinement_rounds)})
+                    "confidence": confidence(win["count"], pl["total"], pl["round"], pl["max_rounds"])})
     return out

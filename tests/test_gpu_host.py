@@ -200,3 +200,45 @@ def test_lesson_cache_equals_first_match_batch(emb):
     idx, _ = cache.match(rows[perm[5]], 0.99)
     assert idx == 5 and len(cache) == 40
     cache.close()
+
+
+def test_config3_tree_through_the_round_loop_matches_the_oracle(emb):
+    """BASELINE config 3's shape -- a depth-4 / fan-out-8 agent tree (8 + 64 + 512 + 4096 agents) -- driven through the
+    consensus round loop (rows A10 / A11) on the real GPU path: scripted pools (the :model_query_fn seam), majority /
+    refinement / forced decision per agent, every sweep ONE batched flush, and the result of every agent equal to
+    the sequential oracle's (execute_consensus_process/3 + execute_refinement/3 restated, consensus.ex:295-390).
+    The oracle embeds through the GPU's own vectors (see oracle_fn): host logic + K3 are under test here."""
+    from tests.test_host_logic import _compare_driver, _tree_agents
+    agents = _tree_agents(4, 8)
+    assert len(agents) == 8 + 64 + 512 + 4096
+    before = emb.ctx.launch_count()
+    got, kinds = _compare_driver(emb, agents, seed=3)
+    launches = emb.ctx.launch_count() - before
+    print(f"config-3 tree: {len(agents)} agents, outcomes {kinds}, {got['__sweeps__']} sweeps, {launches} kernel launches")
+    assert kinds.get("consensus", 0) > 1000 and kinds.get("forced_decision", 0) > 100
+    assert got["__sweeps__"] <= 6
+    assert launches <= got["__sweeps__"] * 12                        # per sweep: pack + K1 + K2 + one K3 per pool size
+
+
+def test_single_agent_latency_through_the_timed_collector(emb):
+    """A11's latency bound: one agent alone, asking for one 8-value merge, is answered within the collector's
+    max_wait_ms + the p95 of a single-decision call (profiles/latency_r1.md: 76 us on the C ABI; the Python mirror adds
+    its own tokenising) + 2 ms of slack -- it never waits for a batch that does not fill."""
+    import time
+    from quoracle_b200.collector import TimedCollector
+    col = TimedCollector(emb, max_pending=4096, max_wait_ms=2.0)
+    try:
+        vals = [f"{SENTENCES[i % len(SENTENCES)]} variant {i}" for i in range(8)]
+        col.decide(vals, 0.9)                                           # warm (first call sizes workspaces)
+        lat = []
+        for k in range(30):
+            vs = [v + f" #{k}" for v in vals]                           # new texts: no embedding-cache hits
+            t0 = time.perf_counter()
+            r, med = col.decide(vs, 0.9)
+            lat.append(time.perf_counter() - t0)
+            assert r[0] in ("ok", "error") and med is not None
+        p95 = float(np.percentile(lat, 95)) * 1e3
+        print(f"single-agent latency through TimedCollector(max_wait_ms=2): p50 {np.percentile(lat, 50) * 1e3:.2f} ms, p95 {p95:.2f} ms")
+        assert p95 <= 2.0 + 0.076 + 2.0
+    finally:
+        col.close()

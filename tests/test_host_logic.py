@@ -458,3 +458,163 @@ def test_lesson_store_equals_the_oracle_over_random_histories():
             assert got == want, (trial, news)
             assert len(store.cache) == sum(1 for r in store.row_of if r >= 0)
         store.close()
+
+
+# ---- A10 / A11: the round loop and the decide step, batched over a tree vs the sequential oracle -------------------
+def scripted_query_fn(seed: int, pool_size_of, p_agree=0.45, p_error=0.06, p_empty=0.05, p_invalid=0.05):
+    """A deterministic `query_fn` (the :model_query_fn seam one level up): what the pool of agent `state["agent_id"]`
+    answers at round `opts["round"]` depends only on (seed, agent, round, attempt), so the batched driver and the
+    sequential oracle see the same LLM."""
+    import zlib
+
+    def fn(state, model_pool, opts):
+        rnd = opts.get("round", 1)
+        key = f"{seed}:{state['agent_id']}:{rnd}:{state.get('consensus_retry_count', 0)}".encode()
+        rng = np.random.default_rng(zlib.crc32(key))
+        roll = rng.random()
+        new_state = dict(state, queries=state.get("queries", 0) + 1)
+        n = pool_size_of(state["agent_id"])
+        if roll < p_error:
+            return ("error", "service_unavailable")
+        if roll < p_error + p_empty:
+            return ("ok", [None] * n, new_state)
+        if roll < p_error + p_empty + p_invalid:
+            return ("ok", [{"action": "invalid", "params": {}} for _ in range(n)], new_state)
+        props = _random_proposals(rng, n)
+        if rng.random() < p_agree:                                  # the pool converges: everyone proposes the same action
+            props = [dict(props[0]) for _ in range(n)]
+        if n > 2 and rng.random() < 0.2:
+            props[int(rng.integers(0, n))] = None                    # one model's answer did not parse
+        return ("ok", props, new_state)
+    return fn
+
+
+def _validate(r):
+    return None if r["action"] == "invalid" else r
+
+
+def _tree_agents(depth, fanout, limit=None):
+    from quoracle_b200 import sharding
+    paths = sharding.tree_agent_order(depth, fanout)
+    if limit:
+        paths = paths[:limit]
+    agents = []
+    for p in paths:
+        aid = "/".join(map(str, p))
+        agents.append({"agent_id": aid,
+                       "state": {"agent_id": aid, "model_histories": {f"m{k}": [] for k in range(3 + (len(aid) % 6))},
+                                 "max_refinement_rounds": [1, 2, 4][len(p) % 3],
+                                 "force_reflection": False}})
+    return agents
+
+
+def _compare_driver(emb, agents, seed):
+    from oracle import consensus_driver as odrv
+    from quoracle_b200 import consensus_driver
+
+    def ofn(value, opts):
+        r = emb.get_embedding(value)
+        return ("ok", {"embedding": r[1]["embedding"].astype(np.float64).tolist()}) if r[0] == "ok" else r
+
+    pool = {a["agent_id"]: len(a["state"]["model_histories"]) for a in agents}
+    qf = scripted_query_fn(seed, lambda i: pool[i])
+    got = consensus_driver.run_consensus_rounds(DecisionCollector(emb), agents, qf, _validate)
+    kinds = {}
+    for a in agents:
+        want = odrv.get_consensus_with_state(a["state"], {}, qf, _validate, embedding_fn=ofn)
+        g = got[a["agent_id"]]
+        assert g[0] == want[0], (a["agent_id"], g, want)
+        if want[0] == "error":
+            assert g[1] == want[1]
+            kinds[want[1]] = kinds.get(want[1], 0) + 1
+            continue
+        kind, action, meta = want[1]
+        assert g[1]["kind"] == kind, (a["agent_id"], g[1], want[1])
+        assert g[2] == want[2]                                        # the state the last query left behind
+        kinds[kind] = kinds.get(kind, 0) + 1
+        if action == "error":
+            assert g[1]["action"]["action"] == "error"
+            continue
+        assert g[1]["action"]["action"] == action["action"] and g[1]["action"]["params"] == action["params"]
+        assert g[1]["action"]["wait"] == action["wait"] and g[1]["action"]["reasoning"] == action["reasoning"]
+        assert abs(g[1]["confidence"] - meta["confidence"]) < 1e-12
+        assert g[1]["meta"].get("forced_reflection_applied", False) == meta.get("forced_reflection_applied", False)
+    return got, kinds
+
+
+def test_round_loop_over_a_tree_equals_the_sequential_oracle():
+    emb, ctx = make_emb()
+    agents = _tree_agents(3, 6, limit=180)
+    # a few single-model pools with forced reflection (consensus.ex:303-321)
+    for a in agents[::17]:
+        a["state"]["model_histories"] = {"solo": []}
+        a["state"]["force_reflection"] = True
+    got, kinds = _compare_driver(emb, agents, seed=7)
+    assert kinds.get("consensus", 0) > 20 and kinds.get("forced_decision", 0) > 5
+    assert kinds.get("all_models_failed", 0) + kinds.get("all_responses_invalid", 0) + kinds.get("service_unavailable", 0) > 3
+    # every sweep is one batched flush: the rounds in flight bound the GPU calls, not the number of agents
+    assert got["__sweeps__"] <= 6 and ctx.calls["embed"] <= got["__sweeps__"]
+
+
+def test_decide_step_retries_at_most_three_times():
+    """run_consensus_cycle/2 + handle_consensus_error/4 (message_handler.ex:125-148,353-389) for a whole tree vs the
+    oracle's per-agent loop: retryable failures get a second and a third attempt, then stall; other errors fail."""
+    from oracle import consensus_driver as odrv
+    from quoracle_b200 import consensus_driver
+    emb, ctx = make_emb()
+    agents = _tree_agents(2, 8, limit=60)
+    pool = {a["agent_id"]: len(a["state"]["model_histories"]) for a in agents}
+    qf = scripted_query_fn(11, lambda i: pool[i], p_agree=0.5, p_error=0.05, p_empty=0.25, p_invalid=0.2)
+
+    def ofn(value, opts):
+        r = emb.get_embedding(value)
+        return ("ok", {"embedding": r[1]["embedding"].astype(np.float64).tolist()}) if r[0] == "ok" else r
+
+    def execute(state, action):
+        return dict(state, executed=action["action"] if isinstance(action, dict) else action)
+
+    got = consensus_driver.run_consensus_cycles(DecisionCollector(emb), agents, qf, execute, _validate)
+    outcomes = {}
+    for a in agents:
+        def cfn(state):
+            r = odrv.get_consensus_with_state(state, {}, qf, _validate, embedding_fn=ofn)
+            return ("ok", r[1][1], r[2], None) if r[0] == "ok" else ("error", r[1], None)
+        w_state, w_out = odrv.run_consensus_cycle(a["state"], cfn, execute)
+        g_state, g_out = got[a["agent_id"]]
+        assert g_out[0] == w_out[0], (a["agent_id"], g_out, w_out)
+        outcomes[w_out[0]] = outcomes.get(w_out[0], 0) + 1
+        if w_out[0] == "executed":
+            assert g_out[1]["action"] == w_out[1]["action"] and g_out[1].get("params") == w_out[1].get("params")
+            assert g_state["executed"] == w_state["executed"] and g_state["consensus_retry_count"] == 0
+        else:
+            assert g_out[1:] == w_out[1:]
+            assert g_state.get("consensus_retry_count", 0) == w_state.get("consensus_retry_count", 0)
+    assert outcomes.get("executed", 0) > 20 and outcomes.get("stalled", 0) >= 1 and outcomes.get("failed", 0) >= 1
+
+
+def test_timed_collector_flushes_on_size_or_deadline():
+    """A lone agent is answered after ~max_wait_ms (no batch ever fills); a burst of agents shares flushes."""
+    import threading
+    import time
+    from quoracle_b200.collector import TimedCollector
+    emb, ctx = make_emb()
+    col = TimedCollector(emb, max_pending=8, max_wait_ms=20.0)
+    try:
+        t0 = time.perf_counter()
+        r, med = col.decide(["send report now", "send the report now", "send report now please"], 0.5)
+        lone = time.perf_counter() - t0
+        assert r[0] in ("ok", "error") and col.flushes == 1
+        assert 0.015 <= lone < 1.0                                   # waited for the deadline, not for 8 merges
+        outs = [None] * 24
+        def agent(i):
+            outs[i] = col.decide([f"restart service {i % 3}", f"restart the service {i % 3}", "ship it"], 0.9)
+        ts = [threading.Thread(target=agent, args=(i,)) for i in range(24)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert all(o is not None for o in outs)
+        assert col.decided == 25 and 4 <= col.flushes <= 25          # bursts batch; size 8 forces at least 3 more flushes
+        assert col.decide(["same", "same"], 0.9)[0] == ("ok", "same")   # identical values short-circuit, no embedding
+    finally:
+        col.close()
