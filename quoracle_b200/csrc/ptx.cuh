@@ -155,6 +155,16 @@ __device__ __forceinline__ long long mbar_wait_cluster(uint64_t* bar, uint32_t p
   return clock64() - t0;
 }
 
+// ---- programmatic dependent launch ------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while the kernel before it in
+// the stream is still running (as soon as every CTA of that kernel has called griddep_launch_dependents() or exited);
+// griddep_wait() then blocks until that kernel has completed and its memory is visible.  Every kernel of this library
+// that is launched with the attribute calls griddep_wait() before it touches anything a previous kernel may have
+// written or may still be reading; what overlaps is launch latency and per-CTA setup (barrier init, TMEM allocation,
+// descriptor prefetch).  Both instructions are no-ops in a kernel launched without the attribute / without dependents.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- cluster ------------------------------------------------------------------------
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");

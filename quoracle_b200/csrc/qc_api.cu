@@ -125,6 +125,7 @@ struct qc_ctx {
   int packing = 0;               // 0 auto, 1 never, 2 whenever the tiling allows (test hook)
   int sim_path = 0;              // K3 for pools 9..64: 0 auto (tcgen05 when the layout allows), 1 mma.sync, 2 tcgen05
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved once at create
+  bool pdl = true;               // programmatic dependent launch of K1 / K2 / K3 (QC_PDL=0 in the environment turns it off)
   bool variant_forced = false;   // set by qc_encoder_set_variant / _set_cta_group; else chosen per call from T
   uint16_t* d_table = nullptr;
   uint16_t* d_wt = nullptr;  // W^T [dim(out) x dim(in)] bf16
@@ -456,7 +457,7 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
     QC_CUDA(packed->ensure(static_cast<size_t>(nchunks) * CH * sizeof(int32_t)));
     QC_CUDA(part.ensure(static_cast<size_t>(nruns > 0 ? nruns : 1) * c->dim * sizeof(float)));
     c->launches++;
-    QC_CUDA(qc::launch_pack_tokens(d_tok, chunk_src, chunk_n, static_cast<int32_t*>(packed->p), nchunks, CH, s));
+    QC_CUDA(qc::launch_pack_tokens(d_tok, chunk_src, chunk_n, static_cast<int32_t*>(packed->p), nchunks, CH, s, c->pdl));
   } else {
     QC_CUDA(part.ensure(static_cast<size_t>(R) * bpc * c->dim * sizeof(float)));
   }
@@ -495,6 +496,7 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
     }
     a.num_sms = c->num_sms;
     a.stream = s;
+    a.pdl = c->pdl;
     QC_CUDA(qc::launch_encode(a));
   }
   {
@@ -504,7 +506,7 @@ int encode_dev(qc_ctx* c, const int32_t* d_tok, const int32_t* d_lens, int R, in
       return QC_OK;
     }
     QC_CUDA(qc::launch_finalize(static_cast<const float*>(part.p), d_lens, scatter ? *scatter : qc::finalize_plain(d_emb),
-                                pack ? row_start : nullptr, R, bpc, TB, c->dim, s));
+                                pack ? row_start : nullptr, R, bpc, TB, c->dim, s, c->pdl));
   }
   return QC_OK;
 }
@@ -599,6 +601,7 @@ int qc_ctx_create(qc_ctx** out, int device_id, const qc_encoder_cfg* enc) {
   if (c == nullptr) return QC_ERR_OUT_OF_MEMORY;
   c->device = device_id;
   c->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("QC_PDL")) c->pdl = e[0] != '0';
   DeviceGuard g(device_id);
   int st = QC_OK;
   do {
@@ -859,10 +862,10 @@ int similarity_dev(qc_ctx* c, const float* d_emb, int B, int N, int D, const flo
         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return QC_ERR_CUDA;
     QC_CUDA(qc::launch_similarity_tc(&xm, B, N, D, d_thr, d_ref_ok, d_medoid, d_cos, err,
-                                     c->stall_on ? static_cast<unsigned long long*>(c->stall.p) : nullptr, c->num_sms, s));
+                                     c->stall_on ? static_cast<unsigned long long*>(c->stall.p) : nullptr, c->num_sms, s, c->pdl));
     return QC_OK;
   }
-  QC_CUDA(qc::launch_similarity(d_emb, B, N, D, d_thr, d_ref_ok, d_medoid, d_cos, c->num_sms, s));
+  QC_CUDA(qc::launch_similarity(d_emb, B, N, D, d_thr, d_ref_ok, d_medoid, d_cos, c->num_sms, s, c->pdl));
   return QC_OK;
 }
 }  // namespace

@@ -4,7 +4,27 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 namespace qc {
+
+// One launch path for every kernel of the library: `pdl` adds the programmatic-stream-serialization attribute (the
+// kernel must then call ptx::griddep_wait() before touching memory of earlier kernels in the stream).
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // K1 tiling variant: tokens per resident block, CTAs per MMA group (1 | 2), k-width of a streamed W stage.
 struct EncoderVariant {
@@ -33,6 +53,7 @@ struct EncoderLaunch {
   int max_clusters;            // co-resident clusters of this variant (0 = ask the occupancy API at launch)
   EncoderVariant variant;
   cudaStream_t stream;
+  bool pdl;                    // launch with programmatic stream serialization (see launch_kernel)
 };
 
 // Per-device function attributes (dynamic shared-memory opt-ins); qc_ctx_create calls these with the context's
@@ -69,11 +90,11 @@ inline FinalizeDst finalize_plain(float* emb) {
   return d;
 }
 cudaError_t launch_finalize(const float* part, const int32_t* lens, const FinalizeDst& dst, const int32_t* row_start,
-                            int R, int bpc, int TB, int dim, cudaStream_t stream);
+                            int R, int bpc, int TB, int dim, cudaStream_t stream, bool pdl = false);
 // Ragged batches: token ids copied into a stream of `chunk`-slot chunks (each chunk belongs to one candidate);
 // chunk = encoder_chunk_tokens(token block): the widest of 32 / 16 / 8 dividing it.
 cudaError_t launch_pack_tokens(const int32_t* token_ids, const int32_t* chunk_src, const int32_t* chunk_n,
-                               int32_t* packed, int nchunks, int chunk, cudaStream_t stream);
+                               int32_t* packed, int nchunks, int chunk, cudaStream_t stream, bool pdl = false);
 inline int encoder_chunk_tokens(int tb) { return tb % 32 == 0 ? 32 : (tb % 16 == 0 ? 16 : 8); }
 
 // Candidates sharded on T: per-rank partial sums [world][max_rows][D] + token counts [world][max_rows] in every
@@ -101,12 +122,12 @@ cudaError_t launch_peer_wait(const PeerFlags& f, uint32_t epoch, int32_t* dbg, c
 
 // K3: per decision: N x N cosine matrix, reference verdict, medoid vote.
 cudaError_t launch_similarity(const float* emb, int B, int N, int D, const float* thr, int32_t* ref_ok,
-                              int32_t* medoid, float* cos, int num_sms, cudaStream_t stream);
+                              int32_t* medoid, float* cos, int num_sms, cudaStream_t stream, bool pdl = false);
 
 // K3 for pools of 9..64 on tcgen05 (kind::tf32, 3xTF32 split); x_tmap views emb as [B*N x D] fp32, box 32 x 128.
 cudaError_t launch_similarity_tc(const CUtensorMap* x_tmap, int B, int N, int D, const float* thr, int32_t* ref_ok,
                                  int32_t* medoid, float* cos, int32_t* dbg, unsigned long long* stall, int num_sms,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, bool pdl = false);
 
 // Lesson dedup: first m with cos(query_q, rows[q, m]) >= thr[q].
 cudaError_t launch_first_match(const float* query, const float* rows, int Q, int M, int D, const float* thr,

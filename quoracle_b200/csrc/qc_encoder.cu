@@ -256,6 +256,12 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
   if constexpr (CL > 1) cluster_sync(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may have run
+  // under the tail of the previous kernel of the stream.  From here on this kernel reads token ids a pack kernel may
+  // have produced and overwrites the partial sums the previous step's K2 read, so every thread waits for the
+  // previous kernel to finish; the kernel after this one (K2) may be staged right away -- it waits the same way.
+  griddep_wait();
+  griddep_launch_dependents();
 
   if (warp < 4) {
     // ===================== epilogue: TMEM -> GELU -> token sum -> part ======================
@@ -622,13 +628,15 @@ static cudaError_t launch_encode_t(const EncoderLaunch& a) {
   cfg.blockDim = dim3(kEncThreads);
   cfg.dynamicSmemBytes = Tr::SMEM_BYTES;
   cfg.stream = a.stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = a.pdl ? 2 : 1;
   if constexpr (CL > 2) {
     // Clusters of 4 / 8 SMs must sit inside one GPC: the persistent grid is as many clusters as can be co-resident
     // (a wave that does not fit would serialise behind the first).  a.max_clusters caches the occupancy query.

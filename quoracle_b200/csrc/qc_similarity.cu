@@ -40,21 +40,31 @@ __global__ void __launch_bounds__(256) qc_finalize_kernel(const float* __restric
                                                           int D) {
   const int r = blockIdx.x;
   if (r >= R) return;
+  ptx::griddep_wait();                 // K1's partial sums (programmatic dependent launch, see ptx.cuh)
+  ptx::griddep_launch_dependents();
   const int len = lens[r];
   // dense: candidate r owns partial rows r*bpc .. (one per token block).  packed (row_start != nullptr): it owns
   // rows row_start[r] .. row_start[r+1]-1, one per 32-token chunk of the packed token stream.
   const int nb = row_start != nullptr ? row_start[r + 1] - row_start[r] : (len + TB - 1) / TB;
   const float* p = part + (row_start != nullptr ? static_cast<size_t>(row_start[r]) : static_cast<size_t>(r) * bpc) * D;
+  // Block sums in fixed block order (j ascending per element), the PER elements of a thread side by side and four
+  // blocks per trip so that a dozen independent loads are in flight (the kernel is latency-bound: 2048 small rows).
   float v[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) v[i] = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < nb; ++j) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int d = threadIdx.x + i * 256;
+      if (d < D) v[i] += p[static_cast<size_t>(j) * D + d];
+    }
+  }
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const int d = threadIdx.x + i * 256;
-    float s = 0.f;
-    if (d < D) {
-      for (int j = 0; j < nb; ++j) s += p[static_cast<size_t>(j) * D + d];  // fixed block order
-      s = len > 0 ? s / static_cast<float>(len) : 0.f;
-    }
+    const float s = (d < D && len > 0) ? v[i] / static_cast<float>(len) : 0.f;
     v[i] = s;
     ss += s * s;
   }
@@ -83,14 +93,13 @@ __global__ void __launch_bounds__(256) qc_finalize_kernel(const float* __restric
 }
 
 cudaError_t launch_finalize(const float* part, const int32_t* lens, const FinalizeDst& dst, const int32_t* row_start,
-                            int R, int bpc, int TB, int dim, cudaStream_t stream) {
+                            int R, int bpc, int TB, int dim, cudaStream_t stream, bool pdl) {
   if (R <= 0) return cudaSuccess;
   if (dst.count < 1 || dst.count > kMaxFinalizeDst || dst.n_local < 1) return cudaErrorInvalidValue;
-  if (dim <= 512) qc_finalize_kernel<2><<<R, 256, 0, stream>>>(part, lens, dst, row_start, R, bpc, TB, dim);
-  else if (dim <= 1024) qc_finalize_kernel<4><<<R, 256, 0, stream>>>(part, lens, dst, row_start, R, bpc, TB, dim);
-  else if (dim <= 2048) qc_finalize_kernel<8><<<R, 256, 0, stream>>>(part, lens, dst, row_start, R, bpc, TB, dim);
-  else return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  if (dim <= 512) return launch_kernel(qc_finalize_kernel<2>, dim3(R), dim3(256), 0, stream, pdl, part, lens, dst, row_start, R, bpc, TB, dim);
+  if (dim <= 1024) return launch_kernel(qc_finalize_kernel<4>, dim3(R), dim3(256), 0, stream, pdl, part, lens, dst, row_start, R, bpc, TB, dim);
+  if (dim <= 2048) return launch_kernel(qc_finalize_kernel<8>, dim3(R), dim3(256), 0, stream, pdl, part, lens, dst, row_start, R, bpc, TB, dim);
+  return cudaErrorInvalidValue;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -103,18 +112,20 @@ __global__ void __launch_bounds__(256) qc_pack_tokens_kernel(const int32_t* __re
                                                              int32_t* __restrict__ packed, int nchunks, int chunk) {
   const int idx = blockIdx.x * 256 + threadIdx.x;
   const int c = idx / chunk, i = idx - c * chunk;
+  ptx::griddep_wait();                 // `packed` may still be read by the previous step's K1
+  ptx::griddep_launch_dependents();
   if (c >= nchunks) return;
   packed[idx] = i < chunk_n[c] ? token_ids[static_cast<size_t>(chunk_src[c]) + i] : -1;
 }
 
 cudaError_t launch_pack_tokens(const int32_t* token_ids, const int32_t* chunk_src, const int32_t* chunk_n,
-                               int32_t* packed, int nchunks, int chunk, cudaStream_t stream) {
+                               int32_t* packed, int nchunks, int chunk, cudaStream_t stream, bool pdl) {
   if (nchunks <= 0) return cudaSuccess;
   const long long slots = static_cast<long long>(nchunks) * chunk;
   if (slots > 0x7fffffffLL) return cudaErrorInvalidValue;
   const int blocks = static_cast<int>((slots + 255) / 256);
-  qc_pack_tokens_kernel<<<blocks, 256, 0, stream>>>(token_ids, chunk_src, chunk_n, packed, nchunks, chunk);
-  return cudaGetLastError();
+  return launch_kernel(qc_pack_tokens_kernel, dim3(blocks), dim3(256), 0, stream, pdl, token_ids, chunk_src, chunk_n, packed,
+                       nchunks, chunk);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -287,6 +298,7 @@ __global__ void __launch_bounds__(256) qc_sim_small_kernel(const float* __restri
   constexpr int GT = 32 * WPD;             // threads cooperating on one decision
   __shared__ float red[DPB][P][GT + 1];
   __shared__ float tot[DPB][P];
+  __shared__ float seg_sum[DPB][P][WPD];
   __shared__ float cs[DPB][N * N];
   __shared__ float rmean[DPB][N];
 
@@ -297,6 +309,8 @@ __global__ void __launch_bounds__(256) qc_sim_small_kernel(const float* __restri
   const int tg = slice * 32 + lane;        // thread index within the decision group
   const int b = blockIdx.x * DPB + ds;
   const bool live = b < B;
+  ptx::griddep_wait();                 // K2's rows (programmatic dependent launch, see ptx.cuh)
+  ptx::griddep_launch_dependents();
 
   float acc[P];
 #pragma unroll
@@ -337,12 +351,33 @@ __global__ void __launch_bounds__(256) qc_sim_small_kernel(const float* __restri
 #pragma unroll
   for (int p = 0; p < P; ++p) red[ds][p][tg] = acc[p];
   __syncthreads();
-  // pair p: fixed-order sum of the GT per-thread partials
-  for (int p = tg; p < P; p += GT) {
-    float s = 0.f;
+  // pair p: fixed-order sum of the GT per-thread partials.  One warp per decision: lane p walks its 32 partials.  Four
+  // warps per decision (small batches, latency matters): the 128 partials of a pair are cut into NSEG segments summed by
+  // different threads, then the segment sums are added in order -- a fixed tree, so results stay run-to-run identical,
+  // with a dependent chain of 32 + 4 adds instead of 128.
+  if constexpr (WPD == 1) {
+    for (int p = tg; p < P; p += GT) {
+      float s = 0.f;
 #pragma unroll 8
-    for (int t = 0; t < GT; ++t) s += red[ds][p][t];
-    tot[ds][p] = s;
+      for (int t = 0; t < GT; ++t) s += red[ds][p][t];
+      tot[ds][p] = s;
+    }
+  } else {
+    constexpr int NSEG = GT / 32;
+    for (int u = tg; u < P * NSEG; u += GT) {
+      const int p = u / NSEG, seg = u - p * NSEG;
+      float s = 0.f;
+#pragma unroll 8
+      for (int t = 0; t < 32; ++t) s += red[ds][p][seg * 32 + t];
+      seg_sum[ds][p][seg] = s;
+    }
+    __syncthreads();
+    for (int p = tg; p < P; p += GT) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < NSEG; ++q) s += seg_sum[ds][p][q];
+      tot[ds][p] = s;
+    }
   }
   __syncthreads();
   // cosine element e = (i, j); pair index of (i <= j) is i*N - i(i-1)/2 + (j - i)
@@ -454,6 +489,8 @@ __global__ void __launch_bounds__(kSimThreads) qc_sim_large_kernel(const float* 
   else if (Np == 48) { rb = warp >> 1; cb0 = (warp & 1) * 3; ncb = warp < 6 ? 3 : 0; }
   else { rb = warp >> 1; cb0 = (warp & 1) * 4; ncb = 4; }
 
+  ptx::griddep_wait();                 // K2's rows (programmatic dependent launch, see ptx.cuh)
+  ptx::griddep_launch_dependents();
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const float* x = emb + static_cast<size_t>(b) * N * D;
     float acc[4][4];
@@ -568,20 +605,19 @@ constexpr int kSimLargeSmem = (2 * 64 * kSimRS + 64 * 65) * static_cast<int>(siz
 
 template <int N>
 static cudaError_t launch_small(const float* emb, int B, int D, const float* thr, int32_t* ref_ok, int32_t* medoid,
-                                float* cos, bool vec, int num_sms, cudaStream_t stream) {
+                                float* cos, bool vec, int num_sms, cudaStream_t stream, bool pdl) {
   // one warp per decision needs >= ~16 warps per SM in flight to cover HBM latency; below that, split the
   // columns of each decision over four warps
   const bool wide = B < num_sms * 16;
   if (wide) {
     const int grid = (B + 1) / 2;
-    if (vec) qc_sim_small_kernel<N, true, 4><<<grid, 256, 0, stream>>>(emb, B, D, thr, ref_ok, medoid, cos);
-    else qc_sim_small_kernel<N, false, 4><<<grid, 256, 0, stream>>>(emb, B, D, thr, ref_ok, medoid, cos);
+    if (vec) return launch_kernel(qc_sim_small_kernel<N, true, 4>, dim3(grid), dim3(256), 0, stream, pdl, emb, B, D, thr, ref_ok, medoid, cos);
+    return launch_kernel(qc_sim_small_kernel<N, false, 4>, dim3(grid), dim3(256), 0, stream, pdl, emb, B, D, thr, ref_ok, medoid, cos);
   } else {
     const int grid = (B + 7) / 8;
-    if (vec) qc_sim_small_kernel<N, true, 1><<<grid, 256, 0, stream>>>(emb, B, D, thr, ref_ok, medoid, cos);
-    else qc_sim_small_kernel<N, false, 1><<<grid, 256, 0, stream>>>(emb, B, D, thr, ref_ok, medoid, cos);
+    if (vec) return launch_kernel(qc_sim_small_kernel<N, true, 1>, dim3(grid), dim3(256), 0, stream, pdl, emb, B, D, thr, ref_ok, medoid, cos);
+    return launch_kernel(qc_sim_small_kernel<N, false, 1>, dim3(grid), dim3(256), 0, stream, pdl, emb, B, D, thr, ref_ok, medoid, cos);
   }
-  return cudaGetLastError();
 }
 
 // Shared-memory opt-in (51 KB) of the mma.sync kernel on the current device (called by qc_ctx_create).
@@ -592,25 +628,24 @@ cudaError_t similarity_prepare_device() {
 }
 
 cudaError_t launch_similarity(const float* emb, int B, int N, int D, const float* thr, int32_t* ref_ok,
-                              int32_t* medoid, float* cos, int num_sms, cudaStream_t stream) {
+                              int32_t* medoid, float* cos, int num_sms, cudaStream_t stream, bool pdl) {
   if (B <= 0) return cudaSuccess;
   if (N < 1 || N > 64 || D < 1) return cudaErrorInvalidValue;
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(emb) & 15) == 0);
   switch (N) {
-    case 1: return launch_small<1>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
-    case 2: return launch_small<2>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
-    case 3: return launch_small<3>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
-    case 4: return launch_small<4>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
-    case 5: return launch_small<5>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
-    case 6: return launch_small<6>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
-    case 7: return launch_small<7>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
-    case 8: return launch_small<8>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream);
+    case 1: return launch_small<1>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream, pdl);
+    case 2: return launch_small<2>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream, pdl);
+    case 3: return launch_small<3>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream, pdl);
+    case 4: return launch_small<4>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream, pdl);
+    case 5: return launch_small<5>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream, pdl);
+    case 6: return launch_small<6>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream, pdl);
+    case 7: return launch_small<7>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream, pdl);
+    case 8: return launch_small<8>(emb, B, D, thr, ref_ok, medoid, cos, vec, num_sms, stream, pdl);
     default: break;
   }
   int grid = B < num_sms * 4 ? B : num_sms * 4;  // four resident CTAs per SM (51 KB each)
-  if (vec) qc_sim_large_kernel<true><<<grid, kSimThreads, kSimLargeSmem, stream>>>(emb, B, N, D, thr, ref_ok, medoid, cos);
-  else qc_sim_large_kernel<false><<<grid, kSimThreads, kSimLargeSmem, stream>>>(emb, B, N, D, thr, ref_ok, medoid, cos);
-  return cudaGetLastError();
+  if (vec) return launch_kernel(qc_sim_large_kernel<true>, dim3(grid), dim3(kSimThreads), kSimLargeSmem, stream, pdl, emb, B, N, D, thr, ref_ok, medoid, cos);
+  return launch_kernel(qc_sim_large_kernel<false>, dim3(grid), dim3(kSimThreads), kSimLargeSmem, stream, pdl, emb, B, N, D, thr, ref_ok, medoid, cos);
 }
 
 // ------------------------------------------------------------------------------------------

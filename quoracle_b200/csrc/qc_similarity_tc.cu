@@ -123,7 +123,11 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&raw_full[s], 1);
       mbar_init(&lo_full[s], 4);                  // one arrival per warp of the owning splitter group
-      mbar_init(&stage_empty[s], 1);              // tcgen05.commit
+      // tcgen05.commit of the MMAs that read the stage + one arrival per warp of every splitter group that does NOT own
+      // the chunk, made after that warp has observed the chunk's raw_full phase: the producer cannot re-arm raw_full[s]
+      // for chunk c + kStages before every waiter has seen chunk c's phase, so no waiter can ever find the barrier two
+      // phases ahead of it (a parity wait cannot tell phase k from k - 2).
+      mbar_init(&stage_empty[s], 1 + 4 * (kSplitGroups - 1));
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
@@ -137,6 +141,8 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();                      // K2's rows; the setup above may have run under the previous kernel's tail
+  griddep_launch_dependents();
 
   if (warp < 4) {
     // ===================== epilogue =========================================================
@@ -275,9 +281,14 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
         // phase k from phase k - 2, so a group that skipped the chunks of the other groups could ask for phase k of a
         // stage whose phase k - 1 (another group's chunk, five chunks earlier) has not landed yet -- TMA completions
         // are not ordered -- and be let through on stale data.  Observing all phases keeps every waiter within one
-        // phase of the barrier; it cannot fall two behind either, because the ring stalls on its own chunks first.
+        // phase of the barrier; and it cannot fall two behind, because a non-owning warp's observation is itself one
+        // of the arrivals the producer needs (stage_empty) before it refills the stage.
         w_raw += mbar_wait_parked(&raw_full[s], (ci / kStages) & 1u, dbg, 710);
-        if (static_cast<int>(ci % kSplitGroups) != grp) continue;
+        if (static_cast<int>(ci % kSplitGroups) != grp) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&stage_empty[s]);        // "this warp has seen the phase" (see stage_empty's init)
+          continue;
+        }
         const float4* src = reinterpret_cast<const float4*>(stages + s * 2 * kChunkBytes);
         float4* dl = reinterpret_cast<float4*>(stages + s * 2 * kChunkBytes + kChunkBytes);
         // 1024 16-byte pieces, consecutive per warp; all loads first so their latencies overlap
@@ -371,14 +382,14 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
 template <int kStages, int kWin, int kTail>
 static cudaError_t launch_tc(const CUtensorMap* x_tmap, int B, int N, int D, const float* thr, int32_t* ref_ok,
                              int32_t* medoid, float* cos, int32_t* dbg, unsigned long long* stall, int num_sms,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, bool pdl) {
   constexpr int smem = tc_smem_bytes(kStages, kWin, kTail);
   static_assert(smem <= 232448, "tcgen05 K3: shared-memory carve-up exceeds the 227 KB opt-in limit");
   const int q = 128 / N;
   const int ntiles = (B + q - 1) / q;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  qc_sim_tc_kernel<kStages, kWin, kTail><<<grid, kTcThreads, smem, stream>>>(*x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall);
-  return cudaGetLastError();
+  return launch_kernel(qc_sim_tc_kernel<kStages, kWin, kTail>, dim3(grid), dim3(kTcThreads), smem, stream, pdl, *x_tmap, B, N, D, thr,
+                       ref_ok, medoid, cos, dbg, stall);
 }
 
 // Shared-memory opt-in of the three instantiations on the current device (called by qc_ctx_create).
@@ -392,10 +403,10 @@ cudaError_t similarity_tc_prepare_device() {
 
 cudaError_t launch_similarity_tc(const CUtensorMap* x_tmap, int B, int N, int D, const float* thr, int32_t* ref_ok,
                                  int32_t* medoid, float* cos, int32_t* dbg, unsigned long long* stall, int num_sms,
-                                 cudaStream_t stream) {
-  if (N <= 32) return launch_tc<5, 33, 7>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream);
-  if (N <= 48) return launch_tc<5, 49, 7>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream);
-  return launch_tc<5, 65, 0>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream);
+                                 cudaStream_t stream, bool pdl) {
+  if (N <= 32) return launch_tc<5, 33, 7>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream, pdl);
+  if (N <= 48) return launch_tc<5, 49, 7>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream, pdl);
+  return launch_tc<5, 65, 0>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream, pdl);
 }
 
 }  // namespace qc

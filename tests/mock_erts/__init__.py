@@ -50,6 +50,8 @@ class BadArg(Exception):
 
 
 class MockVM:
+    _loaded = False
+
     def __init__(self):
         self.lib = ctypes.CDLL(str(build()))
         L, vp, sz = self.lib, ctypes.c_void_p, ctypes.c_size_t
@@ -83,8 +85,12 @@ class MockVM:
         L.mock_func_name.argtypes = [ctypes.c_int]
         L.mock_func_arity.argtypes = [ctypes.c_int]
         L.mock_func_flags.argtypes = [ctypes.c_int]
-        if L.mock_load() != 0:
-            raise RuntimeError("NIF on_load failed")
+        # on_load runs once per loaded library, as in a VM (a second run would re-open the resource types and orphan every
+        # live resource); every MockVM of the process shares the one loaded library
+        if not MockVM._loaded:
+            if L.mock_load() != 0:
+                raise RuntimeError("NIF on_load failed")
+            MockVM._loaded = True
         self.heap = L.mock_env_new()          # where resource terms the test holds on to live
 
     # -- module table --------------------------------------------------------------------------------
