@@ -45,10 +45,19 @@ struct EncTraits {
   static constexpr int WBK = WBK_;                // k elements per streamed W stage
   static constexpr int GM = GM_;                  // gather mode: 0 = cp.async (LDGSTS), 1 = TMA gather4
   static constexpr int BK = 64;                   // bf16 elements per 128-byte swizzle row (token tiles)
-  static constexpr int KB = D / BK;               // resident token k-blocks
+  // K split: when a token block does not fit next to a W ring (dim 1536 with more than 64 tokens per CTA) the
+  // block's rows are held one K HALF at a time and re-gathered for every group of FG feature tiles, whose FG
+  // accumulators (all of TMEM) stay live across the halves.  Twice the tokens per streamed W byte: the kernel is
+  // bound by bytes delivered INTO the SM per flop, and W is two thirds of them.
+  static constexpr int KS = (D * TB * 2 > 196608) ? 2 : 1;   // K parts held in turn
+  static constexpr int KB = D / BK / KS;          // resident token k-blocks (of the current K part)
   static constexpr int NWS = D / WBK;             // W stages per feature tile
+  static constexpr int NWSK = NWS / KS;           // ... per feature tile and K part
   static constexpr int MT = 128 * CG;             // features per MMA tile over the CTA group
   static constexpr int NFT = D / MT;              // feature tiles
+  static constexpr int FG = KS > 1 ? 2 : 1;       // feature tiles accumulating side by side (one TMEM stage each)
+  static constexpr int NG = NFT / FG;             // groups of them per token block
+  static constexpr int NTP = KS > 1 ? NG * KS : 1;   // token passes (gathers of the resident rows) per token block
   static constexpr int UMMA_N = TB * CG;          // tokens per MMA tile
   static constexpr int TOK_KB_BYTES = TB * 128;
   static constexpr int TOK_BYTES = KB * TOK_KB_BYTES;
@@ -66,6 +75,8 @@ struct EncTraits {
   static constexpr int GATHER_LANES = TB > 128 ? 16 : 8;      // gather4 issuing lanes per gather warp (4 rows each)
   static_assert(MC == 1 || (CG == 2 && (MC == 2 || MC == 4)), "W multicast needs CTA pairs; cluster of 4 or 8");
   static_assert(4 * GATHER_LANES * 4 >= TB, "gather lanes must cover the token block");
+  static_assert(KS == 1 || (GM == 1 && WBK == 64 && NFT % 2 == 0 && D % (BK * KS) == 0),
+                "the K-split walk needs TMA gather, 64-wide W stages and an even number of feature tiles");
   static_assert(WBK == 64 || WBK == 32, "W stage width is 64 (SW128) or 32 (SW64)");
   static_assert(D % MT == 0, "feature tiles must cover D");
   static_assert(D % BK == 0, "k-blocks must cover D");
@@ -372,19 +383,24 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
           }
           rid[q] = id >= 0 ? id : vocab;          // out-of-range row -> TMA zero fill
         }
-        const uint32_t par_empty = (it & 1u) ^ 1u;
+        // one pass per token block, or (K split) one per feature-tile group and K part: the same rows, the columns
+        // of K part tp % KS
 #pragma unroll 1
-        for (int kb = 0; kb < KB; ++kb) {
-          if (lane == 0) {
-            st_wait += mbar_wait(&tok_empty[kb], par_empty, dbg, 200 + kb);
-            if (warp == 4 && leader) mbar_expect_tx(&tok_full[kb], CG * Tr::TOK_KB_BYTES);
+        for (int tp = 0; tp < Tr::NTP; ++tp, ++it) {
+          const uint32_t par_empty = (it & 1u) ^ 1u;
+          const int col0 = (tp % Tr::KS) * KB * 64;
+#pragma unroll 1
+          for (int kb = 0; kb < KB; ++kb) {
+            if (lane == 0) {
+              st_wait += mbar_wait(&tok_empty[kb], par_empty, dbg, 200 + kb);
+              if (warp == 4 && leader) mbar_expect_tx(&tok_full[kb], CG * Tr::TOK_KB_BYTES);
+            }
+            __syncwarp();
+            if (active)
+              tma_gather4<CG>(tok_base + kb * Tr::TOK_KB_BYTES + rg * 512, &e_tmap, &tok_full[kb], col0 + kb * 64, rid[0],
+                              rid[1], rid[2], rid[3], lcta);
           }
-          __syncwarp();
-          if (active)
-            tma_gather4<CG>(tok_base + kb * Tr::TOK_KB_BYTES + rg * 512, &e_tmap, &tok_full[kb], kb * 64, rid[0], rid[1],
-                            rid[2], rid[3], lcta);
         }
-        ++it;
       }
       if (stall != nullptr && threadIdx.x == 128) {
         stall[blockIdx.x * 16 + 6] = static_cast<unsigned long long>(clock64() - st_t0);
@@ -500,8 +516,14 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
       // transaction count goes transiently negative, which is legal, and the phase cannot complete without the arm.
       for (int citem = cl; citem < ncitems && (pair == 0 || leader); citem += ncl) {
         if (!__any_sync(0xffffffffu, item_any(citem))) continue;
-        for (int ft = 0; ft < NFT; ++ft) {
-          for (int ws = 0; ws < NWS; ++ws, ++wi) {
+        // tile order = the MMA issuer's: groups of FG feature tiles; per group the K parts; per K part the FG tiles
+        // (without a K split: feature tile after feature tile)
+        for (int g = 0; g < Tr::NG; ++g)
+        for (int kh = 0; kh < Tr::KS; ++kh)
+        for (int f = 0; f < Tr::FG; ++f) {
+          const int ft = g * Tr::FG + f;
+          for (int wsl = 0; wsl < Tr::NWSK; ++wsl, ++wi) {
+            const int ws = kh * Tr::NWSK + wsl;                   // k position of the tile inside the feature tile
             const uint32_t s = wi % WS;
             const uint32_t ph = (wi / WS) & 1u;
             st_wait += mbar_wait(&w_empty[s], ph ^ 1u, dbg, 300 + static_cast<int>(s));
@@ -547,16 +569,29 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
       const long long st_t0 = clock64();
       for (int citem = cl; citem < ncitems; citem += ncl) {
         if (!__any_sync(0xffffffffu, item_any(citem))) continue;
-        for (int ft = 0; ft < NFT; ++ft, ++acc_iter) {
-          const uint32_t as = acc_iter & 1u;
-          if constexpr (CG == 2) st_acc += mbar_wait_cluster(&acc_empty[as], ((acc_iter >> 1) & 1u) ^ 1u, dbg, 400 + ft);
-          else st_acc += mbar_wait(&acc_empty[as], ((acc_iter >> 1) & 1u) ^ 1u, dbg, 400 + ft);
-          tcgen05_fence_after();
+        // Walk: groups of FG feature tiles; per group the K parts; per K part the FG tiles of the group, each into its
+        // own accumulator stage (accumulating across the K parts).  Without a K split FG = KS = 1 and this is "feature
+        // tile after feature tile over resident tokens".  With it, accumulator f of a group is complete after the LAST
+        // K part's f-th tile, i.e. the epilogue of tile 0 runs under the MMAs of tile 1's last part, and the epilogue
+        // of tile 1 under the next group's first tile: the two TMEM stages still overlap MMA and epilogue.
+        for (int g = 0; g < Tr::NG; ++g, acc_iter += Tr::FG)
+        for (int kh = 0; kh < Tr::KS; ++kh, it += (Tr::KS > 1 ? 1u : 0u))
+        for (int f = 0; f < Tr::FG; ++f) {
+          const int ft = g * Tr::FG + f;
+          const uint32_t ai = acc_iter + static_cast<uint32_t>(f);
+          const uint32_t as = ai & 1u;
+          if (kh == 0) {                                          // first MMAs into this accumulator: it must be drained
+            if constexpr (CG == 2) st_acc += mbar_wait_cluster(&acc_empty[as], ((ai >> 1) & 1u) ^ 1u, dbg, 400 + ft);
+            else st_acc += mbar_wait(&acc_empty[as], ((ai >> 1) & 1u) ^ 1u, dbg, 400 + ft);
+            tcgen05_fence_after();
+          }
           const uint32_t tmem_d = tmem_u + as * ACC_COLS;
-          for (int ws = 0; ws < NWS; ++ws, ++wi) {
-            const int kb = ws / WPK;                              // token k-block this W stage multiplies
+          const bool tok_first = Tr::KS > 1 ? (f == 0) : (g == 0);             // first / last use of the resident rows
+          const bool tok_last = Tr::KS > 1 ? (f == Tr::FG - 1) : (g == Tr::NG - 1);
+          for (int ws = 0; ws < Tr::NWSK; ++ws, ++wi) {
+            const int kb = ws / WPK;                              // resident token k-block this W stage multiplies
             const int sub = ws % WPK;                             // which WBK-wide part of it
-            if (ft == 0 && sub == 0) {
+            if (tok_first && sub == 0) {
               if constexpr (CG == 2) st_tok += mbar_wait_cluster(&tok_full[kb], it & 1u, dbg, 500 + kb);
               else st_tok += mbar_wait(&tok_full[kb], it & 1u, dbg, 500 + kb);
             }
@@ -571,18 +606,18 @@ qc_encode_kernel(const __grid_constant__ CUtensorMap w_tmap,          // W^T [D 
 #pragma unroll
               for (int k = 0; k < WBK / 16; ++k) {
                 // +32 bytes per 16-element k step inside the swizzle row (descriptor units of 16 B => +2)
-                umma_bf16<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ws | k) != 0 ? 1u : 0u);
+                umma_bf16<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kh | ws | k) != 0 ? 1u : 0u);
               }
               // W stage reusable once these MMAs retire: the arrival goes to the loading CTAs (cluster ranks 0 and 1)
               // and to this pair's own leader, which arms the next phase (with MC == 1 all of that is this pair)
               umma_commit<CG>(&w_empty[s], MC > 1 ? uint16_t(0x3u | (1u << lcta)) : pair_mask);
-              if (ft == NFT - 1 && sub == WPK - 1) umma_commit<CG>(&tok_empty[kb], pair_mask);   // token k-block free
-              if (ws == NWS - 1) umma_commit<CG>(&acc_full[as], pair_mask);
+              if (tok_last && sub == WPK - 1) umma_commit<CG>(&tok_empty[kb], pair_mask);   // token k-block free
+              if (kh == Tr::KS - 1 && ws == Tr::NWSK - 1) umma_commit<CG>(&acc_full[as], pair_mask);
             }
             __syncwarp();
           }
         }
-        ++it;
+        if constexpr (Tr::KS == 1) ++it;
       }
       if (stall != nullptr && lane == 0) {
         stall[blockIdx.x * 16 + 0] = static_cast<unsigned long long>(clock64() - st_t0);
@@ -664,7 +699,8 @@ static cudaError_t launch_encode_t(const EncoderLaunch& a) {
   X(1536, 64, 1, 64, 0, 1)  X(1536, 64, 2, 64, 0, 1)  X(1536, 48, 2, 64, 0, 1)                                  \
   X(1536, 64, 1, 64, 1, 1)  X(1536, 64, 2, 64, 1, 1)  X(1536, 56, 2, 64, 1, 1)  X(1536, 48, 2, 64, 1, 1)         \
   X(1536, 64, 2, 64, 1, 2)  X(1536, 56, 2, 64, 1, 2)  X(1536, 48, 2, 64, 1, 2)                                  \
-  X(1536, 64, 2, 64, 1, 4)  X(1536, 56, 2, 64, 1, 4)
+  X(1536, 64, 2, 64, 1, 4)  X(1536, 56, 2, 64, 1, 4)                                                          \
+  X(1536, 128, 2, 64, 1, 1)  X(1536, 112, 2, 64, 1, 1)  X(1536, 96, 2, 64, 1, 1)
 
 #define QC_MATCH(D, TB, CG, WBK, GM, MC) \
   (dim == D && v.token_block == TB && v.cta_group == CG && v.w_bk == WBK && v.gather == GM && (v.mcast < 1 ? 1 : v.mcast) == MC)

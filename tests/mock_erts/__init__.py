@@ -126,8 +126,11 @@ class MockVM:
         if k == K_ATOM:
             name = self.lib.mock_atom_name(t).decode()
             return None if name == "nil" else Atom(name)
-        if k == K_INT or k == K_U64:
+        if k == K_U64:
             return int(self.lib.mock_get_uint64(t))
+        if k == K_INT:
+            v = int(self.lib.mock_get_uint64(t))               # two's complement of the signed value
+            return v - (1 << 64) if v >= (1 << 63) else v
         if k == K_BIN:
             n = self.lib.mock_binary_size(t)
             return ctypes.string_at(self.lib.mock_binary_data(t), n) if n else b""

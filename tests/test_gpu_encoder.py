@@ -35,7 +35,8 @@ VARIANTS = {384: [(128, 1, 64, 0), (128, 1, 32, 0), (128, 1, 64, 1), (256, 1, 64
                   (96, 2, 64, 0), (128, 1, 64, 1), (128, 2, 64, 1), (128, 2, 32, 1), (112, 2, 64, 1), (104, 2, 64, 1), (96, 2, 64, 1),
                   (128, 2, 64, 1, 2), (112, 2, 64, 1, 2), (104, 2, 64, 1, 2), (128, 2, 64, 1, 4)],
             1536: [(64, 1, 64, 0), (64, 2, 64, 0), (48, 2, 64, 0), (64, 1, 64, 1), (64, 2, 64, 1), (56, 2, 64, 1),
-                   (48, 2, 64, 1), (64, 2, 64, 1, 2), (56, 2, 64, 1, 2), (48, 2, 64, 1, 2), (64, 2, 64, 1, 4), (56, 2, 64, 1, 4)]}
+                   (48, 2, 64, 1), (64, 2, 64, 1, 2), (56, 2, 64, 1, 2), (48, 2, 64, 1, 2), (64, 2, 64, 1, 4), (56, 2, 64, 1, 4),
+                   (128, 2, 64, 1), (112, 2, 64, 1), (96, 2, 64, 1)]}      # the last three: K-split walk (rows held one K half at a time)
 
 
 @pytest.mark.parametrize("dim", [384, 768, 1536])

@@ -26,8 +26,8 @@ def main():
                     (128, 2, 64, 1, 2), (112, 2, 64, 1, 2), (104, 2, 64, 1, 2), (128, 2, 64, 1, 4)]
     elif args.dim == 1536:
         b, n, t = 32, 16, 2048
-        variants = [(64, 2, 64, 1), (56, 2, 64, 1), (48, 2, 64, 1), (64, 2, 64, 1, 2), (56, 2, 64, 1, 2),
-                    (48, 2, 64, 1, 2), (64, 2, 64, 1, 4), (56, 2, 64, 1, 4)]
+        variants = [(64, 2, 64, 1), (56, 2, 64, 1), (48, 2, 64, 1), (128, 2, 64, 1), (112, 2, 64, 1), (96, 2, 64, 1),
+                    (56, 2, 64, 1, 2), (56, 2, 64, 1, 4)]
     else:
         b, n, t = 512, 8, 512
         variants = [(128, 1, 64, 0), (128, 1, 64, 1), (256, 1, 64, 1)]
