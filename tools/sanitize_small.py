@@ -10,8 +10,9 @@ from quoracle_b200 import native, synth  # noqa: E402
 
 w = synth.make_encoder(768, vocab=2048, seed=1)
 with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
-    for variant in [(128, 2, 64, 1), (128, 1, 64, 0), (104, 2, 64, 1)]:
-        ctx.set_variant(*variant)
+    for variant in [(128, 2, 64, 1), (128, 1, 64, 0), (104, 2, 64, 1), (128, 2, 64, 1, 2), (128, 2, 64, 1, 4)]:
+        ctx.set_variant(*variant[:4])
+        ctx.set_multicast(variant[4] if len(variant) > 4 else 1)      # round 2: W-tile TMA multicast clusters of 4 / 8
         batch = synth.make_decisions(3, 8, 300, vocab=2048, seed=3, ragged=True)
         r = ctx.decide_batch(batch.token_ids, batch.lens, batch.thr, want_cos=True, want_emb=True)
         print(variant, r.ref_ok.tolist(), r.medoid.tolist(), float(np.abs(r.emb).sum()))
@@ -41,4 +42,18 @@ with native.Context(0, w.table_bf16, w.w_bf16) as ctx:            # 56-token blo
     ctx.set_packing(2)
     batch = synth.make_decisions(2, 4, 150, vocab=2048, seed=5, ragged=True)
     print("packed 1536", ctx.decide_batch(batch.token_ids, batch.lens, batch.thr).medoid.tolist())
+    ctx.set_packing(0)
+    for tb in (128, 96):                                            # round 2: K-split walk (rows held one K half at a time)
+        ctx.set_variant(tb, 2, 64, 1)
+        batch = synth.make_decisions(2, 4, 300, vocab=2048, seed=6, ragged=True)
+        print("k-split", tb, ctx.decide_batch(batch.token_ids, batch.lens, batch.thr).medoid.tolist())
+w = synth.make_encoder(384, vocab=2048, seed=3)
+with native.Context(0, w.table_bf16, w.w_bf16) as ctx:            # round 2: 256-token tile (the dim-384 default)
+    batch = synth.make_decisions(3, 5, 300, vocab=2048, seed=7, ragged=True)
+    print("384/256", ctx.decide_batch(batch.token_ids, batch.lens, batch.thr).medoid.tolist())
+    cache = ctx.lesson_cache(16, 384)
+    rows = np.random.default_rng(0).standard_normal((6, 384)).astype(np.float32)
+    cache.append(rows)
+    cache.gather([4, 2, 0])
+    print("lesson cache", cache.match(rows[2], 0.99))
 print("sanitize run done")
