@@ -123,11 +123,14 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&raw_full[s], 1);
       mbar_init(&lo_full[s], 4);                  // one arrival per warp of the owning splitter group
-      // tcgen05.commit of the MMAs that read the stage + one arrival per warp of every splitter group that does NOT own
-      // the chunk, made after that warp has observed the chunk's raw_full phase: the producer cannot re-arm raw_full[s]
-      // for chunk c + kStages before every waiter has seen chunk c's phase, so no waiter can ever find the barrier two
-      // phases ahead of it (a parity wait cannot tell phase k from k - 2).
-      mbar_init(&stage_empty[s], 1 + 4 * (kSplitGroups - 1));
+      // tcgen05.commit of the MMAs that read the stage + one arrival per splitter warp (all groups), made after that
+      // warp has observed the chunk's raw_full phase -- and, for the owning group, after it has written the lo tile: the
+      // producer cannot re-arm raw_full[s] for chunk c + kStages before every waiter has seen chunk c's phase, so no
+      // waiter can ever find the barrier two phases ahead of it (a parity wait cannot tell phase k from k - 2).  The
+      // owners' arrivals add nothing to the protocol (the commit already orders the refill behind the MMAs that read
+      // their tile) but give compute-sanitizer's racecheck a thread-level edge from this lap's lo writes to the next
+      // lap's, which it cannot derive from tcgen05.commit / TMA completions.
+      mbar_init(&stage_empty[s], 1 + 4 * kSplitGroups);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
@@ -306,7 +309,10 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&lo_full[s]);
+        if (lane == 0) {
+          mbar_arrive(&lo_full[s]);
+          mbar_arrive(&stage_empty[s]);                         // see stage_empty's init
+        }
       }
     }
     if (stall != nullptr && threadIdx.x == 128) {
