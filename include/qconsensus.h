@@ -195,6 +195,20 @@ int qc_embed_batch_dev(qc_ctx* ctx, const int32_t* d_token_ids, const int32_t* d
 int qc_similarity_batch_dev(qc_ctx* ctx, const float* d_emb, int B, int N, int D, const float* d_thr,
                             int32_t* d_ref_ok, int32_t* d_medoid, float* d_cos, void* stream);
 
+/*
+ * CUDA graphs over the device entry points.  Between qc_capture_begin and qc_capture_end every `_dev` call made on
+ * `stream` (a non-default stream) is RECORDED instead of executed; qc_capture_end returns a graph that
+ * qc_graph_launch replays with one launch -- the whole inner loop of a caller whose batches are resident in HBM,
+ * with no host work (and no host jitter) between the kernels.  The same calls must have run once before the capture
+ * (workspaces are sized on first use and cannot grow while recording); per-kernel profiling must be off.  Pointers
+ * passed to the recorded calls are baked into the graph and must stay valid while it is replayed.
+ */
+typedef struct qc_graph qc_graph;
+int qc_capture_begin(qc_ctx* ctx, void* stream);
+int qc_capture_end(qc_ctx* ctx, void* stream, qc_graph** out);
+int qc_graph_launch(qc_graph* graph, void* stream);
+void qc_graph_destroy(qc_graph* graph);
+
 /* Introspection ---------------------------------------------------------------------- */
 
 const char* qc_strerror(int status);

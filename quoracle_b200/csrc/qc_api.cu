@@ -1605,6 +1605,64 @@ int qc_first_match_batch(qc_ctx* c, const float* query, const float* rows, int Q
   return QC_OK;
 }
 
+// ---- CUDA graphs over the device entry points -------------------------------------------------------------------
+// A caller whose batches are already in HBM (an inner loop of `_dev` calls on one stream) can record the loop once and
+// replay it with one launch: no host work, and therefore no host jitter, between the kernels.  Everything the `_dev`
+// entry points enqueue is capturable (kernel launches with their cluster / programmatic-dependency attributes); the
+// workspaces must already have their size, i.e. the same calls must have run once before the capture.
+struct qc_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int device = -1;
+};
+
+int qc_capture_begin(qc_ctx* c, void* stream) {
+  if (c == nullptr || stream == nullptr) return QC_ERR_INVALID_INPUT;       // the legacy default stream cannot be captured
+  DeviceGuard g(c->device);
+  if (c->profiling) return QC_ERR_UNSUPPORTED;                               // per-launch events are host-visible state
+  QC_CUDA(cudaStreamBeginCapture(static_cast<cudaStream_t>(stream), cudaStreamCaptureModeRelaxed));
+  return QC_OK;
+}
+
+int qc_capture_end(qc_ctx* c, void* stream, qc_graph** out) {
+  if (c == nullptr || stream == nullptr || out == nullptr) return QC_ERR_INVALID_INPUT;
+  *out = nullptr;
+  DeviceGuard g(c->device);
+  cudaGraph_t graph = nullptr;
+  QC_CUDA(cudaStreamEndCapture(static_cast<cudaStream_t>(stream), &graph));
+  qc_graph* q = new (std::nothrow) qc_graph();
+  if (q == nullptr) {
+    cudaGraphDestroy(graph);
+    return QC_ERR_OUT_OF_MEMORY;
+  }
+  q->graph = graph;
+  q->device = c->device;
+  cudaError_t e = cudaGraphInstantiate(&q->exec, graph, 0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cudaGraphDestroy(graph);
+    delete q;
+    return cuda_status(e);
+  }
+  *out = q;
+  return QC_OK;
+}
+
+int qc_graph_launch(qc_graph* q, void* stream) {
+  if (q == nullptr || q->exec == nullptr) return QC_ERR_INVALID_INPUT;
+  DeviceGuard g(q->device);
+  QC_CUDA(cudaGraphLaunch(q->exec, static_cast<cudaStream_t>(stream)));
+  return QC_OK;
+}
+
+void qc_graph_destroy(qc_graph* q) {
+  if (q == nullptr) return;
+  DeviceGuard g(q->device);
+  if (q->exec) cudaGraphExecDestroy(q->exec);
+  if (q->graph) cudaGraphDestroy(q->graph);
+  delete q;
+}
+
 // ---- device-resident lesson rows -----------------------------------------------------
 // LessonManager.find_similar_lesson/5 (reference lib/quoracle/agent/lesson_manager.ex:150-173) re-embeds every
 // existing lesson (<= 100) for every new one; qc_first_match_batch already batches the comparison but still takes

@@ -35,6 +35,7 @@ ABI_SYMBOLS = (
     "qc_launch_count", "qc_profile_enable", "qc_profile_reset", "qc_kernel_stats",
     "qc_encoder_info", "qc_encoder_set_cta_group", "qc_encoder_set_variant", "qc_encoder_stall_profile",
     "qc_similarity_set_path", "qc_encoder_set_multicast", "qc_encoder_multicast",
+    "qc_capture_begin", "qc_capture_end", "qc_graph_launch", "qc_graph_destroy",
     "qc_lesson_cache_create", "qc_lesson_cache_destroy", "qc_lesson_cache_count", "qc_lesson_cache_put",
     "qc_lesson_cache_gather", "qc_lesson_cache_match", "qc_encoder_token_block", "qc_encoder_hint_block_map", "qc_encoder_set_packing", "qc_debug_pack_plan",
     "qc_split_create", "qc_split_export", "qc_split_attach", "qc_decide_split_dev", "qc_split_gathered",
@@ -167,6 +168,14 @@ def load_library() -> ctypes.CDLL:
     lib.qc_encoder_set_multicast.argtypes = [vp, i32]
     lib.qc_encoder_multicast.restype = i32
     lib.qc_encoder_multicast.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
+    lib.qc_capture_begin.restype = i32
+    lib.qc_capture_begin.argtypes = [vp, vp]
+    lib.qc_capture_end.restype = i32
+    lib.qc_capture_end.argtypes = [vp, vp, ctypes.POINTER(vp)]
+    lib.qc_graph_launch.restype = i32
+    lib.qc_graph_launch.argtypes = [vp, vp]
+    lib.qc_graph_destroy.restype = None
+    lib.qc_graph_destroy.argtypes = [vp]
     lib.qc_lesson_cache_create.restype = i32
     lib.qc_lesson_cache_create.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
     lib.qc_lesson_cache_destroy.restype = None
@@ -408,6 +417,17 @@ class Context:
         _check(self._lib.qc_similarity_batch_dev(self._h, _dev(d_emb), b, n, d, _dev(d_thr), _dev(d_ref_ok),
                                                  _dev(d_medoid), _dev(d_cos), _dev(stream)))
 
+    def capture(self, stream, record) -> "Graph":
+        """Record the `_dev` calls `record()` makes on `stream` (a non-default stream handle) into a CUDA graph."""
+        _check(self._lib.qc_capture_begin(self._h, _dev(stream)))
+        try:
+            record()
+        finally:
+            h = ctypes.c_void_p()
+            st = self._lib.qc_capture_end(self._h, _dev(stream), ctypes.byref(h))
+        _check(st)
+        return Graph(self._lib, h)
+
     def lesson_cache(self, capacity: int = 128, dim: Optional[int] = None) -> "LessonCache":
         """Device-resident rows of one agent's lesson list (qc_lesson_cache_*); see LessonCache."""
         return LessonCache(self, capacity, dim or self.dim)
@@ -615,5 +635,26 @@ class LessonCache:
         try:
             if self._ctx._h:
                 self.close()
+        except Exception:
+            pass
+
+
+class Graph:
+    """A recorded loop of `_dev` calls (qc_capture_*): ``launch(stream)`` replays it with one launch."""
+
+    def __init__(self, lib, handle):
+        self._lib, self._h = lib, handle
+
+    def launch(self, stream) -> None:
+        _check(self._lib.qc_graph_launch(self._h, _dev(stream)))
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.qc_graph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass

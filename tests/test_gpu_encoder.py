@@ -589,3 +589,43 @@ def test_two_devices_in_one_process():
     (s0, d0), (s1, d1) = res
     assert all(np.array_equal(a, b) for a, b in zip(s0, s1))
     assert np.array_equal(d0.cos, d1.cos) and np.array_equal(d0.medoid, d1.medoid)
+
+
+def test_cuda_graph_over_the_device_entry_points():
+    """qc_capture_begin / _end / qc_graph_launch: a recorded loop of qc_decide_batch_dev calls (with their cluster and
+    programmatic-dependency launch attributes) replays to the same bits as the direct calls, repeatedly."""
+    import torch
+    dev = torch.device("cuda:0")
+    w = weights(768, vocab=8192)
+    batches = [synth.make_decisions(12, 8, 200, vocab=8192, seed=500 + i, ragged=(i == 1)) for i in range(3)]
+    with native.Context(0, w.table_bf16, w.w_bf16) as ctx:
+        d_tok = [torch.from_numpy(x.token_ids).to(dev) for x in batches]
+        d_len = [torch.from_numpy(x.lens).to(dev) for x in batches]
+        d_thr = [torch.from_numpy(x.thr).to(dev) for x in batches]
+        outs = [(torch.zeros(12, dtype=torch.int32, device=dev), torch.zeros(12, dtype=torch.int32, device=dev),
+                 torch.zeros((12, 8, 8), dtype=torch.float32, device=dev)) for _ in batches]
+        stream = torch.cuda.Stream(device=dev)
+        torch.cuda.synchronize()
+
+        def loop():
+            for k in range(3):
+                ctx.decide_batch_dev(d_tok[k].data_ptr(), d_len[k].data_ptr(), 12, 8, 200, d_thr[k].data_ptr(),
+                                     outs[k][0].data_ptr(), outs[k][1].data_ptr(), outs[k][2].data_ptr(), 0, stream.cuda_stream)
+
+        loop()                                              # sizes the workspaces; also the expected result
+        torch.cuda.synchronize()
+        want = [tuple(t.clone() for t in o) for o in outs]
+        graph = ctx.capture(stream.cuda_stream, loop)
+        for _ in range(3):
+            for o in outs:
+                for t in o:
+                    t.zero_()
+            torch.cuda.synchronize()
+            graph.launch(stream.cuda_stream)
+            torch.cuda.synchronize()
+            for o, wv in zip(outs, want):
+                assert all(torch.equal(a, b) for a, b in zip(o, wv))
+        graph.close()
+        ctx.check_status()
+        host = ctx.decide_batch(batches[0].token_ids, batches[0].lens, batches[0].thr, want_cos=True)
+        assert np.array_equal(host.cos, want[0][2].cpu().numpy())
