@@ -123,14 +123,19 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&raw_full[s], 1);
       mbar_init(&lo_full[s], 4);                  // one arrival per warp of the owning splitter group
-      // tcgen05.commit of the MMAs that read the stage + one arrival per splitter warp (all groups), made after that
-      // warp has observed the chunk's raw_full phase -- and, for the owning group, after it has written the lo tile: the
-      // producer cannot re-arm raw_full[s] for chunk c + kStages before every waiter has seen chunk c's phase, so no
-      // waiter can ever find the barrier two phases ahead of it (a parity wait cannot tell phase k from k - 2).  The
-      // owners' arrivals add nothing to the protocol (the commit already orders the refill behind the MMAs that read
-      // their tile) but give compute-sanitizer's racecheck a thread-level edge from this lap's lo writes to the next
-      // lap's, which it cannot derive from tcgen05.commit / TMA completions.
-      mbar_init(&stage_empty[s], 1 + 4 * kSplitGroups);
+      // tcgen05.commit of the MMAs that read the stage + one arrival per warp of every splitter group that does NOT own
+      // the chunk, made after that warp has observed the chunk's raw_full phase: the producer cannot re-arm raw_full[s]
+      // for chunk c + kStages before every waiter has seen chunk c's phase, so no waiter can ever find the barrier two
+      // phases ahead of it (a parity wait cannot tell phase k from k - 2).  (The owning group needs no arrival of its
+      // own: its lo tile is read by the MMAs whose commit is the other arrival.)
+      //
+      // compute-sanitizer --tool racecheck reports the lo-tile stores below as write-after-write hazards between the
+      // two groups (with five stages and two groups, consecutive laps of a stage are written by different warps).
+      // The order between lap k's store and lap k + 1's is: store -> arrive(lo_full) -> MMA issue -> tcgen05.commit ->
+      // stage_empty -> TMA refill -> raw_full -> the other group's wait -> store; the tool follows thread arrivals but
+      // not tcgen05.commit / TMA completions, so it cannot see the chain (an experiment that added thread arrivals of
+      // the owners to stage_empty did not change its report; profiles/sanitizer_r2.md).
+      mbar_init(&stage_empty[s], 1 + 4 * (kSplitGroups - 1));
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
@@ -309,10 +314,7 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&lo_full[s]);
-          mbar_arrive(&stage_empty[s]);                         // see stage_empty's init
-        }
+        if (lane == 0) mbar_arrive(&lo_full[s]);
       }
     }
     if (stall != nullptr && threadIdx.x == 128) {

@@ -93,3 +93,54 @@ def test_wait_rule_total_and_typed(values):
     ws = [result.wait_score(x) for x in values]
     assert all(len(w) == 2 and w[0] in (0, 1) for w in ws)
     assert math.isfinite(sum(w[1] for w in ws))
+
+
+# ---- the round loop / decide step restatement (oracle/consensus_driver.py) against facts the reference's tests hold ----
+def _orient(text="Processing"):
+    return {"action": "orient", "params": {"current_situation": text, "goal_clarity": "Clear",
+                                           "available_resources": "Available", "key_challenges": "None",
+                                           "delegation_consideration": "none"}, "reasoning": "Reconsidering"}
+
+
+def test_driver_facts_held_by_the_reference_tests():
+    from oracle import consensus_driver as drv
+    state = {"agent_id": "a", "model_histories": {"model-a": [], "model-b": []}}
+
+    def agree(st, pool, opts):
+        return ("ok", [_orient() for _ in pool], dict(st, seen_round=opts.get("round", 1)))
+
+    # test/quoracle/agent/consensus_per_model_test.exs:294 -- no per-model histories -> {:error, :missing_model_histories}
+    assert drv.get_consensus_with_state({"agent_id": "a"}, {}, agree) == ("error", "missing_model_histories")
+    # test/quoracle/agent/consensus_refinement_context_test.exs:88-101 -- a pool whose members return the same valid
+    # orient answer completes: result type in [:consensus, :forced_decision], action not nil, state handed back
+    r = drv.get_consensus_with_state(state, {}, agree)
+    assert r[0] == "ok" and r[1][0] == "consensus" and r[1][1]["action"] == "orient" and r[1][2]["per_model_queries"] is True
+    assert r[2]["seen_round"] == 1
+    # test/quoracle/agent/consensus_test.exs:177-193 -- no majority through every refinement round -> :forced_decision
+    # with confidence <= 0.5
+    calls = []
+
+    def never(st, pool, opts):
+        calls.append(opts.get("round", 1))
+        # two different ACTIONS (different fingerprints; rewording a semantic parameter would still cluster together)
+        return ("ok", [_orient(), {"action": "send_message", "params": {"to": "parent", "content": "status"},
+                                   "reasoning": "r"}][:len(pool)], st)
+
+    r = drv.get_consensus_with_state(state, {}, never)
+    assert r[0] == "ok" and r[1][0] == "forced_decision" and r[1][2]["confidence"] <= 0.5
+    assert calls == [1, 2, 3, 4, 5]                       # default max_refinement_rounds = 4 (consensus.ex:90): rounds 1..5
+    # test/quoracle/agent/consensus_test.exs:150-163 -- every model failing is {:error, :all_models_failed}
+    assert drv.get_consensus_with_state(state, {}, lambda st, pool, o: ("ok", [None, None], st)) == ("error", "all_models_failed")
+    # answers that do not validate: {:error, :all_responses_invalid} (consensus.ex:132-134)
+    assert drv.get_consensus_with_state(state, {}, agree, validate_fn=lambda r_: None) == ("error", "all_responses_invalid")
+    # lib/quoracle/agent/message_handler.ex:353-354 -- at most three attempts for the two retryable errors
+    attempts = []
+
+    def failing(st):
+        attempts.append(st.get("consensus_retry_count", 0))
+        return ("error", "all_models_failed", None)
+
+    st, out = drv.run_consensus_cycle(state, failing, lambda s, a: s)
+    assert attempts == [0, 1, 2] and out == ("stalled", "all_models_failed", 3) and st["correction_feedback"] == {}
+    st, out = drv.run_consensus_cycle(state, lambda s: ("error", "rate_limit_exceeded", None), lambda s, a: s)
+    assert out == ("failed", "rate_limit_exceeded")
