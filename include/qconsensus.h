@@ -200,8 +200,10 @@ int qc_similarity_batch_dev(qc_ctx* ctx, const float* d_emb, int B, int N, int D
  * `stream` (a non-default stream) is RECORDED instead of executed; qc_capture_end returns a graph that
  * qc_graph_launch replays with one launch -- the whole inner loop of a caller whose batches are resident in HBM,
  * with no host work (and no host jitter) between the kernels.  The same calls must have run once before the capture
- * (workspaces are sized on first use and cannot grow while recording); per-kernel profiling must be off.  Pointers
- * passed to the recorded calls are baked into the graph and must stay valid while it is replayed.
+ * (workspaces are sized on first use and cannot grow while recording).  With qc_profile_enable on, the per-kernel
+ * event brackets are recorded INTO the graph as event-record nodes: replay the graph once, then qc_kernel_stats returns
+ * device-side durations with no host time inside any bracket.  Pointers passed to the recorded calls are baked into
+ * the graph and must stay valid while it is replayed.
  */
 typedef struct qc_graph qc_graph;
 int qc_capture_begin(qc_ctx* ctx, void* stream);

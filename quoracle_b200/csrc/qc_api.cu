@@ -201,14 +201,24 @@ struct KernelScope {
       r.kernel = k;
       r.start = get_event(c);
       r.stop = get_event(c);
-      cudaEventRecord(r.start, s);
+      record(r.start);
     }
   }
   ~KernelScope() {
     if (c->profiling) {
-      cudaEventRecord(r.stop, s);
+      record(r.stop);
       c->recs.push_back(r);
     }
+  }
+  // While the stream is being captured (qc_capture_begin) the bracket becomes a pair of event-record NODES of the graph
+  // (cudaEventRecordExternal): the durations are then taken on the device during a replay, with no host time between
+  // the record and the launch it brackets.
+  void record(cudaEvent_t e) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st == cudaStreamCaptureStatusActive)
+      cudaEventRecordWithFlags(e, s, cudaEventRecordExternal);
+    else
+      cudaEventRecord(e, s);
   }
 };
 
@@ -1619,7 +1629,6 @@ struct qc_graph {
 int qc_capture_begin(qc_ctx* c, void* stream) {
   if (c == nullptr || stream == nullptr) return QC_ERR_INVALID_INPUT;       // the legacy default stream cannot be captured
   DeviceGuard g(c->device);
-  if (c->profiling) return QC_ERR_UNSUPPORTED;                               // per-launch events are host-visible state
   QC_CUDA(cudaStreamBeginCapture(static_cast<cudaStream_t>(stream), cudaStreamCaptureModeRelaxed));
   return QC_OK;
 }

@@ -629,3 +629,16 @@ def test_cuda_graph_over_the_device_entry_points():
         ctx.check_status()
         host = ctx.decide_batch(batches[0].token_ids, batches[0].lens, batches[0].thr, want_cos=True)
         assert np.array_equal(host.cos, want[0][2].cpu().numpy())
+        # per-kernel profiling inside a graph: the event brackets become event-record nodes, durations come from a replay
+        ctx.profile_reset()
+        ctx.profile_enable(True)
+        graph = ctx.capture(stream.cuda_stream, loop)
+        graph.launch(stream.cuda_stream)
+        torch.cuda.synchronize()
+        stats = ctx.kernel_stats()
+        ctx.profile_enable(False)
+        graph.close()
+        assert stats["encode"]["launches"] == 3 and stats["finalize"]["launches"] == 3 and stats["similarity"]["launches"] == 3
+        assert 0.0 < stats["encode"]["ms"] < 50.0 and stats["encode"]["ms"] > stats["similarity"]["ms"]
+        for o, wv in zip(outs, want):
+            assert all(torch.equal(a, b) for a, b in zip(o, wv))

@@ -1,5 +1,5 @@
-"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: verdict gathering and the split-pool
-all-gather path.  The similarity function is injected (the oracle here, K3 on GPUs)."""
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: verdict gathering, the split-pool all-gather path and the
+consensus round loop over a tree sharded by agent.  The similarity function is injected (the oracle here, K3 on GPUs)."""
 import os
 import socket
 import sys
@@ -49,6 +49,35 @@ def _worker(rank, world, port, out_dir):
     (ok2, med2), full = sharding.decide_split_pool(local, thr, sim)
     assert full.shape == (b, n, d) and np.array_equal(full.numpy(), emb)
     assert np.array_equal(ok2, ref_ok) and np.array_equal(med2, ref_med)
+    # 3. the consensus round loop over an agent tree sharded by rank (depth-first blocks: a subtree stays on one
+    #    device): every rank sweeps its own agents (no collective), the union of the results is what one rank computes
+    import pickle
+    from quoracle_b200 import consensus_driver
+    from quoracle_b200.collector import DecisionCollector
+    from tests.test_host_logic import _tree_agents, _validate, make_emb, scripted_query_fn
+    agents = _tree_agents(3, 4)                                   # 4 + 16 + 64 agents
+    pool = {a["agent_id"]: len(a["state"]["model_histories"]) for a in agents}
+    qf = scripted_query_fn(21, lambda i: pool[i])
+    lo, hi = sharding.shard_range(len(agents), rank, world)
+    e1, _ = make_emb()
+    mine = consensus_driver.run_consensus_rounds(DecisionCollector(e1), agents[lo:hi], qf, _validate)
+    mine.pop("__sweeps__")
+    gathered = [None] * world
+    dist.all_gather_object(gathered, pickle.dumps(mine))
+    union = {}
+    for blob in gathered:
+        union.update(pickle.loads(blob))
+    e2, _ = make_emb()
+    whole = consensus_driver.run_consensus_rounds(DecisionCollector(e2), agents, qf, _validate)
+    whole.pop("__sweeps__")
+    assert set(union) == set(whole) and len(union) == 84
+    for k, v in whole.items():
+        u = union[k]
+        assert u[0] == v[0]
+        if v[0] == "ok":
+            assert u[1]["kind"] == v[1]["kind"] and u[1]["action"] == v[1]["action"] and u[1]["confidence"] == v[1]["confidence"]
+        else:
+            assert u[1] == v[1]
     Path(out_dir, f"ok{rank}").write_text("ok")
     dist.destroy_process_group()
 
