@@ -443,9 +443,11 @@ class DecideLeg:
                 "k1_ms_source": "CUDA events around each K1 launch" if k1_used == k1_ms else
                                 "bounded by ms_per_step: the event-bracketed K1 is longer than the whole pipelined step "
                                 "(events expose launch latency the graph / PDL step hides)",
-                "k1_share_of_step": k1_ms / pass_ms if pass_ms else None,
-                "k1_share_note": "K1 events / step time of the SAME event-bracketed pass (like for like); the timed "
-                                 "region itself carries no events and is a CUDA-graph replay",
+                "k1_share_of_step": k1_used / step_ms if step_ms else None,
+                "k1_share_note": "k1_ms_used / ms_per_step of the timed region (a CUDA-graph replay without events); "
+                                 "inside the event-bracketed pass itself, whose event nodes break the programmatic "
+                                 "launch overlap, the share is k1_share_in_event_pass",
+                "k1_share_in_event_pass": k1_ms / pass_ms if pass_ms else None,
                 "k1_pass_ms_per_step": pass_ms,
                 "k1_timing": "CUDA events around every K1 launch on the launching stream, in a separate pass of the "
                              "same steps right after the timed region: " + getattr(self, "k1_pass", "host loop"),

@@ -117,6 +117,11 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
   const int q = 128 / N;                                      // whole decisions per tile
   const int ntiles = (B + q - 1) / q;
   const int nchunks = (D + 31) / 32;
+  // Live rows: a tile holds q * N <= 128 rows of data.  The lo tile is placed right behind them (rounded up to the
+  // 8-row swizzle atom, which keeps it 1024-byte aligned) and the stacked B operand is sized to what is there:
+  // UMMA N = 2 * L8 instead of 256.  Pools that do not divide 128 (48: 96 rows, 24 / 40: 120) then cost neither the
+  // MMA cycles nor the operand reads nor the splitter traffic of the rows they do not have.
+  const int L8 = (q * N + 7) & ~7;
 
   if (warp == 4 + kSplitWarps && lane == 0) {
     tma_prefetch_desc(&x_tmap);
@@ -182,7 +187,7 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
         for (int c0 = 0; c0 < 128; c0 += 32) {
           if (c0 + 32 <= col_lo || c0 >= col_hi) continue;
           uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + as * 256 + half * 128 + c0, v);
+          tmem_ld_32x32b_x32(tmem_base + lane_addr + as * 256 + half * L8 + c0, v);
           tmem_ld_wait();
           if (row_live) {
 #pragma unroll
@@ -298,19 +303,23 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
           continue;
         }
         const float4* src = reinterpret_cast<const float4*>(stages + s * 2 * kChunkBytes);
-        float4* dl = reinterpret_cast<float4*>(stages + s * 2 * kChunkBytes + kChunkBytes);
-        // 1024 16-byte pieces, consecutive per warp; all loads first so their latencies overlap
+        float4* dl = reinterpret_cast<float4*>(stages + s * 2 * kChunkBytes + L8 * 128);   // lo tile behind the live rows
+        // L8 * 8 16-byte pieces (1024 for a full tile), consecutive per warp; all loads first so their latencies overlap
+        const int npieces = L8 * 8;
         float4 x[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) x[it] = src[it * 128 + p];
+        for (int it = 0; it < 8; ++it)
+          if (it * 128 + p < npieces) x[it] = src[it * 128 + p];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           // the tensor core reads the raw tile as TF32 by ignoring the 13 low mantissa bits; lo is the exact
           // fp32 remainder of that truncation (its own low bits are dropped the same way: 2^-20 relative)
-          float4 l;
-          l.x = x[it].x - tf32_trunc(x[it].x); l.y = x[it].y - tf32_trunc(x[it].y);
-          l.z = x[it].z - tf32_trunc(x[it].z); l.w = x[it].w - tf32_trunc(x[it].w);
-          dl[it * 128 + p] = l;
+          if (it * 128 + p < npieces) {
+            float4 l;
+            l.x = x[it].x - tf32_trunc(x[it].x); l.y = x[it].y - tf32_trunc(x[it].y);
+            l.z = x[it].z - tf32_trunc(x[it].z); l.w = x[it].w - tf32_trunc(x[it].w);
+            dl[it * 128 + p] = l;
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -344,7 +353,7 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
     }
   } else {
     // ===================== MMA issuer ==========================================================
-    constexpr uint32_t idesc = make_idesc_tf32(128, 256);   // B = [hi; lo] stacked: D = [HH | HL]
+    const uint32_t idesc = make_idesc_tf32(128, 2u * static_cast<uint32_t>(L8));   // B = [hi; lo] stacked: D = [HH | HL]
     const uint32_t st_base = smem_u32(stages);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     uint32_t ci = 0, acc_iter = 0;
@@ -354,12 +363,12 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
       const uint32_t as = acc_iter & 1u;
       w_acc += mbar_wait_parked(&acc_empty[as], ((acc_iter >> 1) & 1u) ^ 1u, dbg, 730);
       tcgen05_fence_after();
-      const uint32_t d_acc = tmem_u + as * 256;               // columns 0..127 HH, 128..255 HL
+      const uint32_t d_acc = tmem_u + as * 256;               // columns 0..L8-1 HH, L8..2*L8-1 HL
       for (int ch = 0; ch < nchunks; ++ch, ++ci) {
         const uint32_t u = ci % kStages;
         w_hl += mbar_wait_parked(&lo_full[u], (ci / kStages) & 1u, dbg, 731);
         tcgen05_fence_after();
-        // raw and lo tiles are adjacent: as a 256-row K-major operand they are [hi; lo]
+        // the lo tile starts right behind the L8 live rows of the raw tile: as a 2 * L8-row K-major operand they are [hi; lo]
         const uint64_t hdesc = make_kmajor_sw128_desc(st_base + u * 2 * kChunkBytes);
         if (elect_one()) {
 #pragma unroll
