@@ -423,6 +423,13 @@ class DecideLeg:
             graph.close()
         stats["pass_ms_per_step"] = ev0.elapsed_time(ev1) / max(1, steps)    # the event-bracketed pass's own step time
         self.ctx.check_status()
+        # max over ranks, like every other multi-GPU time: the step is the slowest rank's, so K1 must be too
+        names = [k for k, v in stats.items() if isinstance(v, dict)]
+        means = [stats[k]["ms"] / stats[k]["launches"] if stats[k]["launches"] else 0.0 for k in names]
+        red = self.env.max_over_ranks(*means, stats["pass_ms_per_step"])
+        for k, m in zip(names, red[:-1]):
+            stats[k]["ms"] = m * stats[k]["launches"]
+        stats["pass_ms_per_step"] = red[-1]
         return stats
 
     def roofline(self, stats, step_ms, peaks, long_run, traffic=None, traffic_source=None):
