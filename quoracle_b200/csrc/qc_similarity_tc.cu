@@ -5,26 +5,34 @@
 //   * a tile is 128 consecutive rows of the [B*N x D] embedding matrix = floor(128/N) whole decisions (only
 //     those rows are fetched; the rest of the MMA tile is stale shared memory that reaches discarded
 //     accumulator entries only); TMA streams it in 32-column fp32 chunks (128 B rows, 128-byte swizzle)
-//     through a ring of 4 (pools > 32) or 5 stages, each stage = raw tile + lo tile, adjacent;
+//     through a ring of 10-11 stages of 16 KB;
 //   * kind::tf32 reads an fp32 operand by ignoring its 13 low mantissa bits, so the landed tile IS the "hi"
-//     operand; four splitter warps write only the exact remainder lo = x - trunc_tf32(x) next to it (same
-//     swizzled offsets) and publish it to the async proxy;
-//   * one elected lane issues tcgen05.mma kind::tf32, M = 128, N = 256 (B = [raw; lo]), K = 8:
-//     [HH | HL] += H [H; L]^T into a 256-column TMEM accumulator, double-buffered (512 columns).
-//     G = HH + (HL + HL^T) is 3xTF32 with the symmetric term taken from the transpose: fp32-accurate
-//     (<= 2e-6 from the f64 oracle even for inputs living in the dropped bits; the tolerance is 1e-3);
+//     operand H when it is read as B.  Eight splitter warps (two groups, alternate chunks) read each row once,
+//     split it into h = trunc_tf32(x) and the exact remainder l = x - h, and store both as A operands into
+//     TENSOR MEMORY (tcgen05.st; ring of 4 x 64 columns) -- nothing is written back to shared memory;
+//   * one elected lane issues, per K step of 8, two tcgen05.mma kind::tf32 M = 128, N = 128 with A from TMEM
+//     and B = the raw tile:  HH += H H^T  and  LH += L H^T  into two 128-column accumulators (256 TMEM columns;
+//     the other 256 hold the A ring, so the accumulators are single-buffered: the epilogue pulls them into
+//     registers and releases them before it does anything else).  Since HL = LH^T,
+//     G = HH + (LH + LH^T) is the 3xTF32 product: fp32-accurate (<= 2e-6 from the f64 oracle even for inputs
+//     living in the dropped bits; the tolerance is 1e-3);
 //   * four epilogue warps read the accumulator rows back with tcgen05.ld, keep only the columns of the
 //     row's own decision (the off-diagonal blocks of the 128 x 128 tile pair different decisions and are
 //     discarded), and finish reciprocal norms / cosine / row mean / reference verdict / medoid vote through
 //     shared memory; waiting roles park on mbarrier.try_wait with a suspend-time hint.
-// Per 16 KB chunk: 4 MMAs of 128x256x8 (512 tensor cycles) and 96 KB of shared-memory traffic (TMA 16, splitters
-// 32, MMA operands 48) -- shared-memory bandwidth is what bounds the kernel (profiles/k3_tc_full_r1_summary.md).
+// Per 16 KB chunk: 8 MMAs of 128x128x8 (512 tensor cycles) and 64 KB of shared-memory traffic (TMA 16, splitters
+// 16, MMA B operands 32).  Rounds 1-2 used A = H from shared memory and B = [H; L] stacked, with the lo tile written
+// back to shared memory (96 KB per chunk): 0.71-0.74 of the HBM peak where this one gives 0.75-0.78 on the same box
+// (profiles/k3_full_r2_summary.md has the comparison and the ablations that locate what is left).
 //
 // Cosine and verdict definitions are those of qc_similarity.cu (reference
 // lib/quoracle/actions/consensus_rules.ex:189-210,277-286; medoid: SURVEY.md section 8(a) row A13).
 #include "qc_common.cuh"
 #include "ptx.cuh"
 
+#ifndef QC_TC_ABLATE
+#define QC_TC_ABLATE 0      // timing experiments only (wrong results): 1 = no L MMAs, 2 = splitters skip the row reads
+#endif
 #ifndef QC_TC_SPLIT_GROUPS
 #define QC_TC_SPLIT_GROUPS 2
 #endif
@@ -39,20 +47,23 @@ constexpr int kSplitGroups = QC_TC_SPLIT_GROUPS;   // splitter groups of 4 warps
 constexpr int kSplitWarps = 4 * kSplitGroups;
 constexpr int kTcThreads = (4 + kSplitWarps + 2) * 32;   // epilogue, splitters, TMA producer, MMA issuer
 constexpr int kChunkBytes = 128 * 128;       // 128 rows x 32 fp32
-// Shared memory: alignment slack, kStages x (raw 16 KB + lo 16 KB), two [128][kWin] fp32 windows, norms and row
-// means, barriers; five stages for every pool size (the widest windows only just fit, see kTail).
+constexpr int kTmemStages = 4;               // ring of (h, 2l) A operands in TMEM, 64 columns each, behind the accumulators
+constexpr int kAccCols = 128;                // HH in columns 0..127, LH in 128..255, then the A ring at column 256
+static_assert(kTmemStages % kSplitGroups == 0, "a TMEM stage must always belong to the same splitter group");
+// Shared memory: alignment slack, kStages x 16 KB raw tiles, two [128 (+ tail)][kWin] fp32 windows (HH, LH), norms
+// and row means, barriers.
 // The epilogue reads up to 7 entries past a decision's last column / row (blocks of 8, results discarded); those
 // reads must land in memory nobody writes, so each array they can run off carries its own tail: 7 extra window rows
-// after the HL window, 16 extra entries after the norms and after the row means.
+// after the LH window, 16 extra entries after the norms and after the row means.
 constexpr int kVecLen = 144;                 // 128 + over-read tail
-// kTail = 7: the HL window carries seven never-written rows for the transposed over-reads.  kTail = 0 (pools of
-// 49..64, where five stages and 65-column windows fill the 227 KB to the last few hundred bytes): those reads are
+// kTail = 7: the LH window carries seven never-written rows for the transposed over-reads.  kTail = 0 (pools of
+// 49..64, where ten stages and 65-column windows fill the 227 KB to the last few dozen bytes): those reads are
 // clamped to the decision's last row instead, and the alignment slack is 512 bytes -- the dynamic shared window of a
 // kernel without static shared memory starts 1 KB into the SM's shared memory, i.e. already 1024-aligned; the
 // kernel checks and bails out through the watchdog record if that ever stops being true.
 __host__ __device__ constexpr int tc_slack(int tail) { return tail == 0 ? 512 : 1024; }
 constexpr int tc_smem_bytes(int stages, int win, int tail) {
-  return tc_slack(tail) + stages * 2 * kChunkBytes + (2 * 128 + tail) * win * 4 + 2 * kVecLen * 4 + 8 + 256;
+  return tc_slack(tail) + stages * kChunkBytes + (2 * 128 + tail) * win * 4 + 2 * kVecLen * 4 + 8 + 320;
 }
 
 // kind::tf32, fp32 accumulate, both operands K-major: c_format=1 (bit 4), a/b_format=2 (bits 7, 10), N>>3, M>>4
@@ -60,15 +71,16 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] B[smem]^T: the A operand is 128 lanes x 8 columns of 32-bit values at tmem_a
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -98,17 +110,18 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
     return;
   }
   uint8_t* smem = smem_raw + misalign;                        // pointer arithmetic keeps the shared address space
-  uint8_t* stages = smem;                                     // kStages x (raw 16 KB, lo 16 KB)
-  float* whh = reinterpret_cast<float*>(stages + kStages * 2 * kChunkBytes);   // [128][kWin] HH window
-  float* whl = whh + 128 * kWin;                                             // [128][kWin] HL window
-  float* diag = whl + (128 + kTail) * kWin;                                  // [128 + tail] reciprocal row norms
+  uint8_t* stages = smem;                                     // kStages raw tiles of 16 KB
+  float* whh = reinterpret_cast<float*>(stages + kStages * kChunkBytes);     // [128][kWin] HH window
+  float* wlh = whh + 128 * kWin;                                             // [128 + tail][kWin] LH window
+  float* diag = wlh + (128 + kTail) * kWin;                                  // [128 + tail] reciprocal row norms
   float* rmean = diag + kVecLen;                                             // [128 + tail] row means
   // ((256 + kTail) * kWin + 288) floats precede this point: an odd count leaves it 4-byte aligned, mbarriers need 8
   uint64_t* bars = reinterpret_cast<uint64_t*>(rmean + kVecLen + (((256 + kTail) * kWin) & 1));
   uint64_t* raw_full = bars;                                  // TMA landed the raw tile
-  uint64_t* lo_full = raw_full + kStages;                     // splitters wrote the lo tile
-  uint64_t* stage_empty = lo_full + kStages;                  // the MMAs that read the stage retired
-  uint64_t* acc_full = stage_empty + kStages;
+  uint64_t* stage_empty = raw_full + kStages;                 // the MMAs that read the stage retired
+  uint64_t* a_full = stage_empty + kStages;                   // splitters stored (h, 2l) of a chunk into TMEM stage t
+  uint64_t* a_empty = a_full + kTmemStages;                   // the MMAs that read TMEM stage t retired
+  uint64_t* acc_full = a_empty + kTmemStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -117,35 +130,28 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
   const int q = 128 / N;                                      // whole decisions per tile
   const int ntiles = (B + q - 1) / q;
   const int nchunks = (D + 31) / 32;
-  // Live rows: a tile holds q * N <= 128 rows of data.  The lo tile is placed right behind them (rounded up to the
-  // 8-row swizzle atom, which keeps it 1024-byte aligned) and the stacked B operand is sized to what is there:
-  // UMMA N = 2 * L8 instead of 256.  Pools that do not divide 128 (48: 96 rows, 24 / 40: 120) then cost neither the
-  // MMA cycles nor the operand reads nor the splitter traffic of the rows they do not have.
-  const int L8 = (q * N + 7) & ~7;
+  // Live rows: a tile holds q * N <= 128 rows of data, and the B operand is sized to them: UMMA N = LN = q * N rounded
+  // up to 16 (the M = 128 shapes want N % 16 == 0).  Pools that do not divide 128 (48: 96 rows) then cost neither the MMA
+  // cycles nor the operand reads of the rows they do not have.
+  const int LN = (q * N + 15) & ~15;
 
   if (warp == 4 + kSplitWarps && lane == 0) {
     tma_prefetch_desc(&x_tmap);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&lo_full[s], 4);                  // one arrival per warp of the owning splitter group
       // tcgen05.commit of the MMAs that read the stage + one arrival per warp of every splitter group that does NOT own
       // the chunk, made after that warp has observed the chunk's raw_full phase: the producer cannot re-arm raw_full[s]
       // for chunk c + kStages before every waiter has seen chunk c's phase, so no waiter can ever find the barrier two
       // phases ahead of it (a parity wait cannot tell phase k from k - 2).  (The owning group needs no arrival of its
-      // own: its lo tile is read by the MMAs whose commit is the other arrival.)
-      //
-      // compute-sanitizer --tool racecheck reports the lo-tile stores below as write-after-write hazards between the
-      // two groups (with five stages and two groups, consecutive laps of a stage are written by different warps).
-      // The order between lap k's store and lap k + 1's is: store -> arrive(lo_full) -> MMA issue -> tcgen05.commit ->
-      // stage_empty -> TMA refill -> raw_full -> the other group's wait -> store; the tool follows thread arrivals but
-      // not tcgen05.commit / TMA completions, so it cannot see the chain (an experiment that added thread arrivals of
-      // the owners to stage_empty did not change its report; profiles/sanitizer_r2.md).
+      // own: the MMAs whose commit is the other arrival were issued after its a_full arrival, i.e. after its reads.)
       mbar_init(&stage_empty[s], 1 + 4 * (kSplitGroups - 1));
     }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);      // one arrival per epilogue warp
+    for (int t = 0; t < kTmemStages; ++t) {
+      mbar_init(&a_full[t], 4);                   // one arrival per warp of the owning splitter group
+      mbar_init(&a_empty[t], 1);                  // tcgen05.commit
     }
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_empty[0], 4);        // one arrival per epilogue warp
     fence_barrier_init();
   }
   __syncwarp();
@@ -169,44 +175,70 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
     const long long t_role = clock64();
     long long w_acc = 0, t_copy = 0, t_loop = 0, t_vote = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++acc_iter) {
-      const uint32_t as = acc_iter & 1u;
       const int b = tile * q + d;
       const bool live = row_live && b < B;
       const float th = live ? thr[b] : 0.f;                   // in flight while the tile's MMAs finish
-      w_acc += mbar_wait_parked(&acc_full[as], (acc_iter >> 1) & 1u, dbg, 700);
+      w_acc += mbar_wait_parked(&acc_full[0], acc_iter & 1u, dbg, 700);
       long long tp = clock64();
       tcgen05_fence_after();
       // accumulator rows -> shared windows (only the columns of the row's own decision; 32-column groups
-      // that no row of this warp needs are skipped warp-uniformly)
+      // that no row of this warp needs are skipped warp-uniformly).  The accumulators are single-buffered, so the
+      // next tile's MMAs wait for acc_empty: when the warp needs ONE column group (pools that divide 32, i.e. 16
+      // and 32, and whenever the warp's rows fall into one 32-column group) both halves are pulled into registers
+      // and the accumulator is released before the window is written.
       const int col_lo = ((warp * 32) / N) * N;
       const int col_hi = ((warp * 32 + 31) / N) * N + N;
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        float* dstw = (half == 0 ? whh : whl) + i * kWin - base;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          if (c0 + 32 <= col_lo || c0 >= col_hi) continue;
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + as * 256 + half * L8 + c0, v);
-          tmem_ld_wait();
-          if (row_live) {
+      const int g_first = col_lo >> 5, g_last = (col_hi - 1) >> 5;
+      if (g_first == g_last) {
+        const int c0 = g_first << 5;
+        uint32_t vh[32], vl[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + c0, vh);
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + LN + c0, vl);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[0]);
+        if (row_live) {
+          float* dh = whh + i * kWin - base;
+          float* dl = wlh + i * kWin - base;
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const int c = c0 + k - base;
-              if (c >= 0 && c < N) dstw[c0 + k] = __uint_as_float(v[k]);
+          for (int k = 0; k < 32; ++k) {
+            const int c = c0 + k - base;
+            if (c >= 0 && c < N) {
+              dh[c0 + k] = __uint_as_float(vh[k]);
+              dl[c0 + k] = __uint_as_float(vl[k]);
             }
           }
         }
+      } else {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          float* dstw = (half == 0 ? whh : wlh) + i * kWin - base;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            if (c0 + 32 <= col_lo || c0 >= col_hi) continue;
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + half * LN + c0, v);
+            tmem_ld_wait();
+            if (row_live) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                const int c = c0 + k - base;
+                if (c >= 0 && c < N) dstw[c0 + k] = __uint_as_float(v[k]);
+              }
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[0]);
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
       named_bar_sync(1, 128);
       t_copy += clock64() - tp; tp = clock64();
-      // Gram diagonal G_ii = HH_ii + 2 HL_ii -> reciprocal row norm (0 for a zero row: its cosines are 0,
+      // Gram diagonal G_ii = HH_ii + 2 LH_ii -> reciprocal row norm (0 for a zero row: its cosines are 0,
       // reference consensus_rules.ex:205-209)
       if (row_live) {
-        const float nrm2 = (whl[i * kWin + r] + whl[i * kWin + r]) + whh[i * kWin + r];
+        const float nrm2 = (wlh[i * kWin + r] + wlh[i * kWin + r]) + whh[i * kWin + r];
         diag[i] = nrm2 > 0.f ? rsqrtf(nrm2) : 0.f;
       }
       named_bar_sync(1, 128);
@@ -214,14 +246,14 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
       if (live) {
         const float ni = diag[i];
         float s = 0.f;
-        // G_rj = HH_rj + (HL_rj + HL_jr).  HH = H H^T comes out of the tensor core bitwise symmetric (exact
+        // G_rj = HH_rj + (LH_rj + LH_jr).  HH = H H^T comes out of the tensor core bitwise symmetric (exact
         // tf32 products, same k order for (r, j) and (j, r)), and the bracket is symmetric by commutativity, so
         // cos(r, j) == cos(j, r) exactly (asserted in tests/test_gpu_similarity.py).
         const float* hh_row = whh + i * kWin;
-        const float* hl_row = whl + i * kWin;
-        const float* hl_col = whl + base * kWin + r;
+        const float* lh_row = wlh + i * kWin;
+        const float* lh_col = wlh + base * kWin + r;
         const float* nrm = diag + base;                       // reciprocal norms
-        // cos(r, j) == cos(j, r) bitwise (below), so row r's values are stored down column r of the output:
+        // cos(r, j) == cos(j, r) bitwise, so row r's values are stored down column r of the output:
         // consecutive lanes (consecutive r) then write consecutive addresses
         float* cos_col = cos != nullptr ? cos + static_cast<size_t>(b) * N * N + r : nullptr;
         // Blocks of 8 columns, all loads of a block issued before use (shared memory is kept busy by the MMA
@@ -232,9 +264,9 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             up[k] = hh_row[j0 + k];
-            lr[k] = hl_row[j0 + k];
+            lr[k] = lh_row[j0 + k];
             // without tail rows the transposed read is clamped to the decision's last row (result discarded)
-            lc[k] = hl_col[(kTail == 0 ? (j0 + k < N ? j0 + k : N - 1) : j0 + k) * kWin];
+            lc[k] = lh_col[(kTail == 0 ? (j0 + k < N ? j0 + k : N - 1) : j0 + k) * kWin];
             nj[k] = nrm[j0 + k];
           }
           // branch-free so the eight dependency chains interleave
@@ -270,8 +302,8 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
         if (ref_ok) ref_ok[b] = ok;
         if (medoid) medoid[b] = best;
       }
-      named_bar_sync(1, 128);                                 // windows are reused by the next tile
-      t_vote += clock64() - tp; 
+      named_bar_sync(1, 128);                                 // the windows are reused by the next tile
+      t_vote += clock64() - tp;
     }
     if (stall != nullptr && threadIdx.x == 0) {
       stall[blockIdx.x * 16 + 4] = clock64() - t_role;
@@ -281,19 +313,21 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
       stall[blockIdx.x * 16 + 13] = t_vote;
     }
   } else if (warp < 4 + kSplitWarps) {
-    // ===================== splitters: raw fp32 chunk -> lo tile (the raw tile is the hi operand) =====
-    const int p = (threadIdx.x - 128) & 127;                  // position inside the group
+    // ===================== splitters: raw fp32 row -> (h, l) A operands in TMEM =======================
+    const int p = (threadIdx.x - 128) & 127;                  // position inside the group == tile row == TMEM lane
     const int grp = (warp - 4) >> 2;
+    const uint32_t lane_addr = static_cast<uint32_t>((p >> 5) * 32) << 16;   // the warp's own TMEM lane quadrant
+    const bool row_live = p < q * N;
     const long long t_role = clock64();
-    long long w_raw = 0;
+    long long w_raw = 0, w_tmem = 0, t_ld = 0, t_st = 0;
     uint32_t ci = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int ch = 0; ch < nchunks; ++ch, ++ci) {
         const uint32_t s = ci % kStages;
         // Every group observes EVERY phase of raw_full, its own chunks or not: an mbarrier parity wait cannot tell
         // phase k from phase k - 2, so a group that skipped the chunks of the other groups could ask for phase k of a
-        // stage whose phase k - 1 (another group's chunk, five chunks earlier) has not landed yet -- TMA completions
-        // are not ordered -- and be let through on stale data.  Observing all phases keeps every waiter within one
+        // stage whose phase k - 1 (another group's chunk) has not landed yet -- TMA completions are not ordered --
+        // and be let through on stale data.  Observing all phases keeps every waiter within one
         // phase of the barrier; and it cannot fall two behind, because a non-owning warp's observation is itself one
         // of the arrivals the producer needs (stage_empty) before it refills the stage.
         w_raw += mbar_wait_parked(&raw_full[s], (ci / kStages) & 1u, dbg, 710);
@@ -302,33 +336,51 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
           if (lane == 0) mbar_arrive(&stage_empty[s]);        // "this warp has seen the phase" (see stage_empty's init)
           continue;
         }
-        const float4* src = reinterpret_cast<const float4*>(stages + s * 2 * kChunkBytes);
-        float4* dl = reinterpret_cast<float4*>(stages + s * 2 * kChunkBytes + L8 * 128);   // lo tile behind the live rows
-        // L8 * 8 16-byte pieces (1024 for a full tile), consecutive per warp; all loads first so their latencies overlap
-        const int npieces = L8 * 8;
-        float4 x[8];
+        // Thread p reads its row's 32 values (eight 16-byte pieces at their swizzled places: consecutive rows hit
+        // different banks) and splits each into h = what kind::tf32 will see of it and the exact remainder l, the two
+        // A operands of the chunk.  The tensor core drops l's own low bits the same way: 2^-20 relative.
+        const uint32_t t = ci % kTmemStages;
+        const long long c0 = clock64();
+        const uint8_t* row = stages + s * kChunkBytes + p * 128;
+        uint32_t hi[32], lo[32];
+        if (row_live && !(QC_TC_ABLATE & 2)) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it)
-          if (it * 128 + p < npieces) x[it] = src[it * 128 + p];
+          for (int j = 0; j < 8; ++j) {
+            const float4 x = *reinterpret_cast<const float4*>(row + ((j ^ (p & 7)) << 4));
+            const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          // the tensor core reads the raw tile as TF32 by ignoring the 13 low mantissa bits; lo is the exact
-          // fp32 remainder of that truncation (its own low bits are dropped the same way: 2^-20 relative)
-          if (it * 128 + p < npieces) {
-            float4 l;
-            l.x = x[it].x - tf32_trunc(x[it].x); l.y = x[it].y - tf32_trunc(x[it].y);
-            l.z = x[it].z - tf32_trunc(x[it].z); l.w = x[it].w - tf32_trunc(x[it].w);
-            dl[it * 128 + p] = l;
+            for (int e = 0; e < 4; ++e) {
+              const float h = tf32_trunc(xs[e]);
+              hi[4 * j + e] = __float_as_uint(h);
+              lo[4 * j + e] = __float_as_uint(xs[e] - h);
+            }
           }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) hi[e] = lo[e] = 0u;     // rows the tile does not have: accumulator rows nobody reads
         }
-        fence_proxy_async_smem();
+        const long long c1 = clock64();
+        // the row is in registers before the TMEM stage is asked for: only the stores are behind the MMAs
+        w_tmem += mbar_wait_parked(&a_empty[t], ((ci / kTmemStages) & 1u) ^ 1u, dbg, 711);
+        tcgen05_fence_after();
+        const long long c2 = clock64();
+        const uint32_t ta = tmem_base + lane_addr + 2 * kAccCols + t * 64u;
+        tmem_st_32x32b_x32(ta, hi);
+        tmem_st_32x32b_x32(ta + 32u, lo);
+        tmem_st_wait();
+        tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&lo_full[s]);
+        if (lane == 0) mbar_arrive(&a_full[t]);
+        t_ld += c1 - c0;
+        t_st += clock64() - c2;
       }
     }
     if (stall != nullptr && threadIdx.x == 128) {
       stall[blockIdx.x * 16 + 6] = clock64() - t_role;
       stall[blockIdx.x * 16 + 7] = w_raw;
+      stall[blockIdx.x * 16 + 10] = w_tmem;
+      stall[blockIdx.x * 16 + 14] = t_ld;
+      stall[blockIdx.x * 16 + 15] = t_st;
     }
   } else if (warp == 4 + kSplitWarps) {
     // ===================== TMA producer (warp-convergent, elected issue) =====================
@@ -342,7 +394,7 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
         w_free += mbar_wait_parked(&stage_empty[s], ((ci / kStages) & 1u) ^ 1u, dbg, 720);
         if (elect_one()) {
           mbar_expect_tx(&raw_full[s], static_cast<uint32_t>(q * N) * 128u);
-          tma_load_2d(stages + s * 2 * kChunkBytes, &x_tmap, &raw_full[s], ch * 32, row0);
+          tma_load_2d(stages + s * kChunkBytes, &x_tmap, &raw_full[s], ch * 32, row0);
         }
         __syncwarp();
       }
@@ -353,36 +405,41 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
     }
   } else {
     // ===================== MMA issuer ==========================================================
-    const uint32_t idesc = make_idesc_tf32(128, 2u * static_cast<uint32_t>(L8));   // B = [hi; lo] stacked: D = [HH | HL]
+    const uint32_t idesc = make_idesc_tf32(128, static_cast<uint32_t>(LN));
     const uint32_t st_base = smem_u32(stages);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     uint32_t ci = 0, acc_iter = 0;
     const long long t_role = clock64();
-    long long w_hl = 0, w_acc = 0;
+    long long w_a = 0, w_acc = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++acc_iter) {
-      const uint32_t as = acc_iter & 1u;
-      w_acc += mbar_wait_parked(&acc_empty[as], ((acc_iter >> 1) & 1u) ^ 1u, dbg, 730);
+      w_acc += mbar_wait_parked(&acc_empty[0], (acc_iter & 1u) ^ 1u, dbg, 730);
       tcgen05_fence_after();
-      const uint32_t d_acc = tmem_u + as * 256;               // columns 0..L8-1 HH, L8..2*L8-1 HL
+      const uint32_t d_acc = tmem_u;                          // HH at column 0, LH at column LN
       for (int ch = 0; ch < nchunks; ++ch, ++ci) {
         const uint32_t u = ci % kStages;
-        w_hl += mbar_wait_parked(&lo_full[u], (ci / kStages) & 1u, dbg, 731);
+        const uint32_t t = ci % kTmemStages;
+        // The splitters' arrival follows their own wait on raw_full[u], so the raw tile (the B operand) has landed.
+        w_a += mbar_wait_parked(&a_full[t], (ci / kTmemStages) & 1u, dbg, 731);
         tcgen05_fence_after();
-        // the lo tile starts right behind the L8 live rows of the raw tile: as a 2 * L8-row K-major operand they are [hi; lo]
-        const uint64_t hdesc = make_kmajor_sw128_desc(st_base + u * 2 * kChunkBytes);
+        const uint64_t bdesc = make_kmajor_sw128_desc(st_base + u * kChunkBytes);
         if (elect_one()) {
+          const uint32_t a_h = tmem_u + 2 * kAccCols + t * 64u;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)                         // 8 fp32 (32 bytes) per K step
-            umma_tf32(d_acc, hdesc + 2 * k, hdesc + 2 * k, idesc, (ch | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {                       // 8 fp32 per K step: 8 TMEM columns of A, 32 bytes of B
+            umma_tf32_ts(d_acc, a_h + 8 * k, bdesc + 2 * k, idesc, (ch | k) != 0 ? 1u : 0u);             // HH (+)= H H^T
+            if (!(QC_TC_ABLATE & 1))
+              umma_tf32_ts(d_acc + LN, a_h + 32 + 8 * k, bdesc + 2 * k, idesc, (ch | k) != 0 ? 1u : 0u);   // LH (+)= L H^T
+          }
           umma_commit<1>(&stage_empty[u]);
-          if (ch == nchunks - 1) umma_commit<1>(&acc_full[as]);
+          umma_commit<1>(&a_empty[t]);
+          if (ch == nchunks - 1) umma_commit<1>(&acc_full[0]);
         }
         __syncwarp();
       }
     }
     if (stall != nullptr && lane == 0) {
       stall[blockIdx.x * 16 + 0] = clock64() - t_role;
-      stall[blockIdx.x * 16 + 1] = w_hl;
+      stall[blockIdx.x * 16 + 1] = w_a;
       stall[blockIdx.x * 16 + 3] = w_acc;
     }
   }
@@ -405,25 +462,30 @@ static cudaError_t launch_tc(const CUtensorMap* x_tmap, int B, int N, int D, con
   const int q = 128 / N;
   const int ntiles = (B + q - 1) / q;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  return launch_kernel(qc_sim_tc_kernel<kStages, kWin, kTail>, dim3(grid), dim3(kTcThreads), smem, stream, pdl, *x_tmap, B, N, D, thr,
-                       ref_ok, medoid, cos, dbg, stall);
+  return launch_kernel(qc_sim_tc_kernel<kStages, kWin, kTail>, dim3(grid), dim3(kTcThreads), smem, stream, pdl, *x_tmap, B, N, D,
+                       thr, ref_ok, medoid, cos, dbg, stall);
 }
 
-// Shared-memory opt-in of the three instantiations on the current device (called by qc_ctx_create).
+// Instantiations <stages, window, tail>: pools <= 32, <= 48, <= 64 (the windows grow with the pool, the ring shrinks).
+#define QC_TC_VARIANTS(X) X(11, 33, 7) X(10, 49, 7) X(10, 65, 0)
+
+// Shared-memory opt-in of the instantiations on the current device (called by qc_ctx_create).
 cudaError_t similarity_tc_prepare_device() {
-  cudaError_t e = cudaFuncSetAttribute(qc_sim_tc_kernel<5, 33, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(5, 33, 7));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(qc_sim_tc_kernel<5, 49, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(5, 49, 7));
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(qc_sim_tc_kernel<5, 65, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(5, 65, 0));
+  cudaError_t e = cudaSuccess;
+#define X(S, W, T)         \
+  if (e == cudaSuccess)    \
+    e = cudaFuncSetAttribute(qc_sim_tc_kernel<S, W, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(S, W, T));
+  QC_TC_VARIANTS(X)
+#undef X
+  return e;
 }
 
 cudaError_t launch_similarity_tc(const CUtensorMap* x_tmap, int B, int N, int D, const float* thr, int32_t* ref_ok,
                                  int32_t* medoid, float* cos, int32_t* dbg, unsigned long long* stall, int num_sms,
                                  cudaStream_t stream, bool pdl) {
-  if (N <= 32) return launch_tc<5, 33, 7>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream, pdl);
-  if (N <= 48) return launch_tc<5, 49, 7>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream, pdl);
-  return launch_tc<5, 65, 0>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream, pdl);
+  if (N <= 32) return launch_tc<11, 33, 7>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream, pdl);
+  if (N <= 48) return launch_tc<10, 49, 7>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream, pdl);
+  return launch_tc<10, 65, 0>(x_tmap, B, N, D, thr, ref_ok, medoid, cos, dbg, stall, num_sms, stream, pdl);
 }
 
 }  // namespace qc

@@ -471,7 +471,7 @@ class Context:
         return {"cta_group": cg.value, "token_block": tb.value, "w_stages": ws.value, "w_multicast_pairs": self.multicast()}
 
     STALL_FIELDS = ("mma_total", "mma_wait_w", "mma_wait_tokens", "mma_wait_acc", "epi_total", "epi_wait_acc",
-                    "gather_total", "gather_wait_free", "wprod_total", "wprod_wait_free", "gather_wait_loads", "mma_issue", "mma_commit", "gather_fence")
+                    "gather_total", "gather_wait_free", "wprod_total", "wprod_wait_free", "gather_wait_loads", "mma_issue", "mma_commit", "gather_fence", "aux14", "aux15")
 
     def stall_profile(self, enable: bool = True, read: bool = False):
         """K1 tuning aid: per-role barrier stall cycles of the last encoder launch (averaged over CTAs)."""

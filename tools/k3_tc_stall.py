@@ -29,12 +29,13 @@ def main():
         st = ctx.stall_profile(True, read=True)
         chunks = ((b + 128 // n - 1) // (128 // n)) * ((d + 31) // 32) / 148
         print(f"N={n} D={d} B={b} cos={with_cos}: chunks/CTA {chunks:.0f}")
-        names = {"mma_total": "mma total", "mma_wait_w": "mma wait hi/lo", "mma_wait_acc": "mma wait acc free",
+        names = {"mma_total": "mma total", "mma_wait_w": "mma wait A operands", "mma_wait_acc": "mma wait acc free",
                  "epi_total": "epilogue total", "epi_wait_acc": "epilogue wait acc",
                  "gather_total": "splitter total", "gather_wait_free": "splitter wait raw",
-                 "gather_wait_loads": "splitter wait hi/lo free", "wprod_total": "producer total",
+                 "gather_wait_loads": "splitter wait tmem stage free", "wprod_total": "producer total",
                  "wprod_wait_free": "producer wait raw free",
-                 "mma_issue": "epilogue tmem->windows", "mma_commit": "epilogue cosine loop", "gather_fence": "epilogue vote"}
+                 "mma_issue": "epilogue tmem->windows", "mma_commit": "epilogue cosine loop", "gather_fence": "epilogue vote",
+                 "aux14": "splitter row load + split", "aux15": "splitter tmem store"}
         st = dict(st)
         for k, label in names.items():
             print(f"  {label:26s} {st[k]:12.0f}  ({st[k] / chunks:8.1f} per chunk)")
