@@ -1,5 +1,5 @@
 """Instruction census of libqconsensus.so per kernel (cuobjdump -sass): the evidence that the hot path is hand-written
-Blackwell code -- tcgen05 MMAs (UTCHMMA / UTCQMMA...), TMEM loads (LDTM), TMA (UTMALDG, incl. GATHER4 / MULTICAST / 2CTA),
+Blackwell code -- tcgen05 MMAs (UTCHMMA / UTCQMMA...), TMEM loads / stores (LDTM / STTM), TMA (UTMALDG, incl. GATHER4 / MULTICAST / 2CTA),
 tcgen05.commit (UTCBAR), mbarrier traffic (SYNCS), legacy mma.sync (HMMA / IMMA) -- written as a markdown table.
 
   python tools/sass_census.py > profiles/sass_census_r2.md      (needs no GPU)"""
@@ -12,7 +12,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "quoracle_b200" / "lib" / "libqconsensus.so"
 COLS = OrderedDict([
-    ("UTCHMMA", r"\bUTCHMMA"), ("…2CTA", r"\bUTCHMMA\S*\.2CTA"), ("UTCBAR", r"\bUTCBAR"), ("LDTM", r"\bLDTM"),
+    ("UTCHMMA", r"\bUTCHMMA"), ("…2CTA", r"\bUTCHMMA\S*\.2CTA"), ("UTCBAR", r"\bUTCBAR"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"),
     ("UTMALDG", r"\bUTMALDG"), ("…GATHER4", r"\bUTMALDG\S*GATHER4"), ("…MULTICAST", r"\bUTMALDG\S*MULTICAST"),
     ("SYNCS", r"\bSYNCS"), ("LDGSTS", r"\bLDGSTS"), ("HMMA (mma.sync)", r"\bHMMA"), ("MUFU.TANH", r"\bMUFU\.TANH"),
     ("ACQBULK/PDL", r"\bACQBULK|\bPREEXIT"),
