@@ -124,11 +124,12 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "memory");
   return ok != 0;
 }
+template <uint32_t kHintNs = 20000u>
 __device__ __forceinline__ long long mbar_wait_parked(uint64_t* bar, uint32_t parity, int32_t* dbg, int tag) {
   const long long t0 = clock64();
   uint32_t spins = 0;
-  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
-    if ((++spins & 7u) == 0 && hang_check(dbg, t0, tag)) break;
+  while (!mbar_try_wait_hint(bar, parity, kHintNs)) {
+    if ((++spins & (kHintNs >= 4000u ? 7u : 127u)) == 0 && hang_check(dbg, t0, tag)) break;
   }
   return clock64() - t0;
 }

@@ -19,7 +19,9 @@
 //   * four epilogue warps read the accumulator rows back with tcgen05.ld, keep only the columns of the
 //     row's own decision (the off-diagonal blocks of the 128 x 128 tile pair different decisions and are
 //     discarded), and finish reciprocal norms / cosine / row mean / reference verdict / medoid vote through
-//     shared memory; waiting roles park on mbarrier.try_wait with a suspend-time hint.
+//     shared memory.  Every role polls its barriers with plain mbarrier.try_wait: the roles hand chunks to each other
+//     through a 4-stage TMEM ring, so the wake-up latency of a parked wait (try_wait with a suspend-time hint, which
+//     the stacked-B kernel of rounds 1-2 preferred) is on the critical path here -- 670 against 720 cycles per chunk.
 // Per 16 KB chunk: 8 MMAs of 128x128x8 (512 tensor cycles) and 64 KB of shared-memory traffic (TMA 16, splitters
 // 16, MMA B operands 32).  Rounds 1-2 used A = H from shared memory and B = [H; L] stacked, with the lo tile written
 // back to shared memory (96 KB per chunk): 0.71-0.74 of the HBM peak where this one gives 0.75-0.78 on the same box
@@ -178,7 +180,7 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
       const int b = tile * q + d;
       const bool live = row_live && b < B;
       const float th = live ? thr[b] : 0.f;                   // in flight while the tile's MMAs finish
-      w_acc += mbar_wait_parked(&acc_full[0], acc_iter & 1u, dbg, 700);
+      w_acc += mbar_wait(&acc_full[0], acc_iter & 1u, dbg, 700);
       long long tp = clock64();
       tcgen05_fence_after();
       // accumulator rows -> shared windows (only the columns of the row's own decision; 32-column groups
@@ -330,7 +332,7 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
         // and be let through on stale data.  Observing all phases keeps every waiter within one
         // phase of the barrier; and it cannot fall two behind, because a non-owning warp's observation is itself one
         // of the arrivals the producer needs (stage_empty) before it refills the stage.
-        w_raw += mbar_wait_parked(&raw_full[s], (ci / kStages) & 1u, dbg, 710);
+        w_raw += mbar_wait(&raw_full[s], (ci / kStages) & 1u, dbg, 710);
         if (static_cast<int>(ci % kSplitGroups) != grp) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&stage_empty[s]);        // "this warp has seen the phase" (see stage_empty's init)
@@ -361,7 +363,7 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
         }
         const long long c1 = clock64();
         // the row is in registers before the TMEM stage is asked for: only the stores are behind the MMAs
-        w_tmem += mbar_wait_parked(&a_empty[t], ((ci / kTmemStages) & 1u) ^ 1u, dbg, 711);
+        w_tmem += mbar_wait(&a_empty[t], ((ci / kTmemStages) & 1u) ^ 1u, dbg, 711);
         tcgen05_fence_after();
         const long long c2 = clock64();
         const uint32_t ta = tmem_base + lane_addr + 2 * kAccCols + t * 64u;
@@ -391,7 +393,7 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
       const int row0 = tile * q * N;
       for (int ch = 0; ch < nchunks; ++ch, ++ci) {
         const uint32_t s = ci % kStages;
-        w_free += mbar_wait_parked(&stage_empty[s], ((ci / kStages) & 1u) ^ 1u, dbg, 720);
+        w_free += mbar_wait(&stage_empty[s], ((ci / kStages) & 1u) ^ 1u, dbg, 720);
         if (elect_one()) {
           mbar_expect_tx(&raw_full[s], static_cast<uint32_t>(q * N) * 128u);
           tma_load_2d(stages + s * kChunkBytes, &x_tmap, &raw_full[s], ch * 32, row0);
@@ -412,14 +414,14 @@ qc_sim_tc_kernel(const __grid_constant__ CUtensorMap x_tmap,   // emb as [B*N ro
     const long long t_role = clock64();
     long long w_a = 0, w_acc = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++acc_iter) {
-      w_acc += mbar_wait_parked(&acc_empty[0], (acc_iter & 1u) ^ 1u, dbg, 730);
+      w_acc += mbar_wait(&acc_empty[0], (acc_iter & 1u) ^ 1u, dbg, 730);
       tcgen05_fence_after();
       const uint32_t d_acc = tmem_u;                          // HH at column 0, LH at column LN
       for (int ch = 0; ch < nchunks; ++ch, ++ci) {
         const uint32_t u = ci % kStages;
         const uint32_t t = ci % kTmemStages;
         // The splitters' arrival follows their own wait on raw_full[u], so the raw tile (the B operand) has landed.
-        w_a += mbar_wait_parked(&a_full[t], (ci / kTmemStages) & 1u, dbg, 731);
+        w_a += mbar_wait(&a_full[t], (ci / kTmemStages) & 1u, dbg, 731);
         tcgen05_fence_after();
         const uint64_t bdesc = make_kmajor_sw128_desc(st_base + u * kChunkBytes);
         if (elect_one()) {
