@@ -528,12 +528,20 @@ def similarity_corner(env: Env, ctx, n: int, d: int, b: int, peaks):
     nbytes = 4 * n * d + 4 * n * n + 8
     gbs = b * nbytes / (ms * 1e-3) / 1e9
     s = min(256, b, base.shape[0])
+    traffic, traffic_source = None, None
+    tp = ROOT / "profiles" / "k1_traffic.json"            # static ncu numbers, labelled as such (never measured in this run)
+    if tp.exists():
+        tj = json.loads(tp.read_text()).get("k3_corners", {}).get(f"pool{n}_dim{d}_batch{b}")
+        if tj:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_source = "static: " + tj["source"] + " (NOT measured in this run)"
     rec = {"workload": f"config 5 corner: K3 only, pool {n}, dim {d}, batch {b}, embeddings resident in HBM "
                        f"({b * n * d * 4 / 1e6:.0f} MB), 256 MB L2 flush between iterations",
            "ms": ms, "value": b / (ms * 1e-3), "unit": UNIT,
            "roofline": {"bound": "hbm", "kernel": "qc_sim_small_kernel" if n <= 8 else "qc_sim_tc_kernel",
                         "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-                        "bytes_per_decision": nbytes, "traffic": None, "peak_kind": peaks["source"]}}
+                        "bytes_per_decision": nbytes, "algorithmic_bytes": b * nbytes, "traffic": traffic,
+                        "traffic_source": traffic_source, "peak_kind": peaks["source"]}}
     rec["index_mismatch_vs_gpu"] = parity_record(ok[:s].cpu().numpy(), med[:s].cpu().numpy(), base[:s], thr_h[:s],
                                                  oracle="numpy f64 reference rule + medoid on the same synthetic embeddings")
     return rec
