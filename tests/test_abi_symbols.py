@@ -79,6 +79,7 @@ def test_hot_kernels_are_blackwell_native_sass():
     if not Path(cuobjdump).exists():
         pytest.skip("cuobjdump not available")
     from quoracle_b200 import build
+    native.load_library()                                    # builds the library when it is not there yet
     sass = subprocess.run([cuobjdump, "-sass", str(build.LIB)], capture_output=True, text=True, check=True).stdout
     kernels, cur = {}, None
     for line in sass.splitlines():
