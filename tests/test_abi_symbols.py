@@ -79,7 +79,7 @@ def test_hot_kernels_are_blackwell_native_sass():
     if not Path(cuobjdump).exists():
         pytest.skip("cuobjdump not available")
     from quoracle_b200 import build
-    native.load_library()                                    # builds the library when it is not there yet
+    native.load_library()                                    # fails loudly, like every other test, when the library was not built
     sass = subprocess.run([cuobjdump, "-sass", str(build.LIB)], capture_output=True, text=True, check=True).stdout
     kernels, cur = {}, None
     for line in sass.splitlines():
