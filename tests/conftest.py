@@ -13,6 +13,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_sessionstart(session):
+    """A checkout without the built library (the .so files are git-ignored) compiles it once, with nvcc, before the
+    first test -- the same call __graft_entry__.build() makes.  Nothing here replaces the GPU path: without nvcc the
+    build raises and every test that needs the library fails loudly."""
+    from quoracle_b200 import build
+    if not build.LIB.exists():
+        build.build()
+
+
 def _have_gpu() -> bool:
     try:
         import torch
