@@ -112,6 +112,26 @@ def test_large_pools_many_tiles(ctx, n, b):
         ctx.set_similarity_path(0)
 
 
+def test_tcgen05_random_geometry_sweep(ctx):
+    """Forty seeded draws of (pool, batch, dim) through the tcgen05 kernel: every pool size class (tiles of 126 / 128 /
+    120 / 96 / 100 ... live rows, one to fourteen decisions per tile), batches that end inside a tile, dims whose last
+    32-column chunk is partial -- each against the f64 oracle with the margin accounting
+    of the other random-input tests."""
+    rng = np.random.default_rng(20260921)
+    ctx.set_similarity_path(2)
+    try:
+        for case in range(40):
+            n = int(rng.integers(9, 65))
+            d = 4 * int(rng.integers(8, 200))                    # the TMA path wants whole 16-byte pieces per row
+            q = 128 // n
+            b = int(rng.integers(1, 6)) * q * int(rng.integers(1, 40)) + int(rng.integers(0, q))   # ragged last tile
+            emb = _emb(b, n, d, synth.BASE_SEED + 1000 * case + n)
+            thr = np.resize(np.array([0.15, 0.45, 0.8], np.float32), b)
+            _check(ctx, emb, thr, max_rejected_frac=0.05)
+    finally:
+        ctx.set_similarity_path(0)
+
+
 def test_large_pool_paths_agree_and_are_batch_independent(ctx):
     rng = np.random.default_rng(9)
     emb = (rng.standard_normal((500, 20, 256)) * rng.uniform(0.01, 30.0, (500, 20, 1))).astype(np.float32)
