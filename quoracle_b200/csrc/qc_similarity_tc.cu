@@ -24,8 +24,9 @@
 //     the stacked-B kernel of rounds 1-2 preferred) is on the critical path here -- 670 against 720 cycles per chunk.
 // Per 16 KB chunk: 8 MMAs of 128x128x8 (512 tensor cycles) and 64 KB of shared-memory traffic (TMA 16, splitters
 // 16, MMA B operands 32).  Rounds 1-2 used A = H from shared memory and B = [H; L] stacked, with the lo tile written
-// back to shared memory (96 KB per chunk): 0.71-0.74 of the HBM peak where this one gives 0.75-0.78 on the same box
-// (profiles/k3_full_r2_summary.md has the comparison and the ablations that locate what is left).
+// back to shared memory (96 KB per chunk): 0.71-0.74 of the HBM peak where this one gives 0.78-0.81
+// (profiles/k3_tc_tmem_a_r2.md has the same-box comparisons, the ablations that locate what is left -- the splitters' LDS
+// against the asynchronous proxy -- and the formulations that were tried and dropped).
 //
 // Cosine and verdict definitions are those of qc_similarity.cu (reference
 // lib/quoracle/actions/consensus_rules.ex:189-210,277-286; medoid: SURVEY.md section 8(a) row A13).
@@ -49,7 +50,7 @@ constexpr int kSplitGroups = QC_TC_SPLIT_GROUPS;   // splitter groups of 4 warps
 constexpr int kSplitWarps = 4 * kSplitGroups;
 constexpr int kTcThreads = (4 + kSplitWarps + 2) * 32;   // epilogue, splitters, TMA producer, MMA issuer
 constexpr int kChunkBytes = 128 * 128;       // 128 rows x 32 fp32
-constexpr int kTmemStages = 4;               // ring of (h, 2l) A operands in TMEM, 64 columns each, behind the accumulators
+constexpr int kTmemStages = 4;               // ring of (h, l) A operands in TMEM, 64 columns each, behind the accumulators
 constexpr int kAccCols = 128;                // HH in columns 0..127, LH in 128..255, then the A ring at column 256
 static_assert(kTmemStages % kSplitGroups == 0, "a TMEM stage must always belong to the same splitter group");
 // Shared memory: alignment slack, kStages x 16 KB raw tiles, two [128 (+ tail)][kWin] fp32 windows (HH, LH), norms
